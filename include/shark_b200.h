@@ -1,0 +1,188 @@
+/*
+ * shark_b200.h - C ABI of the B200-native implementation of Shark's k-mer Bloom-filter
+ * hot path (index build -> probe + rank -> per-read classification).
+ *
+ * The reference (AlgoLab/shark) has no plugin/FFI interface: its stages are C++ functors wired
+ * together in main.cpp.  Each entry point below names the reference interface it replaces
+ * (file:line relative to the reference tree).  Plain pointers and sizes only; no exceptions
+ * cross this boundary.  Every function returns SHK_OK (0) or a negative shk_status;
+ * shk_last_error() gives the message.  There is NO CPU fallback: without a CUDA device every
+ * compute call fails with SHK_E_CUDA.
+ *
+ * Threading: a context belongs to one CUDA device.  Calls on the same context must be
+ * serialised by the caller, except that slots are independent: one host thread may submit to
+ * slot 0 while another collects slot 1.
+ */
+#ifndef SHARK_B200_H
+#define SHARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHK_ABI_VERSION 1
+
+typedef enum shk_status {
+    SHK_OK = 0,
+    SHK_E_ARG = -1,      /* invalid argument (k outside [1,31], c outside [0,1], ...)            */
+    SHK_E_CUDA = -2,     /* CUDA runtime/driver failure, or no device                             */
+    SHK_E_STATE = -3,    /* call out of order (e.g. reads submitted before the index exists)      */
+    SHK_E_CAPACITY = -4, /* chunk larger than the slot capacity given at shk_create               */
+    SHK_E_LIMIT = -5,    /* input exceeds a documented limit (e.g. > 65536 gene indices)          */
+    SHK_E_NOMEM = -6
+} shk_status;
+
+typedef struct shk_ctx shk_ctx;
+
+/* Options of one run = the reference's `opt::` globals (argument_parser.hpp:49-63). */
+typedef struct shk_params {
+    uint32_t k;                   /* -k, 1..31 (argument_parser.hpp:113-120)                       */
+    double c;                     /* -c, [0,1]; used as `max >= c*len` in IEEE double
+                                     (ReadAnalyzer.hpp:104)                                          */
+    uint64_t bf_bits;             /* Bloom filter size in bits.  The CLI passes -b * 2^33
+                                     (argument_parser.hpp:130-134); any value >= 64 is accepted    */
+    int32_t min_quality;          /* -q as the reference stores it: low 8 bits = its `char`
+                                     (argument_parser.hpp:144); 0 = no masking                     */
+    int32_t single;               /* -s (ReadAnalyzer.hpp:104)                                     */
+    int32_t device;               /* CUDA device ordinal                                           */
+    uint32_t n_slots;             /* chunk slots for double buffering (0 -> 2)                     */
+    uint32_t max_reads_per_chunk; /* slot capacity in reads   (0 -> 1<<20)                         */
+    uint64_t max_bytes_per_chunk; /* slot capacity in sequence bytes (0 -> 320 * max_reads)        */
+    uint32_t reserved[8];         /* must be zero                                                  */
+} shk_params;
+
+typedef struct shk_index_info {
+    uint32_t n_records;  /* FASTA records given (= legend_ID.size(), FastaSplitter.hpp:48)         */
+    uint32_t n_genes;    /* final `nidx` (main.cpp:186): indices 0..n_genes-1 are in use           */
+    uint64_t n_set_bits; /* num_kmer = rank(size) (bloomfilter.h:122)                              */
+    uint64_t tot_ids;    /* tot_idx = total length of all gene-id lists (bloomfilter.h:130-133)    */
+    uint64_t n_windows;  /* k-mer occurrences hashed in each pass                                  */
+    uint64_t bf_bits;
+    uint64_t device_bytes; /* HBM held by the index                                               */
+    float build_ms;        /* device time of the whole build (CUDA events)                         */
+    float reserved_f[3];
+} shk_index_info;
+
+/* One association = one line of the reference's stdout (ReadOutput.hpp:43): read `read_idx`
+ * of the chunk goes with reference record `gene_idx`; the NAME to print is legend[gene_idx]
+ * (ReadAnalyzer.hpp:106 - including the reference's index/name desync). */
+typedef struct shk_assoc {
+    uint32_t read_idx;
+    uint32_t gene_idx;
+} shk_assoc;
+
+typedef struct shk_chunk_result {
+    uint64_t n_assoc;       /* associations, ordered by read_idx then gene_idx                     */
+    const shk_assoc *assoc; /* library-owned pinned host memory, valid until the slot's next
+                               submit                                                                */
+    const uint8_t *keep;    /* n_reads flags: 1 = read has >= 1 association (is written to the
+                               filtered FASTQ, ReadOutput.hpp:44-47)                                */
+    uint32_t n_reads;
+    uint32_t n_slow_reads;  /* reads that took the exact large-table path                          */
+    uint64_t n_probes;      /* valid k-mer windows probed (counted on the device)                  */
+    uint64_t n_hits;        /* probes that found a set bit                                         */
+    float analyze_ms;       /* device time of the classification kernels (CUDA events)             */
+    float total_ms;         /* device time H2D + kernels + D2H of counters                         */
+    uint32_t kernel_launches;
+    uint32_t reserved;
+} shk_chunk_result;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+
+/* Replaces `parse_arguments` validation + `BF bloom(opt::bf_size)` (main.cpp:84,108;
+ * bloomfilter.h:48-53).  Allocates the filter in HBM and the chunk slots. */
+int shk_create(const shk_params *params, shk_ctx **out);
+void shk_destroy(shk_ctx *ctx);
+/* Message of the last failure on this context (ctx may be NULL: last failure of shk_create). */
+const char *shk_last_error(const shk_ctx *ctx);
+int shk_abi_version(void);
+
+/* ---- index build ---------------------------------------------------------------------- */
+
+/* Replaces pass 1 (FastaSplitter -> KmerBuilder::operator() KmerBuilder.hpp:40-72 ->
+ * BloomfilterFiller::operator() BloomfilterFiller.hpp:38-46 -> BF::add_at bloomfilter.h:57-59),
+ * BF::switch_mode(1) (bloomfilter.h:112-125), pass 2 (main.cpp:154-189 -> BF::add_to_kmer
+ * bloomfilter.h:61-75) and BF::switch_mode(2) (bloomfilter.h:126-184).
+ * ref_bases: the record sequences exactly as parsed (case and non-ACGT bytes preserved),
+ * concatenated; rec_offsets[n_records+1] are byte offsets.  Host pointers.  The caller keeps
+ * legend_ID (the record names). */
+int shk_index_build(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_offsets, uint32_t n_records,
+                    shk_index_info *info);
+int shk_index_info_get(const shk_ctx *ctx, shk_index_info *info);
+
+/* Downloads the index in the reference's logical form, for parity checks:
+ * set_bit_pos[n_set_bits] ascending (the 1s of `_bf`), offsets[n_set_bits+1]
+ * (offsets[r] = select(r)+1 over `_bv`, bloomfilter.h:142-148), ids[tot_ids] (`_index_kmer`).
+ * Any pointer may be NULL. */
+int shk_index_export(shk_ctx *ctx, uint64_t *set_bit_pos, uint32_t *offsets, uint16_t *ids);
+
+/* Replication across GPUs (one context per GPU).  The arrays that define the
+ * index are exposed as device buffers so that the host can move them with any transport
+ * (ncclBroadcast over NVLink, cudaMemcpyPeer): call shk_index_views on the source context,
+ * shk_index_adopt (allocates same-sized buffers) + shk_index_views on each destination, copy
+ * every view, then shk_index_finalize on the destinations. */
+#define SHK_INDEX_N_VIEWS 4
+typedef struct shk_index_views {
+    void *dev_ptr[SHK_INDEX_N_VIEWS]; /* 0 filter sectors, 1 per-bit entries, 2 CSR offsets, 3 CSR ids */
+    uint64_t bytes[SHK_INDEX_N_VIEWS];
+    shk_index_info info;
+} shk_index_views;
+int shk_index_views_get(shk_ctx *ctx, shk_index_views *views);
+int shk_index_adopt(shk_ctx *ctx, const shk_index_info *info);
+int shk_index_finalize(shk_ctx *ctx);
+
+/* ---- probe (test / roofline entry) ---------------------------------------------------- */
+
+/* Replaces BF::get_index (bloomfilter.h:78-102) for n canonical k-mers (host pointers):
+ * rank[i] = 0-based index of the set bit or -1 for a miss; [begin, begin+len) is the id range
+ * in `ids` as exported above (the reference's inclusive iterator pair, Q10). */
+int shk_probe(shk_ctx *ctx, const uint64_t *canonical_kmers, uint64_t n, int64_t *rank, uint32_t *list_begin,
+              uint32_t *list_len);
+
+/* Probe throughput through the hot path's own access sequence (filter word -> sector/rank ->
+ * entry): uploads n canonical k-mers once, runs the probe kernel reps times on the resident
+ * array, reports the best kernel time (CUDA events) and the number of hits. */
+int shk_probe_bench(shk_ctx *ctx, const uint64_t *canonical_kmers, uint64_t n, uint32_t reps, float *ms,
+                    uint64_t *n_hits);
+
+/* Measurement only (SURVEY.md 2.3 kernel B0): n_loads independent random 32-byte sector loads
+ * over the first `span_bytes` of the filter allocation (0 = all of it). */
+int shk_random_sector_bench(shk_ctx *ctx, uint64_t n_loads, uint64_t span_bytes, uint64_t seed, float *ms);
+
+/* ---- pinned staging memory ------------------------------------------------------------ */
+int shk_alloc_pinned(void **ptr, size_t bytes);
+int shk_free_pinned(void *ptr);
+
+/* ---- read classification -------------------------------------------------------------- */
+
+/* Replaces FastqSplitter's masking rule (FastqSplitter.hpp:104-109), ReadAnalyzer::operator()
+ * (ReadAnalyzer.hpp:39-110) and the ordering contract of ReadOutput (ReadOutput.hpp:40-49) for
+ * one chunk of reads in SoA form:
+ *   seq           concatenated read texts; a paired read is mate1 + 'N' + mate2
+ *                 (FastqSplitter.hpp:63,83)
+ *   qual          same layout (joiner byte 0x1B, FastqSplitter.hpp:84); may be NULL when
+ *                 min_quality == 0 (the reference never looks at qualities then)
+ *   read_offsets  n_reads+1 byte offsets into seq/qual
+ * Host pointers (pinned memory makes the copies asynchronous).  Asynchronous on the slot's
+ * stream: returns once the work is enqueued. */
+int shk_reads_submit(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint8_t *qual,
+                     const uint32_t *read_offsets, uint32_t n_reads);
+/* Blocks until the slot's chunk is done and returns its result. */
+int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *result);
+
+/* Same work split for kernel-only timing: upload copies the chunk to HBM and waits;
+ * analyze_resident runs only the kernels on the resident chunk (repeatable). */
+int shk_reads_upload(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint8_t *qual,
+                     const uint32_t *read_offsets, uint32_t n_reads);
+int shk_reads_analyze_resident(shk_ctx *ctx, uint32_t slot);
+
+/* Kernel launches issued by this context so far (for bench accounting). */
+uint64_t shk_kernel_launches(const shk_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHARK_B200_H */

@@ -1,0 +1,54 @@
+"""Builds libshark_b200.so (CUDA kernels + C ABI) and the shark-b200 CLI for sm_100a, in-tree.
+
+nvcc cross-compiles without a GPU.  The .so stays next to this file so that it travels to the GPU
+box with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libshark_b200.so")
+CLI = os.path.join(HERE, "shark-b200")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CU_SOURCES = ["shk_capi.cu", "shk_index.cu", "shk_reads.cu"]
+HOST_SOURCES = ["host/fastx.cpp", "host/shark_main.cpp"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _deps():
+    out = [os.path.join(HERE, "..", "include", "shark_b200.h"), os.path.abspath(__file__)]
+    for root, _, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h", ".cpp", ".hpp"))]
+    return out
+
+
+def build(force=False, verbose=False):
+    deps = _deps()
+    if force or _newer(LIB, deps):
+        objs = []
+        for src in CU_SOURCES:
+            obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+            cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3",
+                   "-c", os.path.join(CSRC, src), "-o", obj]
+            subprocess.check_call(cmd)
+            objs.append(obj)
+        subprocess.check_call([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"])
+    host = [os.path.join(CSRC, s) for s in HOST_SOURCES]
+    if all(os.path.exists(h) for h in host) and (force or _newer(CLI, deps + [LIB])):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(HERE, "..", "include"),
+                               *host, "-o", CLI, "-L", HERE, "-lshark_b200", "-Wl,-rpath,$ORIGIN", "-lz"])
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

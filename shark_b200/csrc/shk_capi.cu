@@ -1,0 +1,504 @@
+// C ABI of libshark_b200.so (include/shark_b200.h): contexts, slots, streams, copies.
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "shk_internal.h"
+
+namespace shk {
+
+static std::mutex g_err_mu;
+static char g_err[512] = {0};
+
+void set_global_error(const char *msg)
+{
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    snprintf(g_err, sizeof g_err, "%s", msg);
+}
+
+int fail(shk_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s", buf);
+    set_global_error(buf);
+    return code;
+}
+
+static void free_slot(Slot &s)
+{
+    cudaFree(s.d_seq);
+    cudaFree(s.d_qual);
+    cudaFree(s.d_off);
+    cudaFree(s.d_rec);
+    cudaFree(s.d_pool);
+    cudaFree(s.d_slow_list);
+    cudaFree(s.d_tile_sums);
+    cudaFree(s.d_tile_base);
+    cudaFree(s.d_counters);
+    cudaFree(s.d_assoc);
+    cudaFree(s.d_keep);
+    cudaFreeHost(s.h_counters);
+    cudaFreeHost(s.h_assoc);
+    cudaFreeHost(s.h_keep);
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot{};
+}
+
+static int alloc_slot(shk_ctx *ctx, Slot &s)
+{
+    const uint64_t R = ctx->max_reads, B = ctx->max_bytes;
+    const uint64_t tiles = (R + kReadsPerTile - 1) / kReadsPerTile;
+    SHK_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    SHK_CUDA(ctx, cudaEventCreate(&s.ev_start));
+    SHK_CUDA(ctx, cudaEventCreate(&s.ev_k0));
+    SHK_CUDA(ctx, cudaEventCreate(&s.ev_k1));
+    SHK_CUDA(ctx, cudaEventCreate(&s.ev_done));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_seq, B + 64));
+    if ((ctx->params.min_quality & 0xFF) != 0) SHK_CUDA(ctx, cudaMalloc((void **)&s.d_qual, B + 64));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_off, (R + 1) * 4));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_rec, R * sizeof(uint2)));
+    s.pool_cap = (uint32_t)std::max<uint64_t>(R / 2, 4096);
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_pool, (uint64_t)s.pool_cap * 4));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_slow_list, R * 4));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_tile_sums, (tiles + 1) * 4));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_tile_base, (tiles + 1) * 4));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_counters, sizeof(ChunkCounters)));
+    s.assoc_cap = R + R / 4 + 1024;
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_assoc, s.assoc_cap * sizeof(shk_assoc)));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_keep, R + 64));
+    SHK_CUDA(ctx, cudaMallocHost((void **)&s.h_counters, sizeof(ChunkCounters)));
+    s.h_assoc_cap = s.assoc_cap;
+    SHK_CUDA(ctx, cudaMallocHost((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
+    SHK_CUDA(ctx, cudaMallocHost((void **)&s.h_keep, R + 64));
+    return SHK_OK;
+}
+
+static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
+{
+    ReadKernelArgs a{};
+    a.seq = s.d_seq;
+    a.qual = s.has_qual ? s.d_qual : nullptr;
+    a.off = s.d_off;
+    a.n_reads = s.n_reads;
+    a.sectors = ctx->index.sectors;
+    a.entries = ctx->index.entries;
+    a.csr_off = ctx->index.csr_off;
+    a.csr_ids = ctx->index.csr_ids;
+    a.geom = ctx->index.geom;
+    a.n_genes = ctx->index.info.n_genes;
+    a.k = (int)ctx->params.k;
+    a.c = ctx->params.c;
+    // `const char mq = min_quality + 33` with min_quality a (signed) char: FastqSplitter.hpp:75
+    a.mq = (int)(signed char)(unsigned char)((ctx->params.min_quality & 0xFF) + 33);
+    a.single = ctx->params.single ? 1 : 0;
+    a.rec = s.d_rec;
+    a.pool = s.d_pool;
+    a.pool_cap = s.pool_cap;
+    a.slow_list = s.d_slow_list;
+    a.tile_sums = s.d_tile_sums;
+    a.counters = s.d_counters;
+    a.slow_table = ctx->d_slow_table;
+    a.slow_stamp = ctx->d_slow_stamp;
+    a.n_slow_slabs = ctx->n_slow_slabs;
+    a.tile_base = s.d_tile_base;
+    a.assoc = s.d_assoc;
+    a.keep = s.d_keep;
+    return a;
+}
+
+// The exact-path table depends on the number of gene indices -> (re)allocated after a build.
+static int ensure_slow_table(shk_ctx *ctx)
+{
+    if (ctx->d_slow_table) {
+        cudaFree(ctx->d_slow_table);
+        ctx->d_slow_table = nullptr;
+    }
+    if (ctx->d_slow_stamp) {
+        cudaFree(ctx->d_slow_stamp);
+        ctx->d_slow_stamp = nullptr;
+    }
+    const uint64_t ng = std::max<uint32_t>(ctx->index.info.n_genes, 1);
+    // as many concurrent exact-path warps as 256 MiB of tables allow, at most 4 per SM
+    uint64_t slabs = std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (256ull << 20) / (ng * sizeof(uint4)));
+    slabs = std::max<uint64_t>(slabs, 8);
+    ctx->n_slow_slabs = (uint32_t)slabs;
+    SHK_CUDA(ctx, cudaMalloc((void **)&ctx->d_slow_table, slabs * ng * sizeof(uint4)));
+    SHK_CUDA(ctx, cudaMalloc((void **)&ctx->d_slow_stamp, slabs * 4));
+    SHK_CUDA(ctx, cudaMemset(ctx->d_slow_table, 0, slabs * ng * sizeof(uint4)));
+    SHK_CUDA(ctx, cudaMemset(ctx->d_slow_stamp, 0, slabs * 4));
+    return SHK_OK;
+}
+
+static int enqueue_chunk_kernels(shk_ctx *ctx, Slot &s)
+{
+    SHK_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, sizeof(ChunkCounters), s.stream));
+    ReadKernelArgs a = make_args(ctx, s);
+    s.launches += (uint32_t)launch_read_kernels(ctx, a, s.assoc_cap, s.stream, s.ev_k0, s.ev_k1);
+    SHK_CUDA(ctx, cudaGetLastError());
+    SHK_CUDA(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(ChunkCounters), cudaMemcpyDeviceToHost, s.stream));
+    SHK_CUDA(ctx, cudaEventRecord(s.ev_done, s.stream));
+    return SHK_OK;
+}
+
+static int check_chunk(shk_ctx *ctx, uint32_t slot, const uint32_t *off, uint32_t n_reads, const uint8_t *qual)
+{
+    if (!ctx) return SHK_E_ARG;
+    if (slot >= ctx->n_slots) return fail(ctx, SHK_E_ARG, "slot %u out of range (n_slots=%u)", slot, ctx->n_slots);
+    if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index: call shk_index_build first");
+    if (n_reads > ctx->max_reads)
+        return fail(ctx, SHK_E_CAPACITY, "chunk of %u reads exceeds max_reads_per_chunk=%u", n_reads, ctx->max_reads);
+    if (n_reads && !off) return fail(ctx, SHK_E_ARG, "read_offsets is NULL");
+    if (n_reads && (uint64_t)off[n_reads] > ctx->max_bytes)
+        return fail(ctx, SHK_E_CAPACITY, "chunk of %u bytes exceeds max_bytes_per_chunk=%llu", off[n_reads],
+                    (unsigned long long)ctx->max_bytes);
+    if ((ctx->params.min_quality & 0xFF) != 0 && !qual && n_reads)
+        return fail(ctx, SHK_E_ARG, "min_quality != 0 needs the quality bytes");
+    return SHK_OK;
+}
+
+static int enqueue_upload(shk_ctx *ctx, Slot &s, const uint8_t *seq, const uint8_t *qual, const uint32_t *off,
+                          uint32_t n_reads)
+{
+    s.n_reads = n_reads;
+    s.n_bytes = n_reads ? off[n_reads] : 0;
+    s.has_qual = (ctx->params.min_quality & 0xFF) != 0;
+    s.launches = 0;
+    SHK_CUDA(ctx, cudaEventRecord(s.ev_start, s.stream));
+    if (n_reads) {
+        SHK_CUDA(ctx, cudaMemcpyAsync(s.d_off, off, ((uint64_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+        if (s.n_bytes) {
+            SHK_CUDA(ctx, cudaMemcpyAsync(s.d_seq, seq, s.n_bytes, cudaMemcpyHostToDevice, s.stream));
+            if (s.has_qual) SHK_CUDA(ctx, cudaMemcpyAsync(s.d_qual, qual, s.n_bytes, cudaMemcpyHostToDevice, s.stream));
+        }
+    }
+    return SHK_OK;
+}
+
+}  // namespace shk
+
+using namespace shk;
+
+extern "C" {
+
+int shk_abi_version(void) { return SHK_ABI_VERSION; }
+
+const char *shk_last_error(const shk_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+int shk_create(const shk_params *p, shk_ctx **out)
+{
+    if (!p || !out) return fail(nullptr, SHK_E_ARG, "NULL argument");
+    *out = nullptr;
+    if (p->k == 0 || p->k > 31) return fail(nullptr, SHK_E_ARG, "k must be in the range [1, 31]");
+    if (!(p->c >= 0.0 && p->c <= 1.0)) return fail(nullptr, SHK_E_ARG, "c must be in the range [0, 1]");
+    if (p->bf_bits < 64) return fail(nullptr, SHK_E_ARG, "bf_bits must be >= 64");
+    const uint64_t n_words = (p->bf_bits + 31) / 32;
+    const uint64_t n_sectors = (n_words + kWordsPerSector - 1) / kWordsPerSector;
+    if (n_sectors * 8 > 0xFFFFFFFFull)
+        return fail(nullptr, SHK_E_LIMIT, "bf_bits=%llu: filters above ~2^36.8 bits (-b 14) are not supported",
+                    (unsigned long long)p->bf_bits);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, SHK_E_CUDA, "no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (p->device < 0 || p->device >= n_dev) return fail(nullptr, SHK_E_ARG, "device %d out of range", p->device);
+    shk_ctx *ctx = new (std::nothrow) shk_ctx;
+    if (!ctx) return fail(nullptr, SHK_E_NOMEM, "out of host memory");
+    ctx->params = *p;
+    ctx->device = p->device;
+    int rc = SHK_OK;
+    auto bail = [&](int code) {
+        shk_destroy(ctx);
+        return code;
+    };
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return bail(fail(nullptr, SHK_E_CUDA, "cudaSetDevice failed"));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    FilterGeom &g = ctx->index.geom;
+    g.bf_bits = p->bf_bits;
+    g.n_sectors = n_sectors;
+    if ((p->bf_bits & (p->bf_bits - 1)) == 0) {
+        g.mod_kind = MOD_POW2;
+        g.pow2_mask = p->bf_bits - 1;
+    } else if ((p->bf_bits & ((1ULL << 33) - 1)) == 0 && (p->bf_bits >> 33) < (1ULL << 31)) {
+        g.mod_kind = MOD_B33;
+        g.b33 = (uint32_t)(p->bf_bits >> 33);
+    } else {
+        g.mod_kind = MOD_GENERIC;
+    }
+    ctx->n_slots = p->n_slots ? p->n_slots : 2;
+    ctx->max_reads = p->max_reads_per_chunk ? p->max_reads_per_chunk : (1u << 20);
+    ctx->max_bytes = p->max_bytes_per_chunk ? p->max_bytes_per_chunk : 320ull * ctx->max_reads;
+    if (ctx->max_bytes >= (1ull << 32)) return bail(fail(nullptr, SHK_E_LIMIT, "max_bytes_per_chunk must be < 4 GiB"));
+    if (cudaStreamCreateWithFlags(&ctx->build_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(nullptr, SHK_E_CUDA, "cudaStreamCreate failed"));
+    // BF bloom(opt::bf_size): the filter, zero-initialised (bloomfilter.h:48-53)
+    e = cudaMalloc((void **)&ctx->index.sectors, n_sectors * 32);
+    if (e != cudaSuccess)
+        return bail(fail(nullptr, SHK_E_NOMEM, "cannot allocate %llu bytes for the filter: %s",
+                         (unsigned long long)(n_sectors * 32), cudaGetErrorString(e)));
+    cudaMemset(ctx->index.sectors, 0, n_sectors * 32);
+    ctx->slots = new (std::nothrow) Slot[ctx->n_slots];
+    if (!ctx->slots) return bail(fail(nullptr, SHK_E_NOMEM, "out of host memory"));
+    for (uint32_t i = 0; i < ctx->n_slots; ++i) {
+        rc = alloc_slot(ctx, ctx->slots[i]);
+        if (rc) {
+            set_global_error(ctx->err);
+            return bail(rc);
+        }
+    }
+    *out = ctx;
+    return SHK_OK;
+}
+
+void shk_destroy(shk_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->slots) {
+        for (uint32_t i = 0; i < ctx->n_slots; ++i) free_slot(ctx->slots[i]);
+        delete[] ctx->slots;
+    }
+    cudaFree(ctx->index.sectors);
+    cudaFree(ctx->index.entries);
+    cudaFree(ctx->index.csr_off);
+    cudaFree(ctx->index.csr_ids);
+    cudaFree(ctx->d_slow_table);
+    cudaFree(ctx->d_slow_stamp);
+    if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
+    delete ctx;
+}
+
+int shk_index_build(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_offsets, uint32_t n_records,
+                    shk_index_info *info)
+{
+    if (!ctx || !rec_offsets) return fail(ctx, SHK_E_ARG, "NULL argument");
+    if (rec_offsets[n_records] && !ref_bases) return fail(ctx, SHK_E_ARG, "ref_bases is NULL");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = index_build_device(ctx, ref_bases, rec_offsets, n_records);
+    if (rc) return rc;
+    rc = ensure_slow_table(ctx);
+    if (rc) return rc;
+    if (info) *info = ctx->index.info;
+    return SHK_OK;
+}
+
+int shk_index_info_get(const shk_ctx *ctx, shk_index_info *info)
+{
+    if (!ctx || !info) return SHK_E_ARG;
+    if (!ctx->index.built) return SHK_E_STATE;
+    *info = ctx->index.info;
+    return SHK_OK;
+}
+
+int shk_index_export(shk_ctx *ctx, uint64_t *set_bit_pos, uint32_t *offsets, uint16_t *ids)
+{
+    if (!ctx) return SHK_E_ARG;
+    if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return index_export_device(ctx, set_bit_pos, offsets, ids);
+}
+
+int shk_index_views_get(shk_ctx *ctx, shk_index_views *v)
+{
+    if (!ctx || !v) return SHK_E_ARG;
+    if (!ctx->index.built && !ctx->index.entries) return fail(ctx, SHK_E_STATE, "no index");
+    const DeviceIndex &ix = ctx->index;
+    v->dev_ptr[0] = ix.sectors;
+    v->bytes[0] = ix.geom.n_sectors * 32;
+    v->dev_ptr[1] = ix.entries;
+    v->bytes[1] = (ix.info.n_set_bits + 1) * 8;
+    v->dev_ptr[2] = ix.csr_off;
+    v->bytes[2] = (ix.info.n_set_bits + 1) * 4;
+    v->dev_ptr[3] = ix.csr_ids;
+    v->bytes[3] = std::max<uint64_t>(ix.info.tot_ids, 1) * 2;
+    v->info = ix.info;
+    return SHK_OK;
+}
+
+int shk_index_adopt(shk_ctx *ctx, const shk_index_info *info)
+{
+    if (!ctx || !info) return SHK_E_ARG;
+    if (info->bf_bits != ctx->index.geom.bf_bits)
+        return fail(ctx, SHK_E_ARG, "bf_bits mismatch between source index and this context");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceIndex &ix = ctx->index;
+    cudaFree(ix.entries);
+    cudaFree(ix.csr_off);
+    cudaFree(ix.csr_ids);
+    ix.entries = nullptr, ix.csr_off = nullptr, ix.csr_ids = nullptr;
+    ix.built = false;
+    ix.info = *info;
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.entries, (info->n_set_bits + 1) * 8));
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.csr_off, (info->n_set_bits + 1) * 4));
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.csr_ids, std::max<uint64_t>(info->tot_ids, 1) * 2));
+    return SHK_OK;
+}
+
+int shk_index_finalize(shk_ctx *ctx)
+{
+    if (!ctx) return SHK_E_ARG;
+    if (!ctx->index.entries) return fail(ctx, SHK_E_STATE, "shk_index_adopt was not called");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    SHK_CUDA(ctx, cudaDeviceSynchronize());
+    ctx->index.built = true;
+    return ensure_slow_table(ctx);
+}
+
+int shk_probe(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int64_t *rank, uint32_t *begin, uint32_t *len)
+{
+    if (!ctx || (n && (!kmers || !rank || !begin || !len))) return fail(ctx, SHK_E_ARG, "NULL argument");
+    if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return probe_device(ctx, kmers, n, rank, begin, len);
+}
+
+int shk_probe_bench(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, uint32_t reps, float *ms, uint64_t *n_hits)
+{
+    if (!ctx || !kmers || !n) return fail(ctx, SHK_E_ARG, "bad argument");
+    if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return probe_bench_device(ctx, kmers, n, reps ? reps : 3, ms, n_hits);
+}
+
+int shk_random_sector_bench(shk_ctx *ctx, uint64_t n_loads, uint64_t span_bytes, uint64_t seed, float *ms)
+{
+    if (!ctx || !n_loads) return fail(ctx, SHK_E_ARG, "bad argument");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return random_sector_bench_device(ctx, n_loads, span_bytes, seed, ms);
+}
+
+int shk_alloc_pinned(void **ptr, size_t bytes)
+{
+    if (!ptr) return SHK_E_ARG;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(nullptr, SHK_E_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return SHK_OK;
+}
+
+int shk_free_pinned(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+    return SHK_OK;
+}
+
+int shk_reads_submit(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint8_t *qual, const uint32_t *off,
+                     uint32_t n_reads)
+{
+    int rc = check_chunk(ctx, slot, off, n_reads, qual);
+    if (rc) return rc;
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    rc = enqueue_upload(ctx, s, seq, qual, off, n_reads);
+    if (rc) return rc;
+    rc = enqueue_chunk_kernels(ctx, s);
+    if (rc) return rc;
+    s.pending = true;
+    return SHK_OK;
+}
+
+int shk_reads_upload(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint8_t *qual, const uint32_t *off,
+                     uint32_t n_reads)
+{
+    int rc = check_chunk(ctx, slot, off, n_reads, qual);
+    if (rc) return rc;
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    rc = enqueue_upload(ctx, s, seq, qual, off, n_reads);
+    if (rc) return rc;
+    SHK_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    s.pending = false;
+    return SHK_OK;
+}
+
+int shk_reads_analyze_resident(shk_ctx *ctx, uint32_t slot)
+{
+    if (!ctx || slot >= ctx->n_slots) return fail(ctx, SHK_E_ARG, "bad slot");
+    if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    s.launches = 0;
+    SHK_CUDA(ctx, cudaEventRecord(s.ev_start, s.stream));
+    int rc = enqueue_chunk_kernels(ctx, s);
+    if (rc) return rc;
+    s.pending = true;
+    return SHK_OK;
+}
+
+int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
+{
+    if (!ctx || slot >= ctx->n_slots || !out) return fail(ctx, SHK_E_ARG, "bad argument");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    if (!s.pending) return fail(ctx, SHK_E_STATE, "slot %u has no submitted chunk", slot);
+    for (int attempt = 0;; ++attempt) {
+        SHK_CUDA(ctx, cudaEventSynchronize(s.ev_done));
+        const ChunkCounters &c = *s.h_counters;
+        if (c.pool_overflow) {
+            // more tied winners than the pool holds: grow it and run the chunk again (exact)
+            if (attempt > 8) return fail(ctx, SHK_E_NOMEM, "tie pool keeps overflowing");
+            uint64_t want = std::max<uint64_t>((uint64_t)c.pool_used * 2, (uint64_t)s.pool_cap * 4);
+            if (want > 0xFFFFFFF0ull) return fail(ctx, SHK_E_LIMIT, "tie pool would exceed 2^32 entries");
+            cudaFree(s.d_pool);
+            s.d_pool = nullptr;
+            SHK_CUDA(ctx, cudaMalloc((void **)&s.d_pool, want * 4));
+            s.pool_cap = (uint32_t)want;
+            int rc = enqueue_chunk_kernels(ctx, s);
+            if (rc) return rc;
+            continue;
+        }
+        if (c.n_assoc > s.assoc_cap) {
+            uint64_t want = c.n_assoc + c.n_assoc / 8 + 1024;
+            cudaFree(s.d_assoc);
+            s.d_assoc = nullptr;
+            SHK_CUDA(ctx, cudaMalloc((void **)&s.d_assoc, want * sizeof(shk_assoc)));
+            s.assoc_cap = want;
+            ReadKernelArgs a = make_args(ctx, s);
+            s.launches += (uint32_t)launch_scatter(ctx, a, s.assoc_cap, s.stream);
+            SHK_CUDA(ctx, cudaGetLastError());
+            SHK_CUDA(ctx, cudaEventRecord(s.ev_done, s.stream));
+            continue;
+        }
+        break;
+    }
+    const ChunkCounters c = *s.h_counters;
+    if (c.n_assoc > s.h_assoc_cap) {
+        cudaFreeHost(s.h_assoc);
+        s.h_assoc = nullptr;
+        s.h_assoc_cap = c.n_assoc + c.n_assoc / 8 + 1024;
+        SHK_CUDA(ctx, cudaMallocHost((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
+    }
+    if (c.n_assoc)
+        SHK_CUDA(ctx, cudaMemcpyAsync(s.h_assoc, s.d_assoc, c.n_assoc * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
+    if (s.n_reads) SHK_CUDA(ctx, cudaMemcpyAsync(s.h_keep, s.d_keep, s.n_reads, cudaMemcpyDeviceToHost, s.stream));
+    SHK_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    float k_ms = 0, t_ms = 0;
+    cudaEventElapsedTime(&k_ms, s.ev_k0, s.ev_k1);
+    cudaEventElapsedTime(&t_ms, s.ev_start, s.ev_done);
+    memset(out, 0, sizeof *out);
+    out->n_assoc = c.n_assoc;
+    out->assoc = s.h_assoc;
+    out->keep = s.h_keep;
+    out->n_reads = s.n_reads;
+    out->n_slow_reads = c.n_slow;
+    out->n_probes = c.n_probes;
+    out->n_hits = c.n_hits;
+    out->analyze_ms = k_ms;
+    out->total_ms = t_ms;
+    out->kernel_launches = s.launches;
+    s.pending = false;
+    return SHK_OK;
+}
+
+uint64_t shk_kernel_launches(const shk_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+}  // extern "C"

@@ -1,0 +1,771 @@
+// Index build on the device: replaces KmerBuilder + BloomfilterFiller (pass 1), the pass-2 loop of
+// main.cpp, and both BF::switch_mode transitions.  Also the stand-alone probe (BF::get_index) and
+// the random-sector microbenchmark.  Citations are reference file:line.
+#include <algorithm>
+#include <vector>
+
+#include "shk_internal.h"
+#include "shk_scan.cuh"
+
+namespace shk {
+
+static constexpr uint64_t kInvalidPos = ~0ULL;
+
+// =============================================================================================
+// Device-wide exclusive scan of 32-bit values (hand-written, three phases: tile sums, scan of
+// the tile sums by one CTA, tile scan + output).  Tile = 256 threads x 16 items, each warp owns
+// 512 consecutive items and walks them in 16 coalesced rounds.
+// =============================================================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// popcount of the 224 filter bits of sector i (the rank word w[7] is not counted)
+struct SectorPopIn {
+    const uint32_t *sectors;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const
+    {
+        const uint4 *p = reinterpret_cast<const uint4 *>(sectors + i * 8);
+        uint4 a = p[0], b = p[1];
+        return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z);
+    }
+};
+struct SectorRankOut {
+    uint32_t *sectors;
+    __device__ __forceinline__ void operator()(uint64_t i, uint32_t prefix) const { sectors[i * 8 + 7] = prefix; }
+};
+struct U32In {
+    const uint32_t *p;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return p[i]; }
+};
+struct U32Out {
+    uint32_t *p;
+    __device__ __forceinline__ void operator()(uint64_t i, uint32_t prefix) const { p[i] = prefix; }
+};
+
+template <class In>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(In in, uint64_t n, uint32_t *tile_sums)
+{
+    __shared__ uint32_t warp_tot[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)warp * (32 * kScanItems);
+    uint32_t s = 0;
+#pragma unroll 4
+    for (int r = 0; r < kScanItems; ++r) {
+        uint64_t i = base + (uint64_t)r * 32 + lane;
+        if (i < n) s += in(i);
+    }
+    s = __reduce_add_sync(0xFFFFFFFFu, s);
+    if (lane == 0) warp_tot[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += warp_tot[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+template <class In, class Out>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(In in, Out out, uint64_t n, const uint32_t *tile_sums)
+{
+    __shared__ uint32_t warp_tot[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)warp * (32 * kScanItems);
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r) {
+        uint64_t i = base + (uint64_t)r * 32 + lane;
+        v[r] = i < n ? in(i) : 0;
+        s += v[r];
+    }
+    s = __reduce_add_sync(0xFFFFFFFFu, s);
+    if (lane == 0) warp_tot[warp] = s;
+    __syncthreads();
+    uint32_t run = tile_sums[blockIdx.x];
+    for (int w = 0; w < warp; ++w) run += warp_tot[w];
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r) {
+        uint64_t i = base + (uint64_t)r * 32 + lane;
+        uint32_t incl = warp_incl_scan(v[r], lane);
+        if (i < n) out(i, run + incl - v[r]);
+        run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+}
+
+// Host driver.  tile_sums must hold ceil(n / kScanTile) words; d_total may be nullptr.
+template <class In, class Out>
+static int exclusive_scan(shk_ctx *ctx, cudaStream_t st, In in, Out out, uint64_t n, uint32_t *tile_sums,
+                          uint32_t *d_total)
+{
+    uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+    if (n_tiles == 0) {
+        if (d_total) SHK_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint32_t), st));
+        return SHK_OK;
+    }
+    if (n_tiles > 0x7FFFFFFFull) return fail(ctx, SHK_E_LIMIT, "scan too large");
+    scan_reduce_kernel<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(in, n, tile_sums);
+    scan_tile_sums_kernel<<<1, 1024, 0, st>>>(tile_sums, (uint32_t)n_tiles, d_total);
+    scan_apply_kernel<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(in, out, n, tile_sums);
+    ctx->launches += 3;
+    SHK_CUDA(ctx, cudaGetLastError());
+    return SHK_OK;
+}
+
+// =============================================================================================
+// K1: canonical k-mers of every reference position -> hash -> filter bit.
+// Replaces KmerBuilder::operator() (KmerBuilder.hpp:40-72), BloomfilterFiller::operator()
+// (BloomfilterFiller.hpp:38-46) and BF::add_at (bloomfilter.h:57-59).  One thread owns 8
+// consecutive positions of the concatenated reference and rolls the forward k-mer over them
+// (kmer_utils.hpp:73-75); a window is valid when the last k bytes are all ACGT/acgt and lie in
+// one record.  The bit index of each window is kept (win_pos) for the second pass.
+// =============================================================================================
+constexpr int kPosPerThread = 8;
+
+__device__ __forceinline__ uint32_t record_of(const uint64_t *rec_off, uint32_t n_rec, uint64_t x)
+{
+    // largest r with rec_off[r] <= x  (x < rec_off[n_rec])
+    uint32_t lo = 0, hi = n_rec;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (rec_off[mid] <= x) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int MOD>
+__global__ void __launch_bounds__(256)
+enum_setbits_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ rec_off, uint32_t n_rec,
+                    uint64_t total, int k, FilterGeom g, uint32_t *sectors, uint64_t *win_pos,
+                    uint32_t *rec_has_window, unsigned long long *n_windows)
+{
+    const uint64_t x0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kPosPerThread;
+    uint32_t my_windows = 0;
+    if (x0 < total) {
+        const uint64_t xend = min(x0 + (uint64_t)kPosPerThread, total);
+        uint64_t s = x0 >= (uint64_t)(k - 1) ? x0 - (k - 1) : 0;
+        uint32_t r = record_of(rec_off, n_rec, s);
+        uint64_t next_b = rec_off[r + 1];
+        const uint64_t kmask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
+        uint64_t fwd = 0;
+        int run = 0;
+        uint32_t marked = 0xFFFFFFFFu;
+        for (uint64_t pos = s; pos < xend; ++pos) {
+            while (pos >= next_b) {
+                ++r;
+                next_b = rec_off[r + 1];
+                run = 0;
+            }
+            uint32_t ch = bases[pos];
+            if (base_valid(ch)) {
+                fwd = ((fwd << 2) | base_code(ch)) & kmask;
+                ++run;
+            } else {
+                run = 0;
+            }
+            if (pos >= x0) {
+                uint64_t p = kInvalidPos;
+                if (run >= k) {
+                    p = bit_index<MOD>(xxh64_u64(canonical(fwd, k)), g);
+                    atomicOr(&sectors[phys_word(p)], 1u << (p & 31));  // `_bf[p % _size] = 1`
+                    if (marked != r) {
+                        rec_has_window[r] = 1;
+                        marked = r;
+                    }
+                    ++my_windows;
+                }
+                win_pos[pos] = p;
+            }
+        }
+    }
+    my_windows = __reduce_add_sync(0xFFFFFFFFu, my_windows);
+    if ((threadIdx.x & 31) == 0 && my_windows) atomicAdd(n_windows, (unsigned long long)my_windows);
+}
+
+// Gene index of every record = the reference's `nidx` (main.cpp:158-187): a record consumes an
+// index unless its length is >= k and it has no valid window (`continue` at main.cpp:166 skips
+// `++nidx` at 186).  One CTA; n_rec is small (<= a few 100k).
+__global__ void __launch_bounds__(1024)
+assign_nidx_kernel(const uint64_t *rec_off, const uint32_t *rec_has_window, uint32_t n_rec, int k, uint32_t *nidx,
+                   uint32_t *n_genes)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_rec; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = 0;
+        if (i < n_rec) {
+            uint64_t len = rec_off[i + 1] - rec_off[i];
+            v = (len >= (uint64_t)k && !rec_has_window[i]) ? 0u : 1u;
+        }
+        uint32_t incl = warp_incl_scan(v, lane);
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_tot[lane];
+            uint32_t wi = warp_incl_scan(w, lane);
+            warp_tot[lane] = wi - w;
+        }
+        __syncthreads();
+        uint32_t excl = carry_s + warp_tot[warp] + incl - v;
+        if (i < n_rec) nidx[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_genes = carry_s;
+}
+
+// K3: second pass, counting.  Replaces the rank lookups of BF::add_to_kmer (bloomfilter.h:70):
+// every window's bit index becomes the 0-based rank of its set bit, and cnt[rank] counts the
+// occurrences (an upper bound of the list length before per-gene dedup).
+__global__ void __launch_bounds__(256)
+rank_count_kernel(uint64_t *win_pos, uint64_t total, const uint32_t *__restrict__ sectors, uint32_t *cnt)
+{
+    uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= total) return;
+    uint64_t p = win_pos[x];
+    if (p == kInvalidPos) return;
+    uint64_t q = p >> 5;
+    uint64_t sec = q / kWordsPerSector;
+    uint32_t slot = (uint32_t)(q - sec * kWordsPerSector);
+    const uint4 *sp = reinterpret_cast<const uint4 *>(sectors + sec * 8);
+    uint4 a = sp[0], b = sp[1];
+    Sector s;
+    s.w[0] = a.x, s.w[1] = a.y, s.w[2] = a.z, s.w[3] = a.w, s.w[4] = b.x, s.w[5] = b.y, s.w[6] = b.z, s.w[7] = b.w;
+    uint32_t r = sector_rank(s, slot, (uint32_t)(p & 31));
+    win_pos[x] = r;
+    atomicAdd(&cnt[r], 1u);
+}
+
+// K4: second pass, filling.  Gene ids land unordered (and possibly repeated) in the slots that
+// the scan of cnt reserved for each set bit.
+__global__ void __launch_bounds__(256)
+fill_kernel(const uint64_t *__restrict__ win_pos, uint64_t total, const uint64_t *__restrict__ rec_off, uint32_t n_rec,
+            const uint32_t *__restrict__ nidx, const uint32_t *__restrict__ tmp_off, uint32_t *fill, uint16_t *tmp_ids)
+{
+    uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= total) return;
+    uint64_t v = win_pos[x];
+    if (v == kInvalidPos) return;
+    uint32_t r = (uint32_t)v;
+    uint32_t g = nidx[record_of(rec_off, n_rec, x)];
+    uint32_t slot = tmp_off[r] + atomicAdd(&fill[r], 1u);
+    tmp_ids[slot] = (uint16_t)g;  // small_vector_t::push_back(uint16_t), small_vector.hpp:46
+}
+
+// Sort + unique of each list (BF::add_to_kmer's `last() != input_idx` dedup with genes arriving
+// in ascending order, bloomfilter.h:68-74 => every list is strictly ascending).  One thread
+// per set bit for the common short lists; long lists are queued for the bitmap kernel.
+constexpr uint32_t kShortList = 48;
+
+__global__ void __launch_bounds__(256)
+sort_unique_kernel(const uint32_t *__restrict__ tmp_off, uint32_t n_set, uint16_t *tmp_ids, uint32_t *len,
+                   uint32_t *long_list, uint32_t *n_long)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_set) return;
+    uint32_t b = tmp_off[r], n = tmp_off[r + 1] - b;
+    if (n <= 1) {
+        len[r] = n;
+        return;
+    }
+    if (n > kShortList) {
+        long_list[atomicAdd(n_long, 1u)] = r;
+        return;
+    }
+    uint16_t *a = tmp_ids + b;
+    for (uint32_t i = 1; i < n; ++i) {
+        uint16_t key = a[i];
+        uint32_t j = i;
+        while (j > 0 && a[j - 1] > key) {
+            a[j] = a[j - 1];
+            --j;
+        }
+        a[j] = key;
+    }
+    uint32_t m = 1;
+    for (uint32_t i = 1; i < n; ++i)
+        if (a[i] != a[m - 1]) a[m++] = a[i];
+    len[r] = m;
+}
+
+// Long lists: one CTA per list, a 65536-bit presence bitmap in shared memory gives the sorted
+// unique ids directly (ids are 16-bit).
+__global__ void __launch_bounds__(256)
+sort_unique_long_kernel(const uint32_t *__restrict__ tmp_off, const uint32_t *__restrict__ long_list, uint16_t *tmp_ids,
+                        uint32_t *len)
+{
+    __shared__ uint32_t bitmap[2048];
+    __shared__ uint32_t warp_tot[8];
+    const uint32_t r = long_list[blockIdx.x];
+    const uint32_t b = tmp_off[r], n = tmp_off[r + 1] - b;
+    for (int i = threadIdx.x; i < 2048; i += 256) bitmap[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += 256) {
+        uint32_t id = tmp_ids[b + i];
+        atomicOr(&bitmap[id >> 5], 1u << (id & 31));
+    }
+    __syncthreads();
+    // thread t owns words [8t, 8t+8)
+    uint32_t c = 0;
+    for (int w = 0; w < 8; ++w) c += __popc(bitmap[threadIdx.x * 8 + w]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = warp_incl_scan(c, lane);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t off = incl - c;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    for (int w = 0; w < 8; ++w) {
+        uint32_t bits = bitmap[threadIdx.x * 8 + w];
+        while (bits) {
+            int bpos = __ffs(bits) - 1;
+            bits &= bits - 1;
+            tmp_ids[b + off++] = (uint16_t)((threadIdx.x * 8 + w) * 32 + bpos);
+        }
+    }
+    if (threadIdx.x == 255) len[r] = off;
+}
+
+// Final layout (BF::switch_mode(2), bloomfilter.h:126-168): ids concatenated in rank order
+// (`_index_kmer`), offsets (= select over `_bv`), and the 8-byte entry per set bit.
+__global__ void __launch_bounds__(256)
+finalize_lists_kernel(const uint32_t *__restrict__ tmp_off, const uint16_t *__restrict__ tmp_ids,
+                      const uint32_t *__restrict__ csr_off, uint32_t n_set, uint16_t *csr_ids, uint64_t *entries)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_set) return;
+    uint32_t o = csr_off[r], m = csr_off[r + 1] - o;
+    const uint16_t *src = tmp_ids + tmp_off[r];
+    if (m == 0) {
+        entries[r] = 0;
+        return;
+    }
+    for (uint32_t t = 0; t < m; ++t) csr_ids[o + t] = src[t];
+    uint32_t id0 = src[0];
+    uint32_t lo = m == 1 ? 0u : (m == 2 ? (uint32_t)src[1] : o);
+    entries[r] = make_entry(id0, m, lo);
+}
+
+// Logical positions of the set bits in rank order (for shk_index_export).
+__global__ void __launch_bounds__(256)
+export_positions_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, uint64_t *pos)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sectors) return;
+    const uint4 *sp = reinterpret_cast<const uint4 *>(sectors + s * 8);
+    uint4 a = sp[0], b = sp[1];
+    uint32_t w[7] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z};
+    uint32_t r = b.w;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        uint32_t bits = w[i];
+        while (bits) {
+            int bpos = __ffs(bits) - 1;
+            bits &= bits - 1;
+            pos[r++] = (s * kWordsPerSector + i) * 32 + bpos;
+        }
+    }
+}
+
+// =============================================================================================
+// Host orchestration of the build.
+// =============================================================================================
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(uint64_t n) { return cudaMalloc((void **)&p, std::max<uint64_t>(n, 1) * sizeof(T)); }
+    T *release()
+    {
+        T *q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
+static void free_index_arrays(DeviceIndex &ix)
+{
+    if (ix.entries) cudaFree(ix.entries);
+    if (ix.csr_off) cudaFree(ix.csr_off);
+    if (ix.csr_ids) cudaFree(ix.csr_ids);
+    ix.entries = nullptr;
+    ix.csr_off = nullptr;
+    ix.csr_ids = nullptr;
+    ix.built = false;
+}
+
+template <int MOD>
+static void launch_enum(shk_ctx *ctx, cudaStream_t st, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec,
+                        uint64_t total, uint64_t *win_pos, uint32_t *has_window, unsigned long long *n_windows)
+{
+    uint64_t threads = (total + kPosPerThread - 1) / kPosPerThread;
+    unsigned blocks = (unsigned)((threads + 255) / 256);
+    enum_setbits_kernel<MOD><<<blocks, 256, 0, st>>>(bases, rec_off, n_rec, total, (int)ctx->params.k, ctx->index.geom,
+                                                      ctx->index.sectors, win_pos, has_window, n_windows);
+    ctx->launches += 1;
+}
+
+int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_rec)
+{
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    const uint64_t total = rec_off[n_rec];
+    if (total >= (1ULL << 32)) return fail(ctx, SHK_E_LIMIT, "reference larger than 4 Gbases is not supported");
+    for (uint32_t i = 0; i < n_rec; ++i)
+        if (rec_off[i + 1] < rec_off[i]) return fail(ctx, SHK_E_ARG, "rec_offsets must be non-decreasing");
+    free_index_arrays(ix);
+    const uint64_t sector_bytes = ix.geom.n_sectors * 32;
+
+    cudaEvent_t e0, e1;
+    SHK_CUDA(ctx, cudaEventCreate(&e0));
+    SHK_CUDA(ctx, cudaEventCreate(&e1));
+    SHK_CUDA(ctx, cudaEventRecord(e0, st));
+
+    DevBuf<uint8_t> d_bases;
+    DevBuf<uint64_t> d_rec_off, d_win;
+    DevBuf<uint32_t> d_has, d_nidx, d_scalars, d_tiles;
+    DevBuf<unsigned long long> d_nwin;
+    SHK_CUDA(ctx, d_bases.alloc(total));
+    SHK_CUDA(ctx, d_rec_off.alloc((uint64_t)n_rec + 1));
+    SHK_CUDA(ctx, d_win.alloc(total));
+    SHK_CUDA(ctx, d_has.alloc(n_rec));
+    SHK_CUDA(ctx, d_nidx.alloc(n_rec));
+    SHK_CUDA(ctx, d_scalars.alloc(8));  // 0 n_genes, 1 n_set, 2 n_occ, 3 tot_ids, 4 n_long
+    SHK_CUDA(ctx, d_nwin.alloc(1));
+    uint64_t max_scan_n = std::max<uint64_t>(ix.geom.n_sectors, total + 1);
+    SHK_CUDA(ctx, d_tiles.alloc(max_scan_n / kScanTile + 2));
+    SHK_CUDA(ctx, cudaMemcpyAsync(d_bases.p, ref_bases, total, cudaMemcpyHostToDevice, st));
+    SHK_CUDA(ctx, cudaMemcpyAsync(d_rec_off.p, rec_off, ((uint64_t)n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    SHK_CUDA(ctx, cudaMemsetAsync(ix.sectors, 0, sector_bytes, st));
+    SHK_CUDA(ctx, cudaMemsetAsync(d_has.p, 0, std::max<uint64_t>(n_rec, 1) * 4, st));
+    SHK_CUDA(ctx, cudaMemsetAsync(d_scalars.p, 0, 8 * 4, st));
+    SHK_CUDA(ctx, cudaMemsetAsync(d_nwin.p, 0, 8, st));
+
+    // pass 1
+    if (total > 0) {
+        switch (ix.geom.mod_kind) {
+        case MOD_POW2: launch_enum<MOD_POW2>(ctx, st, d_bases.p, d_rec_off.p, n_rec, total, d_win.p, d_has.p, d_nwin.p); break;
+        case MOD_B33: launch_enum<MOD_B33>(ctx, st, d_bases.p, d_rec_off.p, n_rec, total, d_win.p, d_has.p, d_nwin.p); break;
+        default: launch_enum<MOD_GENERIC>(ctx, st, d_bases.p, d_rec_off.p, n_rec, total, d_win.p, d_has.p, d_nwin.p); break;
+        }
+        SHK_CUDA(ctx, cudaGetLastError());
+    }
+    assign_nidx_kernel<<<1, 1024, 0, st>>>(d_rec_off.p, d_has.p, n_rec, (int)ctx->params.k, d_nidx.p, d_scalars.p + 0);
+    ctx->launches += 1;
+    // switch_mode(1): rank directory (bloomfilter.h:121-122)
+    int rc = exclusive_scan(ctx, st, SectorPopIn{ix.sectors}, SectorRankOut{ix.sectors}, ix.geom.n_sectors, d_tiles.p,
+                            d_scalars.p + 1);
+    if (rc) return rc;
+    uint32_t h_scalars[8];
+    unsigned long long h_nwin = 0;
+    SHK_CUDA(ctx, cudaMemcpyAsync(h_scalars, d_scalars.p, sizeof h_scalars, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaMemcpyAsync(&h_nwin, d_nwin.p, 8, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t n_genes = h_scalars[0];
+    const uint32_t n_set = h_scalars[1];
+    if (n_genes > 65536)
+        return fail(ctx, SHK_E_LIMIT,
+                    "%u gene indices: the reference stores gene ids in 16 bits (small_vector.hpp:46), "
+                    "more than 65536 is not supported",
+                    n_genes);
+    if (n_set >= 0x7FFFFFFFu || h_nwin >= 0xFFFFFFFFull) return fail(ctx, SHK_E_LIMIT, "too many set bits / windows");
+
+    // pass 2
+    DevBuf<uint32_t> d_cnt, d_fill, d_tmp_off, d_long;
+    DevBuf<uint16_t> d_tmp_ids;
+    DevBuf<uint32_t> d_csr_off;
+    DevBuf<uint16_t> d_csr_ids;
+    DevBuf<uint64_t> d_entries;
+    SHK_CUDA(ctx, d_cnt.alloc((uint64_t)n_set + 1));
+    SHK_CUDA(ctx, d_fill.alloc((uint64_t)n_set + 1));
+    SHK_CUDA(ctx, d_tmp_off.alloc((uint64_t)n_set + 1));
+    SHK_CUDA(ctx, d_long.alloc((uint64_t)n_set + 1));
+    SHK_CUDA(ctx, d_tmp_ids.alloc(h_nwin + 1));
+    SHK_CUDA(ctx, d_csr_off.alloc((uint64_t)n_set + 1));
+    SHK_CUDA(ctx, d_entries.alloc((uint64_t)n_set + 1));
+    SHK_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, ((uint64_t)n_set + 1) * 4, st));
+    SHK_CUDA(ctx, cudaMemsetAsync(d_fill.p, 0, ((uint64_t)n_set + 1) * 4, st));
+    uint64_t tot_ids = 0;
+    if (n_set > 0) {
+        unsigned blocks_x = (unsigned)((total + 255) / 256);
+        unsigned blocks_r = (unsigned)(((uint64_t)n_set + 255) / 256);
+        rank_count_kernel<<<blocks_x, 256, 0, st>>>(d_win.p, total, ix.sectors, d_cnt.p);
+        ctx->launches += 1;
+        rc = exclusive_scan(ctx, st, U32In{d_cnt.p}, U32Out{d_tmp_off.p}, (uint64_t)n_set, d_tiles.p, d_tmp_off.p + n_set);
+        if (rc) return rc;
+        fill_kernel<<<blocks_x, 256, 0, st>>>(d_win.p, total, d_rec_off.p, n_rec, d_nidx.p, d_tmp_off.p, d_fill.p,
+                                              d_tmp_ids.p);
+        // d_fill is reused as the final length of each list
+        sort_unique_kernel<<<blocks_r, 256, 0, st>>>(d_tmp_off.p, n_set, d_tmp_ids.p, d_fill.p, d_long.p, d_scalars.p + 4);
+        ctx->launches += 2;
+        SHK_CUDA(ctx, cudaMemcpyAsync(h_scalars, d_scalars.p, sizeof h_scalars, cudaMemcpyDeviceToHost, st));
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h_scalars[4] > 0) {
+            sort_unique_long_kernel<<<h_scalars[4], 256, 0, st>>>(d_tmp_off.p, d_long.p, d_tmp_ids.p, d_fill.p);
+            ctx->launches += 1;
+        }
+        rc = exclusive_scan(ctx, st, U32In{d_fill.p}, U32Out{d_csr_off.p}, (uint64_t)n_set, d_tiles.p, d_csr_off.p + n_set);
+        if (rc) return rc;
+        uint32_t h_tot = 0;
+        SHK_CUDA(ctx, cudaMemcpyAsync(&h_tot, d_csr_off.p + n_set, 4, cudaMemcpyDeviceToHost, st));
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+        tot_ids = h_tot;
+        if (tot_ids >= 0x7FFFFFFFull)
+            return fail(ctx, SHK_E_LIMIT, "total id count overflows the reference's int (bloomfilter.h:130)");
+        SHK_CUDA(ctx, d_csr_ids.alloc(tot_ids));
+        finalize_lists_kernel<<<blocks_r, 256, 0, st>>>(d_tmp_off.p, d_tmp_ids.p, d_csr_off.p, n_set, d_csr_ids.p,
+                                                        d_entries.p);
+        ctx->launches += 1;
+        SHK_CUDA(ctx, cudaGetLastError());
+    } else {
+        SHK_CUDA(ctx, cudaMemsetAsync(d_csr_off.p, 0, 4, st));
+        SHK_CUDA(ctx, d_csr_ids.alloc(1));
+    }
+    SHK_CUDA(ctx, cudaEventRecord(e1, st));
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+
+    ix.entries = d_entries.release();
+    ix.csr_off = d_csr_off.release();
+    ix.csr_ids = d_csr_ids.release();
+    ix.info.n_records = n_rec;
+    ix.info.n_genes = n_genes;
+    ix.info.n_set_bits = n_set;
+    ix.info.tot_ids = tot_ids;
+    ix.info.n_windows = h_nwin;
+    ix.info.bf_bits = ix.geom.bf_bits;
+    ix.info.device_bytes = sector_bytes + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2;
+    ix.info.build_ms = ms;
+    ix.built = true;
+    return SHK_OK;
+}
+
+int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *ids)
+{
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    const uint64_t n_set = ix.info.n_set_bits;
+    if (pos && n_set) {
+        DevBuf<uint64_t> d_pos;
+        SHK_CUDA(ctx, d_pos.alloc(n_set));
+        unsigned blocks = (unsigned)((ix.geom.n_sectors + 255) / 256);
+        export_positions_kernel<<<blocks, 256, 0, st>>>(ix.sectors, ix.geom.n_sectors, d_pos.p);
+        ctx->launches += 1;
+        SHK_CUDA(ctx, cudaGetLastError());
+        SHK_CUDA(ctx, cudaMemcpyAsync(pos, d_pos.p, n_set * 8, cudaMemcpyDeviceToHost, st));
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (off) SHK_CUDA(ctx, cudaMemcpyAsync(off, ix.csr_off, (n_set + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (ids && ix.info.tot_ids)
+        SHK_CUDA(ctx, cudaMemcpyAsync(ids, ix.csr_ids, ix.info.tot_ids * 2, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    return SHK_OK;
+}
+
+// =============================================================================================
+// K5: stand-alone probe = BF::get_index (bloomfilter.h:78-102), one thread per k-mer.
+// =============================================================================================
+template <int MOD>
+__global__ void __launch_bounds__(256)
+probe_kernel(const uint64_t *__restrict__ kmers, uint64_t n, FilterGeom g, const uint32_t *__restrict__ sectors,
+             const uint32_t *__restrict__ csr_off, long long *rank, uint32_t *begin, uint32_t *len)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t p = bit_index<MOD>(xxh64_u64(kmers[i]), g);
+    uint64_t q = p >> 5;
+    uint64_t sec = q / kWordsPerSector;
+    uint32_t slot = (uint32_t)(q - sec * kWordsPerSector), bit = (uint32_t)(p & 31);
+    Sector s = ld_sector(reinterpret_cast<const Sector *>(sectors) + sec);
+    if ((s.w[slot] >> bit) & 1u) {  // `_bf[bf_idx]`
+        uint32_t r = sector_rank(s, slot, bit);  // `_brank(bf_idx + 1) - 1`
+        rank[i] = r;
+        uint32_t b = csr_off[r];  // `_select_bv(rank - 1) + 1`
+        begin[i] = b;
+        len[i] = csr_off[r + 1] - b;  // `_select_bv(rank)` inclusive end
+    } else {
+        rank[i] = -1;
+        begin[i] = 0;
+        len[i] = 0;
+    }
+}
+
+int probe_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int64_t *rank, uint32_t *begin, uint32_t *len)
+{
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    if (n == 0) return SHK_OK;
+    DevBuf<uint64_t> d_k;
+    DevBuf<long long> d_rank;
+    DevBuf<uint32_t> d_begin, d_len;
+    SHK_CUDA(ctx, d_k.alloc(n));
+    SHK_CUDA(ctx, d_rank.alloc(n));
+    SHK_CUDA(ctx, d_begin.alloc(n));
+    SHK_CUDA(ctx, d_len.alloc(n));
+    SHK_CUDA(ctx, cudaMemcpyAsync(d_k.p, kmers, n * 8, cudaMemcpyHostToDevice, st));
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    switch (ix.geom.mod_kind) {
+    case MOD_POW2: probe_kernel<MOD_POW2><<<blocks, 256, 0, st>>>(d_k.p, n, ix.geom, ix.sectors, ix.csr_off, d_rank.p, d_begin.p, d_len.p); break;
+    case MOD_B33: probe_kernel<MOD_B33><<<blocks, 256, 0, st>>>(d_k.p, n, ix.geom, ix.sectors, ix.csr_off, d_rank.p, d_begin.p, d_len.p); break;
+    default: probe_kernel<MOD_GENERIC><<<blocks, 256, 0, st>>>(d_k.p, n, ix.geom, ix.sectors, ix.csr_off, d_rank.p, d_begin.p, d_len.p); break;
+    }
+    ctx->launches += 1;
+    SHK_CUDA(ctx, cudaGetLastError());
+    SHK_CUDA(ctx, cudaMemcpyAsync(rank, d_rank.p, n * 8, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaMemcpyAsync(begin, d_begin.p, n * 4, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaMemcpyAsync(len, d_len.p, n * 4, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    return SHK_OK;
+}
+
+// Probe throughput on resident k-mers, through the hot path's own access sequence:
+// one filter word (32 B sector) -> on a hit the whole sector (rank) -> the 8-byte entry.
+template <int MOD>
+__global__ void __launch_bounds__(256)
+probe_bench_kernel(const uint64_t *__restrict__ kmers, uint64_t n, FilterGeom g, const uint32_t *__restrict__ sectors,
+                   const uint64_t *__restrict__ entries, unsigned long long *hits, unsigned long long *checksum)
+{
+    constexpr int ILP = 4;
+    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t my_hits = 0;
+    uint64_t acc = 0;
+    for (uint64_t i = i0; i < n; i += stride * ILP) {
+        uint64_t p[ILP];
+        uint32_t w[ILP];
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            uint64_t idx = i + (uint64_t)j * stride;
+            p[j] = idx < n ? bit_index<MOD>(xxh64_u64(kmers[idx]), g) : kInvalidPos;
+        }
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) w[j] = p[j] != kInvalidPos ? ld_filter_word(sectors + phys_word(p[j]), pol_first) : 0u;
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            if (p[j] != kInvalidPos && ((w[j] >> (p[j] & 31)) & 1u)) {
+                uint64_t q = p[j] >> 5, sec = q / kWordsPerSector;
+                Sector s = ld_sector(reinterpret_cast<const Sector *>(sectors) + sec);
+                uint32_t r = sector_rank(s, (uint32_t)(q - sec * kWordsPerSector), (uint32_t)(p[j] & 31));
+                acc += ld_u64_hint(entries + r, pol_last);
+                ++my_hits;
+            }
+        }
+    }
+    my_hits = __reduce_add_sync(0xFFFFFFFFu, my_hits);
+    if ((threadIdx.x & 31) == 0) {
+        if (my_hits) atomicAdd(hits, (unsigned long long)my_hits);
+    }
+    if (acc == 0x1234567ULL) atomicAdd(checksum, acc);  // keeps the entry loads alive
+}
+
+int probe_bench_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, uint32_t reps, float *ms, uint64_t *hits)
+{
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    DevBuf<uint64_t> d_k;
+    DevBuf<unsigned long long> d_c;
+    SHK_CUDA(ctx, d_k.alloc(n));
+    SHK_CUDA(ctx, d_c.alloc(2));
+    SHK_CUDA(ctx, cudaMemcpyAsync(d_k.p, kmers, n * 8, cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1;
+    SHK_CUDA(ctx, cudaEventCreate(&e0));
+    SHK_CUDA(ctx, cudaEventCreate(&e1));
+    unsigned blocks = (unsigned)ctx->sm_count * 8;
+    float best = 1e30f;
+    for (uint32_t r = 0; r < reps + 1; ++r) {  // first repetition is the warm-up
+        SHK_CUDA(ctx, cudaMemsetAsync(d_c.p, 0, 16, st));
+        SHK_CUDA(ctx, cudaEventRecord(e0, st));
+        switch (ix.geom.mod_kind) {
+        case MOD_POW2: probe_bench_kernel<MOD_POW2><<<blocks, 256, 0, st>>>(d_k.p, n, ix.geom, ix.sectors, ix.entries, d_c.p, d_c.p + 1); break;
+        case MOD_B33: probe_bench_kernel<MOD_B33><<<blocks, 256, 0, st>>>(d_k.p, n, ix.geom, ix.sectors, ix.entries, d_c.p, d_c.p + 1); break;
+        default: probe_bench_kernel<MOD_GENERIC><<<blocks, 256, 0, st>>>(d_k.p, n, ix.geom, ix.sectors, ix.entries, d_c.p, d_c.p + 1); break;
+        }
+        ctx->launches += 1;
+        SHK_CUDA(ctx, cudaEventRecord(e1, st));
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+        float t = 0;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (r > 0 && t < best) best = t;
+    }
+    unsigned long long h[2] = {0, 0};
+    SHK_CUDA(ctx, cudaMemcpy(h, d_c.p, 16, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = best;
+    if (hits) *hits = h[0];
+    return SHK_OK;
+}
+
+// =============================================================================================
+// B0: random 32-byte-sector loads over the filter allocation = the measured ceiling that the
+// probe throughput is normalised by.  Independent addresses (splitmix64 of a
+// counter), 8 loads in flight per thread, whole sector consumed.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+random_sector_kernel(const Sector *__restrict__ base, uint64_t n_sectors, uint64_t n_loads, uint64_t seed,
+                     unsigned long long *sink)
+{
+    constexpr int ILP = 8;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t acc = 0;
+    for (uint64_t i = i0; i < n_loads; i += stride * ILP) {
+        Sector s[ILP];
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            uint64_t idx = i + (uint64_t)j * stride;
+            uint64_t a = __umul64hi(splitmix64(seed + idx), n_sectors);  // uniform in [0, n_sectors)
+            if (idx < n_loads) s[j] = ld_sector(base + a);
+            else s[j].w[0] = s[j].w[7] = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) acc ^= s[j].w[0] ^ s[j].w[7];
+    }
+    if (acc == 0x9E3779B9u) atomicAdd(sink, 1ULL);
+}
+
+int random_sector_bench_device(shk_ctx *ctx, uint64_t n_loads, uint64_t span_bytes, uint64_t seed, float *ms)
+{
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    uint64_t n_sectors = ix.geom.n_sectors;
+    if (span_bytes && span_bytes / 32 < n_sectors) n_sectors = span_bytes / 32;
+    if (n_sectors == 0) return fail(ctx, SHK_E_ARG, "empty span");
+    DevBuf<unsigned long long> d_sink;
+    SHK_CUDA(ctx, d_sink.alloc(1));
+    SHK_CUDA(ctx, cudaMemsetAsync(d_sink.p, 0, 8, st));
+    cudaEvent_t e0, e1;
+    SHK_CUDA(ctx, cudaEventCreate(&e0));
+    SHK_CUDA(ctx, cudaEventCreate(&e1));
+    unsigned blocks = (unsigned)ctx->sm_count * 8;
+    float best = 1e30f;
+    for (int r = 0; r < 4; ++r) {
+        SHK_CUDA(ctx, cudaEventRecord(e0, st));
+        random_sector_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const Sector *>(ix.sectors), n_sectors, n_loads,
+                                                     seed + (uint64_t)r * n_loads, d_sink.p);
+        ctx->launches += 1;
+        SHK_CUDA(ctx, cudaEventRecord(e1, st));
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+        float t = 0;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (r > 0 && t < best) best = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = best;
+    return SHK_OK;
+}
+
+}  // namespace shk

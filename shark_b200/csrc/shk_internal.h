@@ -1,0 +1,149 @@
+// Host-side internals shared by the translation units of libshark_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/shark_b200.h"
+#include "shk_device.cuh"
+
+namespace shk {
+
+// Device-resident index (the reference's class BF in mode 2, bloomfilter.h:36-203).
+struct DeviceIndex {
+    FilterGeom geom{};
+    uint32_t *sectors = nullptr;  // n_sectors * 8 words (filter bits + in-sector rank)
+    uint64_t *entries = nullptr;  // one per set bit
+    uint32_t *csr_off = nullptr;  // n_set + 1
+    uint16_t *csr_ids = nullptr;  // tot_ids
+    shk_index_info info{};
+    bool built = false;
+};
+
+// Counters the classification kernels maintain per chunk (device, mirrored to pinned host).
+struct ChunkCounters {
+    unsigned long long n_probes;
+    unsigned long long n_hits;
+    unsigned long long n_assoc;
+    unsigned int pool_used;   // entries of the tie pool in use
+    unsigned int n_slow;      // reads queued for the exact large-table path
+    unsigned int pool_overflow;
+    unsigned int pad;
+};
+
+struct ReadKernelArgs {
+    // inputs
+    const uint8_t *seq;
+    const uint8_t *qual;  // nullptr when min_quality == 0
+    const uint32_t *off;
+    uint32_t n_reads;
+    // index
+    const uint32_t *sectors;
+    const uint64_t *entries;
+    const uint32_t *csr_off;
+    const uint16_t *csr_ids;
+    FilterGeom geom;
+    uint32_t n_genes;
+    // options
+    int k;
+    double c;
+    int mq;  // (signed char)(min_quality + 33), FastqSplitter.hpp:75
+    int single;
+    // outputs
+    uint2 *rec;              // per read: x = association count, y = gene id (count==1) or pool offset
+    uint32_t *pool;          // winners of reads with >= 2 associations, ascending gene id
+    uint32_t pool_cap;
+    uint32_t *slow_list;     // read indices for the exact path
+    uint32_t *tile_sums;     // associations per tile of kReadsPerTile reads
+    ChunkCounters *counters;
+    // exact-path scratch
+    uint4 *slow_table;       // n_slow_slabs * n_genes entries {stamp, cov, hits, last}
+    uint32_t *slow_stamp;    // per slab
+    uint32_t n_slow_slabs;
+    // compaction outputs
+    uint32_t *tile_base;
+    shk_assoc *assoc;
+    uint8_t *keep;
+};
+
+constexpr uint32_t kReadsPerTile = 64;  // one CTA of 8 warps x 8 reads
+constexpr uint32_t kMaxFastLen = 1024;  // longer reads take the exact path (32 chunks x 32)
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    // device
+    uint8_t *d_seq = nullptr, *d_qual = nullptr;
+    uint32_t *d_off = nullptr;
+    uint2 *d_rec = nullptr;
+    uint32_t *d_pool = nullptr;
+    uint32_t pool_cap = 0;
+    uint32_t *d_slow_list = nullptr;
+    uint32_t *d_tile_sums = nullptr, *d_tile_base = nullptr;
+    ChunkCounters *d_counters = nullptr;
+    shk_assoc *d_assoc = nullptr;
+    uint64_t assoc_cap = 0;
+    uint8_t *d_keep = nullptr;
+    // pinned host
+    ChunkCounters *h_counters = nullptr;
+    shk_assoc *h_assoc = nullptr;
+    uint64_t h_assoc_cap = 0;
+    uint8_t *h_keep = nullptr;
+    // state
+    uint32_t n_reads = 0;
+    uint64_t n_bytes = 0;
+    bool has_qual = false;
+    bool pending = false;
+    uint32_t launches = 0;
+};
+
+}  // namespace shk
+
+struct shk_ctx {
+    shk_params params{};
+    int device = 0;
+    int sm_count = 148;
+    shk::DeviceIndex index;
+    shk::Slot *slots = nullptr;
+    uint32_t n_slots = 0;
+    uint32_t max_reads = 0;
+    uint64_t max_bytes = 0;
+    uint4 *d_slow_table = nullptr;
+    uint32_t *d_slow_stamp = nullptr;
+    uint32_t n_slow_slabs = 0;
+    std::atomic<uint64_t> launches{0};
+    cudaStream_t build_stream = nullptr;
+    char err[512] = {0};
+};
+
+namespace shk {
+
+void set_global_error(const char *msg);
+int fail(shk_ctx *ctx, int code, const char *fmt, ...);
+
+#define SHK_CUDA(ctx, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return shk::fail(ctx, SHK_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                             __FILE__, __LINE__);                                                        \
+    } while (0)
+
+// shk_index.cu
+int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_records);
+int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *ids);
+int probe_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int64_t *rank, uint32_t *begin, uint32_t *len);
+int probe_bench_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, uint32_t reps, float *ms, uint64_t *hits);
+int random_sector_bench_device(shk_ctx *ctx, uint64_t n_loads, uint64_t span_bytes, uint64_t seed, float *ms);
+
+// shk_reads.cu
+// Enqueues the classification kernels of one chunk on `st`; returns the number of launches.
+int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st, cudaEvent_t ev_k0,
+                        cudaEvent_t ev_k1);
+int launch_scatter(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st);
+
+}  // namespace shk

@@ -1,0 +1,222 @@
+"""Host-side mirror of the reference's hot-path interface on top of the C ABI.
+
+`Shark` owns one context (= one GPU).  Its methods follow the reference's stages:
+  build_index   = pass 1 + BF::switch_mode(1) + pass 2 + BF::switch_mode(2)   (main.cpp:128-193)
+  get_index     = BF::get_index                                               (bloomfilter.h:78-102)
+  analyze       = FastqSplitter masking + ReadAnalyzer::operator()            (ReadAnalyzer.hpp:39-110)
+All compute happens in libshark_b200.so; nothing here touches oracle/.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class Shark:
+    def __init__(self, k=17, c=0.6, bf_bits=1 << 33, min_quality=0, single=False, device=0, n_slots=2,
+                 max_reads_per_chunk=1 << 20, max_bytes_per_chunk=0):
+        self.lib = capi.load()
+        self.params = capi.Params(k=k, c=c, bf_bits=bf_bits, min_quality=min_quality, single=int(bool(single)),
+                                  device=device, n_slots=n_slots, max_reads_per_chunk=max_reads_per_chunk,
+                                  max_bytes_per_chunk=max_bytes_per_chunk)
+        self.ctx = C.c_void_p()
+        rc = self.lib.shk_create(C.byref(self.params), C.byref(self.ctx))
+        if rc:
+            raise capi.SharkError(rc, self.lib.shk_last_error(None).decode())
+        self.k, self.c, self.bf_bits = k, c, bf_bits
+        self.min_quality, self.single = min_quality, bool(single)
+        self.n_slots = n_slots
+        self.max_reads = max_reads_per_chunk
+        self.max_bytes = max_bytes_per_chunk or 320 * max_reads_per_chunk
+        self.info = None
+        self._staging = {}
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.shk_destroy(self.ctx)
+            self.ctx = None
+        for b in getattr(self, "_staging", {}).values():
+            b.free()
+        self._staging = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise capi.SharkError(rc, self.lib.shk_last_error(self.ctx).decode())
+
+    # -- index ------------------------------------------------------------------------------
+    def build_index(self, bases, rec_off):
+        """bases: uint8 concatenated record sequences as parsed; rec_off: uint64[n_records+1]."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        info = capi.IndexInfo()
+        self._check(self.lib.shk_index_build(self.ctx, capi.ptr(bases) if len(bases) else None, capi.ptr(rec_off),
+                                             len(rec_off) - 1, C.byref(info)))
+        self.info = info
+        return info
+
+    def export_index(self):
+        """-> (set_bit_pos uint64[n_set], offsets uint32[n_set+1], ids uint16[tot_ids])"""
+        n, t = self.info.n_set_bits, self.info.tot_ids
+        pos = np.zeros(n, np.uint64)
+        off = np.zeros(n + 1, np.uint32)
+        ids = np.zeros(t, np.uint16)
+        self._check(self.lib.shk_index_export(self.ctx, capi.ptr(pos) if n else None, capi.ptr(off),
+                                              capi.ptr(ids) if t else None))
+        return pos, off, ids
+
+    def index_views(self):
+        v = capi.IndexViews()
+        self._check(self.lib.shk_index_views_get(self.ctx, C.byref(v)))
+        return v
+
+    def adopt_index(self, info):
+        self._check(self.lib.shk_index_adopt(self.ctx, C.byref(info)))
+        self.info = info
+
+    def finalize_index(self):
+        self._check(self.lib.shk_index_finalize(self.ctx))
+
+    def get_index(self, kmers):
+        """BF::get_index for canonical k-mers -> (rank int64 (-1 = miss), begin uint32, len uint32)."""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        n = len(kmers)
+        rank = np.zeros(n, np.int64)
+        begin = np.zeros(n, np.uint32)
+        ln = np.zeros(n, np.uint32)
+        if n:
+            self._check(self.lib.shk_probe(self.ctx, capi.ptr(kmers), n, capi.ptr(rank), capi.ptr(begin), capi.ptr(ln)))
+        return rank, begin, ln
+
+    def probe_bench(self, kmers, reps=3):
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        ms, hits = C.c_float(), C.c_uint64()
+        self._check(self.lib.shk_probe_bench(self.ctx, capi.ptr(kmers), len(kmers), reps, C.byref(ms), C.byref(hits)))
+        return ms.value, hits.value
+
+    def random_sector_bench(self, n_loads, span_bytes=0, seed=1):
+        ms = C.c_float()
+        self._check(self.lib.shk_random_sector_bench(self.ctx, n_loads, span_bytes, seed, C.byref(ms)))
+        return ms.value
+
+    # -- reads ------------------------------------------------------------------------------
+    def submit(self, slot, seq, qual, off32, n_reads):
+        self._check(self.lib.shk_reads_submit(self.ctx, slot, capi.ptr(seq), capi.ptr(qual) if qual is not None else None,
+                                              capi.ptr(off32), n_reads))
+
+    def upload(self, slot, seq, qual, off32, n_reads):
+        self._check(self.lib.shk_reads_upload(self.ctx, slot, capi.ptr(seq), capi.ptr(qual) if qual is not None else None,
+                                              capi.ptr(off32), n_reads))
+
+    def analyze_resident(self, slot):
+        self._check(self.lib.shk_reads_analyze_resident(self.ctx, slot))
+
+    def collect(self, slot, copy=True):
+        """-> dict(read_idx, gene_idx, keep, n_probes, n_hits, analyze_ms, ...)"""
+        res = capi.ChunkResult()
+        self._check(self.lib.shk_reads_collect(self.ctx, slot, C.byref(res)))
+        n = res.n_assoc
+        if n:
+            a = np.ctypeslib.as_array(C.cast(res.assoc, C.POINTER(C.c_uint32)), shape=(n, 2))
+        else:
+            a = np.zeros((0, 2), np.uint32)
+        keep = np.ctypeslib.as_array(res.keep, shape=(max(res.n_reads, 1),))[: res.n_reads]
+        if copy:
+            a, keep = a.copy(), keep.copy()
+        return dict(read_idx=a[:, 0], gene_idx=a[:, 1], keep=keep, n_assoc=int(n), n_reads=res.n_reads,
+                    n_slow_reads=res.n_slow_reads, n_probes=res.n_probes, n_hits=res.n_hits,
+                    analyze_ms=res.analyze_ms, total_ms=res.total_ms, kernel_launches=res.kernel_launches)
+
+    def kernel_launches(self):
+        return int(self.lib.shk_kernel_launches(self.ctx))
+
+    def _stage(self, slot, nbytes_seq, n_reads, with_qual):
+        key = slot
+        need = (nbytes_seq, n_reads, with_qual)
+        cur = self._staging.get(key)
+        if cur is None or cur[0][0] < nbytes_seq or cur[0][1] < n_reads or (with_qual and not cur[0][2]):
+            if cur is not None:
+                for b in cur[1]:
+                    if b is not None:
+                        b.free()
+            cap_b = max(nbytes_seq, 1 << 16)
+            cap_r = max(n_reads, 1 << 10)
+            bufs = (capi.PinnedBuffer(cap_b), capi.PinnedBuffer(cap_b) if with_qual else None,
+                    capi.PinnedBuffer((cap_r + 1) * 4))
+            cur = ((cap_b, cap_r, with_qual), bufs)
+            self._staging[key] = cur
+        return cur[1]
+
+    def plan_chunks(self, off):
+        """Splits reads [0, n) into chunks that fit a slot -> list of (first, last) read indices."""
+        off = np.asarray(off)
+        n = len(off) - 1
+        chunks, i = [], 0
+        while i < n:
+            j = min(i + self.max_reads, n)
+            if int(off[j]) - int(off[i]) > self.max_bytes:
+                j = int(np.searchsorted(off, int(off[i]) + self.max_bytes, side="right")) - 1
+                if j <= i:
+                    raise capi.SharkError(-4, "read %d alone exceeds max_bytes_per_chunk" % i)
+            chunks.append((i, j))
+            i = j
+        return chunks
+
+    def analyze(self, seq, off, qual=None):
+        """Classifies reads given as SoA (seq uint8, off uint64/uint32 [n+1], qual uint8|None):
+        chunks them, streams the chunks through the slots (pinned staging, double buffered) and
+        returns (keep uint8[n], assoc_read uint64[m], assoc_gene uint32[m], stats)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(off)
+        n = len(off) - 1
+        with_qual = (self.min_quality & 0xFF) != 0
+        if with_qual and qual is None:
+            raise capi.SharkError(-1, "min_quality != 0 needs qualities")
+        keep = np.zeros(n, np.uint8)
+        out_r, out_g = [], []
+        stats = dict(n_probes=0, n_hits=0, analyze_ms=0.0, n_slow_reads=0, kernel_launches=0, chunks=0)
+        chunks = self.plan_chunks(off) if n else []
+        pending = []
+
+        def drain():
+            slot, first = pending.pop(0)
+            r = self.collect(slot)
+            keep[first:first + r["n_reads"]] = r["keep"]
+            out_r.append(r["read_idx"].astype(np.uint64) + np.uint64(first))
+            out_g.append(r["gene_idx"])
+            for key in ("n_probes", "n_hits", "analyze_ms", "n_slow_reads", "kernel_launches"):
+                stats[key] += r[key]
+            stats["chunks"] += 1
+
+        for ci, (a, b) in enumerate(chunks):
+            slot = ci % self.n_slots
+            if len(pending) == self.n_slots:
+                drain()
+            base = int(off[a])
+            nb = int(off[b]) - base
+            s_seq, s_qual, s_off = self._stage(slot, nb, b - a, with_qual)
+            s_seq.u8[:nb] = seq[base:base + nb]
+            if with_qual:
+                s_qual.u8[:nb] = qual[base:base + nb]
+            o32 = s_off.view(np.uint32, b - a + 1)
+            o32[:] = (off[a:b + 1] - off[a]).astype(np.uint32)
+            self.submit(slot, s_seq.u8, s_qual.u8 if with_qual else None, o32, b - a)
+            pending.append((slot, a))
+        while pending:
+            drain()
+        ar = np.concatenate(out_r) if out_r else np.zeros(0, np.uint64)
+        ag = np.concatenate(out_g) if out_g else np.zeros(0, np.uint32)
+        return keep, ar, ag, stats
