@@ -87,7 +87,7 @@ typedef struct shk_chunk_result {
     float analyze_ms;       /* device time of the classification kernels (CUDA events)             */
     float total_ms;         /* device time H2D + kernels + D2H of counters                         */
     uint32_t kernel_launches;
-    uint32_t reserved;
+    float probe_kernel_ms;  /* device time of the dominant kernel alone (analyze_reads_kernel)     */
 } shk_chunk_result;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

@@ -53,7 +53,7 @@ class ChunkResult(C.Structure):
     _fields_ = [("n_assoc", C.c_uint64), ("assoc", C.POINTER(Assoc)), ("keep", C.POINTER(C.c_uint8)),
                 ("n_reads", C.c_uint32), ("n_slow_reads", C.c_uint32), ("n_probes", C.c_uint64), ("n_hits", C.c_uint64),
                 ("analyze_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("probe_kernel_ms", C.c_float)]
 
 
 _lib = None

@@ -41,11 +41,14 @@ static void free_slot(Slot &s)
     cudaFree(s.d_counters);
     cudaFree(s.d_assoc);
     cudaFree(s.d_keep);
+    cudaFree(s.d_slow_table);
+    cudaFree(s.d_slow_stamp);
     cudaFreeHost(s.h_counters);
     cudaFreeHost(s.h_assoc);
     cudaFreeHost(s.h_keep);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_ka) cudaEventDestroy(s.ev_ka);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -59,6 +62,7 @@ static int alloc_slot(shk_ctx *ctx, Slot &s)
     SHK_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     SHK_CUDA(ctx, cudaEventCreate(&s.ev_start));
     SHK_CUDA(ctx, cudaEventCreate(&s.ev_k0));
+    SHK_CUDA(ctx, cudaEventCreate(&s.ev_ka));
     SHK_CUDA(ctx, cudaEventCreate(&s.ev_k1));
     SHK_CUDA(ctx, cudaEventCreate(&s.ev_done));
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_seq, B + 64));
@@ -105,8 +109,8 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     a.slow_list = s.d_slow_list;
     a.tile_sums = s.d_tile_sums;
     a.counters = s.d_counters;
-    a.slow_table = ctx->d_slow_table;
-    a.slow_stamp = ctx->d_slow_stamp;
+    a.slow_table = s.d_slow_table;
+    a.slow_stamp = s.d_slow_stamp;
     a.n_slow_slabs = ctx->n_slow_slabs;
     a.tile_base = s.d_tile_base;
     a.assoc = s.d_assoc;
@@ -114,26 +118,26 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     return a;
 }
 
-// The exact-path table depends on the number of gene indices -> (re)allocated after a build.
+// The exact-path tables depend on the number of gene indices -> (re)allocated after a build,
+// one set per slot because the slots' kernels run concurrently.
 static int ensure_slow_table(shk_ctx *ctx)
 {
-    if (ctx->d_slow_table) {
-        cudaFree(ctx->d_slow_table);
-        ctx->d_slow_table = nullptr;
-    }
-    if (ctx->d_slow_stamp) {
-        cudaFree(ctx->d_slow_stamp);
-        ctx->d_slow_stamp = nullptr;
-    }
     const uint64_t ng = std::max<uint32_t>(ctx->index.info.n_genes, 1);
-    // as many concurrent exact-path warps as 256 MiB of tables allow, at most 4 per SM
-    uint64_t slabs = std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (256ull << 20) / (ng * sizeof(uint4)));
+    // as many concurrent exact-path warps as 128 MiB of tables allow, at most 4 per SM
+    uint64_t slabs = std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (128ull << 20) / (ng * sizeof(uint4)));
     slabs = std::max<uint64_t>(slabs, 8);
     ctx->n_slow_slabs = (uint32_t)slabs;
-    SHK_CUDA(ctx, cudaMalloc((void **)&ctx->d_slow_table, slabs * ng * sizeof(uint4)));
-    SHK_CUDA(ctx, cudaMalloc((void **)&ctx->d_slow_stamp, slabs * 4));
-    SHK_CUDA(ctx, cudaMemset(ctx->d_slow_table, 0, slabs * ng * sizeof(uint4)));
-    SHK_CUDA(ctx, cudaMemset(ctx->d_slow_stamp, 0, slabs * 4));
+    for (uint32_t i = 0; i < ctx->n_slots; ++i) {
+        Slot &s = ctx->slots[i];
+        cudaFree(s.d_slow_table);
+        cudaFree(s.d_slow_stamp);
+        s.d_slow_table = nullptr;
+        s.d_slow_stamp = nullptr;
+        SHK_CUDA(ctx, cudaMalloc((void **)&s.d_slow_table, slabs * ng * sizeof(uint4)));
+        SHK_CUDA(ctx, cudaMalloc((void **)&s.d_slow_stamp, slabs * 4));
+        SHK_CUDA(ctx, cudaMemset(s.d_slow_table, 0, slabs * ng * sizeof(uint4)));
+        SHK_CUDA(ctx, cudaMemset(s.d_slow_stamp, 0, slabs * 4));
+    }
     return SHK_OK;
 }
 
@@ -141,7 +145,7 @@ static int enqueue_chunk_kernels(shk_ctx *ctx, Slot &s)
 {
     SHK_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, sizeof(ChunkCounters), s.stream));
     ReadKernelArgs a = make_args(ctx, s);
-    s.launches += (uint32_t)launch_read_kernels(ctx, a, s.assoc_cap, s.stream, s.ev_k0, s.ev_k1);
+    s.launches += (uint32_t)launch_read_kernels(ctx, a, s.assoc_cap, s.stream, s.ev_k0, s.ev_ka, s.ev_k1);
     SHK_CUDA(ctx, cudaGetLastError());
     SHK_CUDA(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(ChunkCounters), cudaMemcpyDeviceToHost, s.stream));
     SHK_CUDA(ctx, cudaEventRecord(s.ev_done, s.stream));
@@ -272,8 +276,6 @@ void shk_destroy(shk_ctx *ctx)
     cudaFree(ctx->index.entries);
     cudaFree(ctx->index.csr_off);
     cudaFree(ctx->index.csr_ids);
-    cudaFree(ctx->d_slow_table);
-    cudaFree(ctx->d_slow_stamp);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
     delete ctx;
 }
@@ -481,8 +483,9 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
         SHK_CUDA(ctx, cudaMemcpyAsync(s.h_assoc, s.d_assoc, c.n_assoc * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
     if (s.n_reads) SHK_CUDA(ctx, cudaMemcpyAsync(s.h_keep, s.d_keep, s.n_reads, cudaMemcpyDeviceToHost, s.stream));
     SHK_CUDA(ctx, cudaStreamSynchronize(s.stream));
-    float k_ms = 0, t_ms = 0;
+    float k_ms = 0, t_ms = 0, p_ms = 0;
     cudaEventElapsedTime(&k_ms, s.ev_k0, s.ev_k1);
+    cudaEventElapsedTime(&p_ms, s.ev_k0, s.ev_ka);
     cudaEventElapsedTime(&t_ms, s.ev_start, s.ev_done);
     memset(out, 0, sizeof *out);
     out->n_assoc = c.n_assoc;
@@ -493,6 +496,7 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
     out->n_probes = c.n_probes;
     out->n_hits = c.n_hits;
     out->analyze_ms = k_ms;
+    out->probe_kernel_ms = p_ms;
     out->total_ms = t_ms;
     out->kernel_launches = s.launches;
     s.pending = false;

@@ -75,7 +75,7 @@ constexpr uint32_t kMaxFastLen = 1024;  // longer reads take the exact path (32 
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_ka = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     // device
     uint8_t *d_seq = nullptr, *d_qual = nullptr;
     uint32_t *d_off = nullptr;
@@ -88,6 +88,8 @@ struct Slot {
     shk_assoc *d_assoc = nullptr;
     uint64_t assoc_cap = 0;
     uint8_t *d_keep = nullptr;
+    uint4 *d_slow_table = nullptr;   // exact-path tables: private to the slot (slots run concurrently)
+    uint32_t *d_slow_stamp = nullptr;
     // pinned host
     ChunkCounters *h_counters = nullptr;
     shk_assoc *h_assoc = nullptr;
@@ -112,8 +114,6 @@ struct shk_ctx {
     uint32_t n_slots = 0;
     uint32_t max_reads = 0;
     uint64_t max_bytes = 0;
-    uint4 *d_slow_table = nullptr;
-    uint32_t *d_slow_stamp = nullptr;
     uint32_t n_slow_slabs = 0;
     std::atomic<uint64_t> launches{0};
     cudaStream_t build_stream = nullptr;
@@ -143,7 +143,7 @@ int random_sector_bench_device(shk_ctx *ctx, uint64_t n_loads, uint64_t span_byt
 // shk_reads.cu
 // Enqueues the classification kernels of one chunk on `st`; returns the number of launches.
 int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st, cudaEvent_t ev_k0,
-                        cudaEvent_t ev_k1);
+                        cudaEvent_t ev_ka, cudaEvent_t ev_k1);
 int launch_scatter(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st);
 
 }  // namespace shk

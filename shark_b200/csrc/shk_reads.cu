@@ -459,14 +459,15 @@ scatter_assoc_kernel(const ReadKernelArgs a, uint64_t assoc_cap, const uint32_t 
 }
 
 template <bool HAS_QUAL, int MOD>
-static void launch_typed(const ReadKernelArgs &a, cudaStream_t st, unsigned tiles, unsigned slow_blocks)
+static void launch_typed(const ReadKernelArgs &a, cudaStream_t st, unsigned tiles, unsigned slow_blocks, cudaEvent_t ev_ka)
 {
     analyze_reads_kernel<HAS_QUAL, MOD><<<tiles, kWarpsPerCta * 32, 0, st>>>(a);
+    if (ev_ka) cudaEventRecord(ev_ka, st);
     analyze_slow_kernel<HAS_QUAL, MOD><<<slow_blocks, 128, 0, st>>>(a);
 }
 
 int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st, cudaEvent_t ev_k0,
-                        cudaEvent_t ev_k1)
+                        cudaEvent_t ev_ka, cudaEvent_t ev_k1)
 {
     if (ev_k0) cudaEventRecord(ev_k0, st);
     int launched = 0;
@@ -475,9 +476,9 @@ int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_ca
         const unsigned slow_blocks = (a.n_slow_slabs + 3) / 4;
         const bool q = a.qual != nullptr;
         switch (a.geom.mod_kind) {
-        case MOD_POW2: q ? launch_typed<true, MOD_POW2>(a, st, tiles, slow_blocks) : launch_typed<false, MOD_POW2>(a, st, tiles, slow_blocks); break;
-        case MOD_B33: q ? launch_typed<true, MOD_B33>(a, st, tiles, slow_blocks) : launch_typed<false, MOD_B33>(a, st, tiles, slow_blocks); break;
-        default: q ? launch_typed<true, MOD_GENERIC>(a, st, tiles, slow_blocks) : launch_typed<false, MOD_GENERIC>(a, st, tiles, slow_blocks); break;
+        case MOD_POW2: q ? launch_typed<true, MOD_POW2>(a, st, tiles, slow_blocks, ev_ka) : launch_typed<false, MOD_POW2>(a, st, tiles, slow_blocks, ev_ka); break;
+        case MOD_B33: q ? launch_typed<true, MOD_B33>(a, st, tiles, slow_blocks, ev_ka) : launch_typed<false, MOD_B33>(a, st, tiles, slow_blocks, ev_ka); break;
+        default: q ? launch_typed<true, MOD_GENERIC>(a, st, tiles, slow_blocks, ev_ka) : launch_typed<false, MOD_GENERIC>(a, st, tiles, slow_blocks, ev_ka); break;
         }
         // tile_base <- exclusive scan(tile_sums); the grand total lands in tile_base[tiles]
         cudaMemcpyAsync(a.tile_base, a.tile_sums, (size_t)tiles * 4, cudaMemcpyDeviceToDevice, st);
@@ -486,6 +487,7 @@ int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_ca
         launched = 4;
         ctx->launches += 4;
     }
+    else if (ev_ka) cudaEventRecord(ev_ka, st);
     if (ev_k1) cudaEventRecord(ev_k1, st);
     return launched;
 }

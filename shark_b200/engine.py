@@ -37,8 +37,10 @@ class Shark:
         if getattr(self, "ctx", None):
             self.lib.shk_destroy(self.ctx)
             self.ctx = None
-        for b in getattr(self, "_staging", {}).values():
-            b.free()
+        for _, bufs in getattr(self, "_staging", {}).values():
+            for b in bufs:
+                if b is not None:
+                    b.free()
         self._staging = {}
 
     def __del__(self):
@@ -138,7 +140,8 @@ class Shark:
             a, keep = a.copy(), keep.copy()
         return dict(read_idx=a[:, 0], gene_idx=a[:, 1], keep=keep, n_assoc=int(n), n_reads=res.n_reads,
                     n_slow_reads=res.n_slow_reads, n_probes=res.n_probes, n_hits=res.n_hits,
-                    analyze_ms=res.analyze_ms, total_ms=res.total_ms, kernel_launches=res.kernel_launches)
+                    analyze_ms=res.analyze_ms, total_ms=res.total_ms, kernel_launches=res.kernel_launches,
+                    probe_kernel_ms=res.probe_kernel_ms)
 
     def kernel_launches(self):
         return int(self.lib.shk_kernel_launches(self.ctx))
@@ -187,7 +190,7 @@ class Shark:
             raise capi.SharkError(-1, "min_quality != 0 needs qualities")
         keep = np.zeros(n, np.uint8)
         out_r, out_g = [], []
-        stats = dict(n_probes=0, n_hits=0, analyze_ms=0.0, n_slow_reads=0, kernel_launches=0, chunks=0)
+        stats = dict(n_probes=0, n_hits=0, analyze_ms=0.0, probe_kernel_ms=0.0, n_slow_reads=0, kernel_launches=0, chunks=0)
         chunks = self.plan_chunks(off) if n else []
         pending = []
 
@@ -197,7 +200,7 @@ class Shark:
             keep[first:first + r["n_reads"]] = r["keep"]
             out_r.append(r["read_idx"].astype(np.uint64) + np.uint64(first))
             out_g.append(r["gene_idx"])
-            for key in ("n_probes", "n_hits", "analyze_ms", "n_slow_reads", "kernel_launches"):
+            for key in ("n_probes", "n_hits", "analyze_ms", "probe_kernel_ms", "n_slow_reads", "kernel_launches"):
                 stats[key] += r[key]
             stats["chunks"] += 1
 
@@ -220,3 +223,30 @@ class Shark:
         ar = np.concatenate(out_r) if out_r else np.zeros(0, np.uint64)
         ag = np.concatenate(out_g) if out_g else np.zeros(0, np.uint32)
         return keep, ar, ag, stats
+
+    def analyze_chunks(self, chunks, copy=True, on_result=None):
+        """Streams pre-chunked host inputs through the slots, double buffered: chunk i+1 is
+        submitted (H2D + kernels enqueued) before chunk i is collected.  `chunks` is a sequence
+        of (seq uint8, qual uint8|None, off32 uint32[n+1], n_reads) whose arrays should live in
+        pinned memory (capi.PinnedBuffer) so that the copies are asynchronous - this is what the
+        FASTQ batcher of the host side produces.  Returns the per-chunk result dicts in order
+        (or feeds them to on_result)."""
+        results, pending = [], []
+
+        def drain():
+            slot = pending.pop(0)
+            r = self.collect(slot, copy=copy)
+            if on_result is not None:
+                on_result(r)
+            else:
+                results.append(r)
+
+        for ci, (seq, qual, off32, n_reads) in enumerate(chunks):
+            slot = ci % self.n_slots
+            if len(pending) == self.n_slots:
+                drain()
+            self.submit(slot, seq, qual, off32, n_reads)
+            pending.append(slot)
+        while pending:
+            drain()
+        return results
