@@ -124,9 +124,10 @@ int shk_index_export(shk_ctx *ctx, uint64_t *set_bit_pos, uint32_t *offsets, uin
  * (ncclBroadcast over NVLink, cudaMemcpyPeer): call shk_index_views on the source context,
  * shk_index_adopt (allocates same-sized buffers) + shk_index_views on each destination, copy
  * every view, then shk_index_finalize on the destinations. */
-#define SHK_INDEX_N_VIEWS 4
+#define SHK_INDEX_N_VIEWS 5
 typedef struct shk_index_views {
-    void *dev_ptr[SHK_INDEX_N_VIEWS]; /* 0 filter sectors, 1 per-bit entries, 2 CSR offsets, 3 CSR ids */
+    void *dev_ptr[SHK_INDEX_N_VIEWS]; /* 0 filter sectors, 1 per-bit entries, 2 CSR offsets, 3 CSR ids,
+                                         4 front table */
     uint64_t bytes[SHK_INDEX_N_VIEWS];
     shk_index_info info;
 } shk_index_views;

@@ -42,7 +42,7 @@ class IndexInfo(C.Structure):
 
 
 class IndexViews(C.Structure):
-    _fields_ = [("dev_ptr", C.c_void_p * 4), ("bytes", C.c_uint64 * 4), ("info", IndexInfo)]
+    _fields_ = [("dev_ptr", C.c_void_p * 5), ("bytes", C.c_uint64 * 5), ("info", IndexInfo)]
 
 
 class Assoc(C.Structure):

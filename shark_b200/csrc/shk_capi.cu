@@ -97,6 +97,8 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     a.csr_off = ctx->index.csr_off;
     a.csr_ids = ctx->index.csr_ids;
     a.geom = ctx->index.geom;
+    a.front = ctx->index.front;
+    a.fgeom = ctx->index.fgeom;
     a.n_genes = ctx->index.info.n_genes;
     a.k = (int)ctx->params.k;
     a.c = ctx->params.c;
@@ -276,6 +278,7 @@ void shk_destroy(shk_ctx *ctx)
     cudaFree(ctx->index.entries);
     cudaFree(ctx->index.csr_off);
     cudaFree(ctx->index.csr_ids);
+    cudaFree(ctx->index.front);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
     delete ctx;
 }
@@ -323,6 +326,8 @@ int shk_index_views_get(shk_ctx *ctx, shk_index_views *v)
     v->bytes[2] = (ix.info.n_set_bits + 1) * 4;
     v->dev_ptr[3] = ix.csr_ids;
     v->bytes[3] = std::max<uint64_t>(ix.info.tot_ids, 1) * 2;
+    v->dev_ptr[4] = ix.front;
+    v->bytes[4] = ix.fgeom.n_buckets * 16;
     v->info = ix.info;
     return SHK_OK;
 }
@@ -343,7 +348,7 @@ int shk_index_adopt(shk_ctx *ctx, const shk_index_info *info)
     SHK_CUDA(ctx, cudaMalloc((void **)&ix.entries, (info->n_set_bits + 1) * 8));
     SHK_CUDA(ctx, cudaMalloc((void **)&ix.csr_off, (info->n_set_bits + 1) * 4));
     SHK_CUDA(ctx, cudaMalloc((void **)&ix.csr_ids, std::max<uint64_t>(info->tot_ids, 1) * 2));
-    return SHK_OK;
+    return index_alloc_front(ctx);
 }
 
 int shk_index_finalize(shk_ctx *ctx)

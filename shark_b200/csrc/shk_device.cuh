@@ -173,6 +173,58 @@ __device__ __forceinline__ uint32_t entry_id0(uint64_t e) { return (uint32_t)(e 
 __device__ __forceinline__ uint32_t entry_len(uint64_t e) { return ((uint32_t)(e >> 32) & 0xFFFFu) + 1u; }
 __device__ __forceinline__ uint32_t entry_lo(uint64_t e) { return (uint32_t)e; }
 
+// ---------------------------------------------------------------------------------------------
+// Front table: an exact, L2-sized accelerator in front of the bit vector.  The filter is sparse
+// (load 0.03 % .. 1 %), so the set bits themselves fit in tens of MB.  The bit positions are
+// uniformly distributed hash values, which makes "bucket = position >> shift" a perfect
+// bucketing: bucket b describes positions [b << shift, (b+1) << shift) with four 32-bit slots
+//     bits 31..17 : position - (b << shift)          (shift <= 15)
+//     bit  16     : 0 = the gene list has exactly one id, in bits 15..0
+//                   1 = longer list: take the full path (bit vector -> rank -> entry)
+// 0xFFFFFFFF = empty slot; 0xFFFFFFFE in slot 3 = bucket overflowed, unmatched positions take
+// the full path.  One 16-byte load therefore answers "definitely not set" / "set, gene g" for
+// almost every probe; everything else falls back to the reference-shaped structures, so the
+// results are identical by construction.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kFrontEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kFrontOverflow = 0xFFFFFFFEu;
+constexpr uint32_t kFrontMultiFlag = 0x10000u;
+
+struct FrontGeom {
+    uint32_t shift;     // log2(positions per bucket), 5..15
+    uint32_t off_mask;  // (1 << shift) - 1
+    uint64_t n_buckets;
+};
+
+__device__ __forceinline__ bool front_slot_matches(uint32_t slot, uint32_t off)
+{
+    return (slot >> 17) == off && (slot & 0x1FFFFu) < 0x1FFFEu;
+}
+
+enum FrontResult : int { FRONT_MISS = 0, FRONT_SINGLE = 1, FRONT_FULL = 2 };
+
+// -> FRONT_MISS, FRONT_SINGLE (gene id in `gene`) or FRONT_FULL (consult the bit vector)
+__device__ __forceinline__ int front_lookup(const uint4 &q, uint32_t off, uint32_t &gene)
+{
+    const bool m0 = front_slot_matches(q.x, off), m1 = front_slot_matches(q.y, off),
+               m2 = front_slot_matches(q.z, off), m3 = front_slot_matches(q.w, off);
+    const uint32_t sl = m0 ? q.x : (m1 ? q.y : (m2 ? q.z : q.w));
+    if (m0 | m1 | m2 | m3) {
+        gene = sl & 0xFFFFu;
+        return (sl & kFrontMultiFlag) ? FRONT_FULL : FRONT_SINGLE;
+    }
+    return q.w == kFrontOverflow ? FRONT_FULL : FRONT_MISS;
+}
+
+__device__ __forceinline__ uint4 ld_front(const uint4 *p, uint64_t pol)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 {
     x += 0x9E3779B97F4A7C15ULL;

@@ -372,6 +372,41 @@ export_positions_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors
     }
 }
 
+// Front table fill (see shk_device.cuh): one thread per filter sector walks its set bits in rank
+// order and inserts (offset, single gene | multi flag) into the bucket of each position with
+// compare-and-swap on the first free slot; a fifth key turns slot 3 into the overflow marker.
+__global__ void __launch_bounds__(256)
+front_fill_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, const uint64_t *__restrict__ entries,
+                  FrontGeom fg, uint32_t *front)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sectors) return;
+    const uint4 *sp = reinterpret_cast<const uint4 *>(sectors + s * 8);
+    uint4 a = sp[0], b = sp[1];
+    uint32_t w[7] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z};
+    uint32_t r = b.w;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        uint32_t bits = w[i];
+        while (bits) {
+            int bpos = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint64_t p = (s * kWordsPerSector + i) * 32 + bpos;
+            const uint64_t e = entries[r++];
+            const uint32_t off = (uint32_t)p & fg.off_mask;
+            const uint32_t v = (off << 17) | (entry_len(e) == 1 ? entry_id0(e) : kFrontMultiFlag);
+            uint32_t *slot = front + (p >> fg.shift) * 4;
+            bool placed = false;
+            for (int j = 0; j < 4 && !placed; ++j) {
+                uint32_t old = atomicCAS(&slot[j], kFrontEmpty, v);
+                placed = old == kFrontEmpty;
+                if (!placed && old == kFrontOverflow) placed = true;  // already overflowed
+            }
+            if (!placed) atomicExch(&slot[3], kFrontOverflow);
+        }
+    }
+}
+
 // =============================================================================================
 // Host orchestration of the build.
 // =============================================================================================
@@ -396,10 +431,29 @@ static void free_index_arrays(DeviceIndex &ix)
     if (ix.entries) cudaFree(ix.entries);
     if (ix.csr_off) cudaFree(ix.csr_off);
     if (ix.csr_ids) cudaFree(ix.csr_ids);
+    if (ix.front) cudaFree(ix.front);
+    ix.front = nullptr;
     ix.entries = nullptr;
     ix.csr_off = nullptr;
     ix.csr_ids = nullptr;
     ix.built = false;
+}
+
+// Front table geometry: about 0.7 keys per 4-slot bucket, at least 32 positions per bucket (the
+// table is then at most 4x the plain bit vector), at most 2^15 (15-bit offsets).
+int index_alloc_front(shk_ctx *ctx)
+{
+    DeviceIndex &ix = ctx->index;
+    if (ix.front) cudaFree(ix.front);
+    ix.front = nullptr;
+    const double per_key = 0.7 * (double)ix.geom.bf_bits / (double)std::max<uint64_t>(ix.info.n_set_bits, 1);
+    uint32_t shift = 5;
+    while (shift < 15 && (double)(1ull << (shift + 1)) <= per_key) ++shift;
+    ix.fgeom.shift = shift;
+    ix.fgeom.off_mask = (1u << shift) - 1u;
+    ix.fgeom.n_buckets = (ix.geom.bf_bits + (1ull << shift) - 1) >> shift;
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.front, ix.fgeom.n_buckets * 16));
+    return SHK_OK;
 }
 
 template <int MOD>
@@ -529,6 +583,18 @@ int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *r
         SHK_CUDA(ctx, cudaMemsetAsync(d_csr_off.p, 0, 4, st));
         SHK_CUDA(ctx, d_csr_ids.alloc(1));
     }
+    // front table over the finished entries
+    ix.info.n_set_bits = n_set;
+    rc = index_alloc_front(ctx);
+    if (rc) return rc;
+    SHK_CUDA(ctx, cudaMemsetAsync(ix.front, 0xFF, ix.fgeom.n_buckets * 16, st));
+    if (n_set > 0) {
+        unsigned blocks_s = (unsigned)((ix.geom.n_sectors + 255) / 256);
+        front_fill_kernel<<<blocks_s, 256, 0, st>>>(ix.sectors, ix.geom.n_sectors, d_entries.p, ix.fgeom,
+                                                    reinterpret_cast<uint32_t *>(ix.front));
+        ctx->launches += 1;
+        SHK_CUDA(ctx, cudaGetLastError());
+    }
     SHK_CUDA(ctx, cudaEventRecord(e1, st));
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
     float ms = 0;
@@ -545,7 +611,7 @@ int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *r
     ix.info.tot_ids = tot_ids;
     ix.info.n_windows = h_nwin;
     ix.info.bf_bits = ix.geom.bf_bits;
-    ix.info.device_bytes = sector_bytes + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2;
+    ix.info.device_bytes = sector_bytes + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2 + ix.fgeom.n_buckets * 16;
     ix.info.build_ms = ms;
     ix.built = true;
     return SHK_OK;

@@ -20,6 +20,8 @@ struct DeviceIndex {
     uint64_t *entries = nullptr;  // one per set bit
     uint32_t *csr_off = nullptr;  // n_set + 1
     uint16_t *csr_ids = nullptr;  // tot_ids
+    uint4 *front = nullptr;       // front table, fgeom.n_buckets x 16 bytes
+    FrontGeom fgeom{};
     shk_index_info info{};
     bool built = false;
 };
@@ -47,6 +49,8 @@ struct ReadKernelArgs {
     const uint32_t *csr_off;
     const uint16_t *csr_ids;
     FilterGeom geom;
+    const uint4 *front;
+    FrontGeom fgeom;
     uint32_t n_genes;
     // options
     int k;
@@ -135,6 +139,7 @@ int fail(shk_ctx *ctx, int code, const char *fmt, ...);
 
 // shk_index.cu
 int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_records);
+int index_alloc_front(shk_ctx *ctx);  // sizes fgeom from info and allocates the table
 int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *ids);
 int probe_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int64_t *rank, uint32_t *begin, uint32_t *len);
 int probe_bench_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, uint32_t reps, float *ms, uint64_t *hits);

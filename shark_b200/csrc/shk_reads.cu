@@ -2,8 +2,9 @@
 // and the ordering contract of ReadOutput.  Citations are reference file:line.
 //
 // Kernels of one chunk (all on the slot's stream):
-//   analyze_reads_kernel   one warp per read: mask, 2-bit pack, canonical k-mers, probe, per-gene
-//                          coverage/hits in a register-resident 8-gene table, argmax, threshold
+//   analyze_reads_kernel   one warp per read: mask, 2-bit pack, canonical k-mers, front-table probe
+//                          (one 16-byte load per k-mer), per-gene coverage/hits in a
+//                          register-resident 8-gene table, argmax, threshold
 //   analyze_slow_kernel    exact path for reads the fast path gives up on (more than 8 genes, a
 //                          list longer than 8, or a text longer than 1024 bytes)
 //   scan_tile_sums_kernel  exclusive scan of the per-tile association counts
@@ -14,7 +15,7 @@
 namespace shk {
 
 constexpr int kSlots = 8;        // genes tracked per read on the fast path
-constexpr int kGroup = 4;        // 32-position chunks whose probes are in flight together
+constexpr int kGroup = 3;        // rounds of 32 windows whose probes are in flight together
 constexpr int kWarpsPerCta = 8;
 constexpr int kReadsPerWarp = kReadsPerTile / kWarpsPerCta;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
@@ -56,8 +57,9 @@ struct WarpTable {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) mask[s] = 0;
     }
-    // all arguments are warp-uniform
-    __device__ __forceinline__ void update(uint32_t g, int chunk, uint32_t m, int lane)
+    // all arguments are warp-uniform: gene g was hit by the windows ending at positions
+    // base + i for every set bit i of m
+    __device__ __forceinline__ void update(uint32_t g, uint32_t base, uint32_t m, int lane)
     {
         uint32_t found = __ballot_sync(kFull, lane < nslots && gene == g);
         int idx;
@@ -71,11 +73,13 @@ struct WarpTable {
             idx = nslots++;
             if (lane == idx) gene = g;
         }
-        if (lane == chunk) {
+        const uint32_t w0 = base >> 5, sh = base & 31u;
+        uint32_t add = 0;
+        if ((uint32_t)lane == w0) add = m << sh;
+        else if ((uint32_t)lane == w0 + 1 && sh) add = m >> (32u - sh);
 #pragma unroll
-            for (int s = 0; s < kSlots; ++s)
-                if (s == idx) mask[s] |= m;
-        }
+        for (int s = 0; s < kSlots; ++s)
+            if (s == idx) mask[s] |= add;
     }
 };
 
@@ -129,9 +133,10 @@ __device__ __forceinline__ bool chunk_window(const ReadKernelArgs &a, uint32_t o
     return wv;
 }
 
-// Adds the hits of one chunk to the table.  H = ballot of hit lanes, e = the lane's entry.
-__device__ __forceinline__ void accumulate_chunk(const ReadKernelArgs &a, WarpTable &tab, int chunk, uint32_t H, bool hit,
-                                                 uint64_t e, int lane)
+// Adds the hits of one round (windows ending at base + lane) to the table.  H = ballot of hit
+// lanes, e = the lane's entry.
+__device__ __forceinline__ void accumulate_round(const ReadKernelArgs &a, WarpTable &tab, uint32_t base, uint32_t H,
+                                                 bool hit, uint64_t e, int lane)
 {
     uint32_t rem = H;
     while (rem && !tab.overflow) {
@@ -144,12 +149,12 @@ __device__ __forceinline__ void accumulate_chunk(const ReadKernelArgs &a, WarpTa
             tab.overflow = true;
             break;
         }
-        tab.update(entry_id0(el), chunk, grp, lane);
+        tab.update(entry_id0(el), base, grp, lane);
         if (ln == 2) {
-            tab.update(entry_lo(el), chunk, grp, lane);
+            tab.update(entry_lo(el), base, grp, lane);
         } else if (ln >= 3) {
             const uint32_t b = entry_lo(el);
-            for (uint32_t t = 1; t < ln; ++t) tab.update(a.csr_ids[b + t], chunk, grp, lane);
+            for (uint32_t t = 1; t < ln; ++t) tab.update(a.csr_ids[b + t], base, grp, lane);
         }
     }
 }
@@ -168,73 +173,136 @@ __device__ __forceinline__ uint32_t pool_reserve(const ReadKernelArgs &a, uint32
     return base;
 }
 
-template <bool HAS_QUAL, int MOD>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) analyze_reads_kernel(const ReadKernelArgs a)
+// Full path for one position p: bit vector word -> sector rank -> entry (bloomfilter.h:87-101).
+// Returns false when the bit is clear.
+__device__ __forceinline__ bool full_probe(const ReadKernelArgs &a, uint64_t p, uint64_t pol_first, uint64_t pol_last,
+                                           uint64_t &e)
 {
+    const uint32_t pw = (uint32_t)phys_word(p), bit = (uint32_t)(p & 31);
+    const uint32_t w = ld_filter_word(a.sectors + pw, pol_first);
+    if (!((w >> bit) & 1u)) return false;
+    Sector s = ld_sector(reinterpret_cast<const Sector *>(a.sectors) + (pw >> 3));
+    e = ld_u64_hint(a.entries + sector_rank(s, pw & 7u, bit), pol_last);
+    return true;
+}
+
+template <bool HAS_QUAL, int MOD>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) analyze_reads_kernel(const ReadKernelArgs a)
+{
+    // per warp: packed 2-bit codes and validity masks of the read's 32-byte chunks; index c+1
+    // holds chunk c, index 0 is the all-invalid chunk "-1"
+    __shared__ uint64_t sP[kWarpsPerCta][kMaxFastLen / 32 + 2];
+    __shared__ uint32_t sV[kWarpsPerCta][kMaxFastLen / 32 + 2];
     __shared__ uint32_t s_assoc[kWarpsPerCta];
     __shared__ uint32_t s_probes[kWarpsPerCta];
     __shared__ uint32_t s_hits[kWarpsPerCta];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
-    const Sector *sector_base = reinterpret_cast<const Sector *>(a.sectors);
     uint32_t warp_assoc = 0, warp_probes = 0, warp_hits = 0;
+    const int k = a.k;
+    const uint32_t kbits = (1u << k) - 1u;
+    const uint64_t kmask2 = (1ULL << (2 * k)) - 1ULL;
+    if (lane == 0) {
+        sP[warp][0] = 0;
+        sV[warp][0] = 0;
+    }
 
     for (int it = 0; it < kReadsPerWarp; ++it) {
         const uint32_t r = blockIdx.x * kReadsPerTile + (uint32_t)it * kWarpsPerCta + (uint32_t)warp;
         if (r >= a.n_reads) break;
         const uint32_t off0 = a.off[r];
         const uint32_t n = a.off[r + 1] - off0;
-        bool slow = n > kMaxFastLen;
+        if (n > kMaxFastLen) {
+            if (lane == 0) {
+                a.rec[r] = make_uint2(0u, 0u);
+                a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
+            }
+            continue;
+        }
+        // ---- phase 1: text -> validity masks + packed codes (FastqSplitter.hpp:104-109,
+        //      kmer_utils.hpp:29-41), number of valid bases (ReadAnalyzer.hpp:46-49)
+        const int nch = (int)((n + 31u) >> 5);
+        uint32_t len = 0;
+        __syncwarp();
+        for (int c = 0; c < nch; ++c) {
+            const uint32_t pos = (uint32_t)c * 32u + (uint32_t)lane;
+            uint32_t ch = 0;
+            if (pos < n) {
+                ch = a.seq[off0 + pos];
+                if (HAS_QUAL) {
+                    int q = (int)(signed char)a.qual[off0 + pos];
+                    if (q < a.mq) ch = (ch - 64u) & 0xFFu;  // seq[i] = seq[i] - 64
+                }
+            }
+            const bool valid = base_valid(ch);
+            const uint32_t V = __ballot_sync(kFull, valid);
+            len += __popc(V);
+            const uint32_t val = valid ? base_code(ch) << (30 - 2 * (lane & 15)) : 0u;
+            const uint32_t hiw = __reduce_or_sync(kFull, lane < 16 ? val : 0u);
+            const uint32_t low = __reduce_or_sync(kFull, lane >= 16 ? val : 0u);
+            if (lane == 0) {
+                sP[warp][c + 1] = ((uint64_t)hiw << 32) | low;
+                sV[warp][c + 1] = V;
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: every candidate window end e = k-1 .. n-1, 32 per round, kGroup rounds of
+        //      front-table loads in flight (ReadAnalyzer.hpp:50-87 without the sequential roll)
         WarpTable tab;
         tab.init();
-        uint32_t len = 0;
-        if (!slow) {
-            const int nch = (int)((n + 31u) >> 5);
-            ChunkState cs{0ULL, 0u};
-            for (int c0 = 0; c0 < nch && !tab.overflow; c0 += kGroup) {
-                uint32_t pw[kGroup], bit[kGroup], w[kGroup];
-                bool wv[kGroup];
-                uint64_t e[kGroup];
+        const int n_rounds = n >= (uint32_t)k && len >= (uint32_t)k ? (int)((n - (uint32_t)k + 32u) >> 5) : 0;
+        for (int t0 = 0; t0 < n_rounds && !tab.overflow; t0 += kGroup) {
+            uint4 q[kGroup];
+            uint32_t bucket[kGroup], offk[kGroup];
+            bool wv[kGroup];
 #pragma unroll
-                for (int j = 0; j < kGroup; ++j) {
-                    wv[j] = false;
-                    pw[j] = bit[j] = 0;
-                    if (c0 + j < nch) wv[j] = chunk_window<HAS_QUAL, MOD>(a, off0, n, c0 + j, lane, cs, len, pw[j], bit[j]);
-                }
-                // (1) one filter word per window: the random 32-byte sector access
-#pragma unroll
-                for (int j = 0; j < kGroup; ++j) w[j] = wv[j] ? ld_filter_word(a.sectors + pw[j], pol_first) : 0u;
-                uint32_t H[kGroup];
-#pragma unroll
-                for (int j = 0; j < kGroup; ++j) {
-                    const bool hit = wv[j] && ((w[j] >> bit[j]) & 1u);  // `_bf[bf_idx]`, bloomfilter.h:89
-                    warp_probes += __popc(__ballot_sync(kFull, wv[j]));
-                    H[j] = __ballot_sync(kFull, hit);
-                    wv[j] = hit;
-                }
-                // (2) hits: whole sector (now in L2) -> rank, bloomfilter.h:90
-#pragma unroll
-                for (int j = 0; j < kGroup; ++j) {
+            for (int j = 0; j < kGroup; ++j) {
+                wv[j] = false;
+                bucket[j] = offk[j] = 0;
+                const uint32_t e = (uint32_t)(k - 1) + 32u * (uint32_t)(t0 + j) + (uint32_t)lane;
+                if (t0 + j < n_rounds && e < n) {
+                    const uint32_t c = e >> 5, i = e & 31u;
+                    const uint64_t VV = (uint64_t)sV[warp][c] | ((uint64_t)sV[warp][c + 1] << 32);
+                    wv[j] = (((uint32_t)(VV >> (33u + i - (uint32_t)k))) & kbits) == kbits;
                     if (wv[j]) {
-                        Sector s = ld_sector(sector_base + (pw[j] >> 3));
-                        w[j] = sector_rank(s, pw[j] & 7u, bit[j]);
-                    }
-                }
-                // (3) hits: the 8-byte entry of the set bit (gene list head), bloomfilter.h:91-101
-#pragma unroll
-                for (int j = 0; j < kGroup; ++j) e[j] = wv[j] ? ld_u64_hint(a.entries + w[j], pol_last) : 0ULL;
-                // (4) per-gene hit masks, ReadAnalyzer.hpp:56-62,79-86
-#pragma unroll
-                for (int j = 0; j < kGroup; ++j) {
-                    if (H[j]) {
-                        warp_hits += __popc(H[j]);
-                        accumulate_chunk(a, tab, c0 + j, H[j], wv[j], e[j], lane);
+                        const int sh = 2 * (31 - (int)i);
+                        uint64_t fwd = sP[warp][c + 1] >> sh;
+                        if (sh) fwd |= sP[warp][c] << (64 - sh);
+                        fwd &= kmask2;
+                        const uint64_t p = bit_index<MOD>(xxh64_u64(canonical(fwd, k)), a.geom);
+                        bucket[j] = (uint32_t)(p >> a.fgeom.shift);
+                        offk[j] = (uint32_t)p & a.fgeom.off_mask;
                     }
                 }
             }
-            slow = tab.overflow;
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j)
+                q[j] = wv[j] ? ld_front(a.front + bucket[j], pol_last) : make_uint4(kFrontEmpty, kFrontEmpty, kFrontEmpty, kFrontEmpty);
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                if (t0 + j >= n_rounds) break;
+                uint32_t g = 0;
+                uint64_t e = 0;
+                bool hit = false;
+                if (wv[j]) {
+                    const int res = front_lookup(q[j], offk[j], g);
+                    if (res == FRONT_SINGLE) {
+                        hit = true;
+                        e = make_entry(g, 1u, 0u);
+                    } else if (res == FRONT_FULL) {
+                        const uint64_t p = ((uint64_t)bucket[j] << a.fgeom.shift) | offk[j];
+                        hit = full_probe(a, p, pol_first, pol_last, e);
+                    }
+                }
+                warp_probes += __popc(__ballot_sync(kFull, wv[j]));
+                const uint32_t H = __ballot_sync(kFull, hit);
+                if (H) {
+                    warp_hits += __popc(H);
+                    accumulate_round(a, tab, (uint32_t)(k - 1) + 32u * (uint32_t)(t0 + j), H, hit, e, lane);
+                }
+            }
         }
-        if (slow) {
+        if (tab.overflow) {
             if (lane == 0) {
                 a.rec[r] = make_uint2(0u, 0u);
                 a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
@@ -249,7 +317,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) analyze_reads_kernel(con
                 const uint32_t W = tab.mask[s];
                 uint32_t Wn = __shfl_down_sync(kFull, W, 1);
                 if (lane == 31) Wn = 0;
-                const uint64_t D = dilate_down((uint64_t)W | ((uint64_t)Wn << 32), a.k);
+                const uint64_t D = dilate_down((uint64_t)W | ((uint64_t)Wn << 32), k);
                 const uint32_t cov = __reduce_add_sync(kFull, (uint32_t)__popc((uint32_t)D));
                 const uint32_t hits = __reduce_add_sync(kFull, (uint32_t)__popc(W));
                 if (lane == s) {

@@ -66,7 +66,7 @@ def broadcast_index(sh, src=0):
     views = sh.index_views()
     torch.cuda.synchronize()
     e0.record()
-    for i in range(4):
+    for i in range(len(views.bytes)):
         if views.bytes[i]:
             broadcast_bytes(view_tensor(views.dev_ptr[i], views.bytes[i], dev), src)
     e1.record()

@@ -43,7 +43,7 @@ def test_struct_sizes():
     assert ctypes.sizeof(capi.IndexInfo) == 64
     assert ctypes.sizeof(capi.Assoc) == 8
     assert ctypes.sizeof(capi.ChunkResult) == 64
-    assert ctypes.sizeof(capi.IndexViews) == 32 + 32 + 64
+    assert ctypes.sizeof(capi.IndexViews) == 40 + 40 + 64
 
 
 def test_no_cpu_fallback(lib_path):
