@@ -63,7 +63,8 @@ typedef struct shk_index_info {
     uint64_t bf_bits;
     uint64_t device_bytes; /* HBM held by the index                                               */
     float build_ms;        /* device time of the whole build (CUDA events)                         */
-    float reserved_f[3];
+    uint32_t front_shift;  /* front table: log2(positions per bucket)                              */
+    uint64_t front_entries; /* front table: 16-byte entries (buckets + overflow records)          */
 } shk_index_info;
 
 /* One association = one line of the reference's stdout (ReadOutput.hpp:43): read `read_idx`

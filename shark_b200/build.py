@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
         for src in CU_SOURCES:
             obj = os.path.join(CSRC, src.replace(".cu", ".o"))
             cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3",
-                   "-c", os.path.join(CSRC, src), "-o", obj]
+                   *os.environ.get("SHK_NVCC_FLAGS", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
             subprocess.check_call(cmd)
             objs.append(obj)
         subprocess.check_call([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"])

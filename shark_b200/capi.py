@@ -38,7 +38,7 @@ class Params(C.Structure):
 class IndexInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint32), ("n_genes", C.c_uint32), ("n_set_bits", C.c_uint64), ("tot_ids", C.c_uint64),
                 ("n_windows", C.c_uint64), ("bf_bits", C.c_uint64), ("device_bytes", C.c_uint64), ("build_ms", C.c_float),
-                ("reserved_f", C.c_float * 3)]
+                ("front_shift", C.c_uint32), ("front_entries", C.c_uint64)]
 
 
 class IndexViews(C.Structure):

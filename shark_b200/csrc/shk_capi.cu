@@ -327,7 +327,7 @@ int shk_index_views_get(shk_ctx *ctx, shk_index_views *v)
     v->dev_ptr[3] = ix.csr_ids;
     v->bytes[3] = std::max<uint64_t>(ix.info.tot_ids, 1) * 2;
     v->dev_ptr[4] = ix.front;
-    v->bytes[4] = ix.fgeom.n_buckets * 16;
+    v->bytes[4] = ix.fgeom.n_entries * 16;
     v->info = ix.info;
     return SHK_OK;
 }

@@ -178,43 +178,39 @@ __device__ __forceinline__ uint32_t entry_lo(uint64_t e) { return (uint32_t)e; }
 // (load 0.03 % .. 1 %), so the set bits themselves fit in tens of MB.  The bit positions are
 // uniformly distributed hash values, which makes "bucket = position >> shift" a perfect
 // bucketing: bucket b describes positions [b << shift, (b+1) << shift) with four 32-bit slots
-//     bits 31..17 : position - (b << shift)          (shift <= 15)
-//     bit  16     : 0 = the gene list has exactly one id, in bits 15..0
-//                   1 = longer list: take the full path (bit vector -> rank -> entry)
-// 0xFFFFFFFF = empty slot; 0xFFFFFFFE in slot 3 = bucket overflowed, unmatched positions take
-// the full path.  One 16-byte load therefore answers "definitely not set" / "set, gene g" for
-// almost every probe; everything else falls back to the reference-shaped structures, so the
-// results are identical by construction.
+//     bit  31     : 0
+//     bits 30..17 : position - (b << shift)                       (shift <= 14)
+//     bit  16     : 0 = (position, gene id in bits 15..0); a position whose list has L <= 4
+//                       ids owns L such slots
+//                   1 = the position is set but its list is longer than 4 ids (the fast path
+//                       cannot hold it anyway and hands the read to the exact path)
+// 0xFFFFFFFF = empty slot.  A bucket that needs more than 4 slots keeps 3 and stores in slot 3 a
+// chain pointer (bit 31 set, low 31 bits = index of a 16-byte overflow record with the same
+// layout, appended to the same array).  One 16-byte load therefore answers "definitely not set"
+// / "set, genes g.." for almost every probe, the rest follows a short chain that is L2-resident
+// too - no probe of the fast path touches DRAM-sized structures.  The table is derived from the
+// bit vector + rank + CSR (the reference-shaped index), so results are identical by construction.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kFrontEmpty = 0xFFFFFFFFu;
-constexpr uint32_t kFrontOverflow = 0xFFFFFFFEu;
-constexpr uint32_t kFrontMultiFlag = 0x10000u;
+constexpr uint32_t kFrontLongFlag = 0x10000u;
+constexpr uint32_t kFrontChainBit = 0x80000000u;
+constexpr uint32_t kFrontMaxShift = 14;
+constexpr uint32_t kFrontInlineMax = 4;  // longest gene list stored inline
 
 struct FrontGeom {
-    uint32_t shift;     // log2(positions per bucket), 5..15
+    uint32_t shift;     // log2(positions per bucket), 5..14
     uint32_t off_mask;  // (1 << shift) - 1
     uint64_t n_buckets;
+    uint64_t n_entries;  // buckets + overflow records
 };
 
-__device__ __forceinline__ bool front_slot_matches(uint32_t slot, uint32_t off)
+__device__ __forceinline__ uint32_t front_key(uint32_t off) { return off << 17; }
+// key slot of offset `off` (either kind)?
+__device__ __forceinline__ bool front_slot_matches(uint32_t slot, uint32_t key)
 {
-    return (slot >> 17) == off && (slot & 0x1FFFFu) < 0x1FFFEu;
+    return (slot & 0xFFFE0000u) == key;  // bit 31 clear and offset equal (EMPTY and chains have bit 31 set)
 }
-
-enum FrontResult : int { FRONT_MISS = 0, FRONT_SINGLE = 1, FRONT_FULL = 2 };
-
-// -> FRONT_MISS, FRONT_SINGLE (gene id in `gene`) or FRONT_FULL (consult the bit vector)
-__device__ __forceinline__ int front_lookup(const uint4 &q, uint32_t off, uint32_t &gene)
-{
-    const bool m0 = front_slot_matches(q.x, off), m1 = front_slot_matches(q.y, off),
-               m2 = front_slot_matches(q.z, off), m3 = front_slot_matches(q.w, off);
-    const uint32_t sl = m0 ? q.x : (m1 ? q.y : (m2 ? q.z : q.w));
-    if (m0 | m1 | m2 | m3) {
-        gene = sl & 0xFFFFu;
-        return (sl & kFrontMultiFlag) ? FRONT_FULL : FRONT_SINGLE;
-    }
-    return q.w == kFrontOverflow ? FRONT_FULL : FRONT_MISS;
-}
+__device__ __forceinline__ bool front_is_chain(uint32_t slot) { return (slot & kFrontChainBit) && slot != kFrontEmpty; }
 
 __device__ __forceinline__ uint4 ld_front(const uint4 *p, uint64_t pol)
 {
@@ -222,6 +218,14 @@ __device__ __forceinline__ uint4 ld_front(const uint4 *p, uint64_t pol)
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p), "l"(pol));
+    return r;
+}
+// text words: keep the 128-byte line in L1 (the thread comes back for the next word), but let it
+// leave L2 first
+__device__ __forceinline__ uint32_t ld_text_word(const uint32_t *p, uint64_t pol_evict_first)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol_evict_first));
     return r;
 }
 

@@ -2,6 +2,7 @@
 // main.cpp, and both BF::switch_mode transitions.  Also the stand-alone probe (BF::get_index) and
 // the random-sector microbenchmark.  Citations are reference file:line.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "shk_internal.h"
@@ -372,15 +373,17 @@ export_positions_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors
     }
 }
 
-// Front table fill (see shk_device.cuh): one thread per filter sector walks its set bits in rank
-// order and inserts (offset, single gene | multi flag) into the bucket of each position with
-// compare-and-swap on the first free slot; a fifth key turns slot 3 into the overflow marker.
-__global__ void __launch_bounds__(256)
-front_fill_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, const uint64_t *__restrict__ entries,
-                  FrontGeom fg, uint32_t *front)
+// Front table build (layout in shk_device.cuh).  Every set bit contributes L slots to its bucket
+// (L = list length if <= 4, else one "long list" slot).  Three passes over the set bits / buckets:
+//   front_count   slots needed per bucket
+//   (scan)        overflow records needed per bucket -> first record index of each bucket
+//   front_place   each set bit claims its logical slot range in the bucket with one atomicAdd and
+//                 writes its slots; logical slot t lives in the bucket (t < 3 or the bucket fits)
+//                 or in overflow record (t-3)/3, slot (t-3)%3
+//   front_chain   chain pointers of the overflowing buckets
+template <class F>
+__device__ __forceinline__ void for_each_set_bit(const uint32_t *__restrict__ sectors, uint64_t s, F f)
 {
-    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_sectors) return;
     const uint4 *sp = reinterpret_cast<const uint4 *>(sectors + s * 8);
     uint4 a = sp[0], b = sp[1];
     uint32_t w[7] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z};
@@ -391,20 +394,80 @@ front_fill_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, cons
         while (bits) {
             int bpos = __ffs(bits) - 1;
             bits &= bits - 1;
-            const uint64_t p = (s * kWordsPerSector + i) * 32 + bpos;
-            const uint64_t e = entries[r++];
-            const uint32_t off = (uint32_t)p & fg.off_mask;
-            const uint32_t v = (off << 17) | (entry_len(e) == 1 ? entry_id0(e) : kFrontMultiFlag);
-            uint32_t *slot = front + (p >> fg.shift) * 4;
-            bool placed = false;
-            for (int j = 0; j < 4 && !placed; ++j) {
-                uint32_t old = atomicCAS(&slot[j], kFrontEmpty, v);
-                placed = old == kFrontEmpty;
-                if (!placed && old == kFrontOverflow) placed = true;  // already overflowed
-            }
-            if (!placed) atomicExch(&slot[3], kFrontOverflow);
+            f((s * kWordsPerSector + i) * 32 + bpos, r++);
         }
     }
+}
+
+__device__ __forceinline__ uint32_t front_slots_of(uint64_t e)
+{
+    const uint32_t ln = entry_len(e);
+    return ln <= kFrontInlineMax ? ln : 1u;
+}
+
+__global__ void __launch_bounds__(256)
+front_count_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, const uint64_t *__restrict__ entries,
+                   FrontGeom fg, uint32_t *cnt)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sectors) return;
+    for_each_set_bit(sectors, s, [&](uint64_t p, uint32_t r) { atomicAdd(&cnt[p >> fg.shift], front_slots_of(entries[r])); });
+}
+
+// overflow records needed by a bucket with c slots: 3 stay in the bucket, the rest in records of 3
+struct FrontRecordsIn {
+    const uint32_t *cnt;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const
+    {
+        uint32_t c = cnt[i];
+        return c <= 4 ? 0u : (c - 3u + 2u) / 3u;
+    }
+};
+
+__device__ __forceinline__ uint32_t *front_slot_ptr(uint32_t *front, uint64_t bucket, uint32_t total, uint32_t t,
+                                                    uint64_t n_buckets, uint32_t rec_base)
+{
+    if (total <= 4 || t < 3) return front + bucket * 4 + t;
+    const uint32_t u = t - 3;
+    return front + (n_buckets + rec_base + u / 3) * 4 + (u % 3);
+}
+
+__global__ void __launch_bounds__(256)
+front_place_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, const uint64_t *__restrict__ entries,
+                   const uint16_t *__restrict__ csr_ids, FrontGeom fg, const uint32_t *__restrict__ cnt,
+                   const uint32_t *__restrict__ rec_base, uint32_t *cur, uint32_t *front)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sectors) return;
+    for_each_set_bit(sectors, s, [&](uint64_t p, uint32_t r) {
+        const uint64_t e = entries[r];
+        const uint64_t bkt = p >> fg.shift;
+        const uint32_t key = front_key((uint32_t)p & fg.off_mask);
+        const uint32_t ln = entry_len(e), L = front_slots_of(e);
+        const uint32_t total = cnt[bkt], rb = rec_base[bkt];
+        const uint32_t t0 = atomicAdd(&cur[bkt], L);
+        if (ln > kFrontInlineMax) {
+            *front_slot_ptr(front, bkt, total, t0, fg.n_buckets, rb) = key | kFrontLongFlag;
+        } else {
+            for (uint32_t i = 0; i < ln; ++i) {
+                uint32_t g = i == 0 ? entry_id0(e) : (ln == 2 ? entry_lo(e) : (uint32_t)csr_ids[entry_lo(e) + i]);
+                *front_slot_ptr(front, bkt, total, t0 + i, fg.n_buckets, rb) = key | g;
+            }
+        }
+    });
+}
+
+__global__ void __launch_bounds__(256)
+front_chain_kernel(FrontGeom fg, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ rec_base, uint32_t *front)
+{
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= fg.n_buckets) return;
+    const uint32_t c = cnt[b];
+    if (c <= 4) return;
+    const uint32_t nrec = (c - 3u + 2u) / 3u, rb = rec_base[b];
+    front[b * 4 + 3] = kFrontChainBit | (uint32_t)(fg.n_buckets + rb);
+    for (uint32_t i = 0; i + 1 < nrec; ++i)
+        front[(fg.n_buckets + rb + i) * 4 + 3] = kFrontChainBit | (uint32_t)(fg.n_buckets + rb + i + 1);
 }
 
 // =============================================================================================
@@ -439,20 +502,82 @@ static void free_index_arrays(DeviceIndex &ix)
     ix.built = false;
 }
 
-// Front table geometry: about 0.7 keys per 4-slot bucket, at least 32 positions per bucket (the
-// table is then at most 4x the plain bit vector), at most 2^15 (15-bit offsets).
+// Front table geometry: at most ~0.7 keys per 4-slot bucket (C2: 64 MB for 2.8 M keys; measured
+// faster than 1.5 keys/bucket = 32 MB because chains are rarer, profiles/analyze_r1_v3.md), at
+// least 32 positions per bucket (the table is then at most 4x the plain bit vector), at most 2^14
+// (14-bit offsets).  SHK_FRONT_LOAD overrides the 0.7 (tuning).
+static void front_geometry(DeviceIndex &ix)
+{
+    double load = 0.7;
+    if (const char *ev = getenv("SHK_FRONT_LOAD")) {
+        double v = atof(ev);
+        if (v > 0.01 && v < 64) load = v;
+    }
+    const double per_key = load * (double)ix.geom.bf_bits / (double)std::max<uint64_t>(ix.info.n_set_bits, 1);
+    uint32_t shift = 5;
+    while (shift < kFrontMaxShift && (double)(1ull << (shift + 1)) <= per_key) ++shift;
+    ix.fgeom.shift = shift;
+    ix.fgeom.off_mask = (1u << shift) - 1u;
+    ix.fgeom.n_buckets = (ix.geom.bf_bits + (1ull << shift) - 1) >> shift;
+}
+
+// Allocates the table for a known geometry (info.front_shift / info.front_entries): used when the
+// index is adopted from another GPU.
 int index_alloc_front(shk_ctx *ctx)
 {
     DeviceIndex &ix = ctx->index;
     if (ix.front) cudaFree(ix.front);
     ix.front = nullptr;
-    const double per_key = 0.7 * (double)ix.geom.bf_bits / (double)std::max<uint64_t>(ix.info.n_set_bits, 1);
-    uint32_t shift = 5;
-    while (shift < 15 && (double)(1ull << (shift + 1)) <= per_key) ++shift;
-    ix.fgeom.shift = shift;
-    ix.fgeom.off_mask = (1u << shift) - 1u;
-    ix.fgeom.n_buckets = (ix.geom.bf_bits + (1ull << shift) - 1) >> shift;
-    SHK_CUDA(ctx, cudaMalloc((void **)&ix.front, ix.fgeom.n_buckets * 16));
+    ix.fgeom.shift = ix.info.front_shift;
+    ix.fgeom.off_mask = (1u << ix.fgeom.shift) - 1u;
+    ix.fgeom.n_buckets = (ix.geom.bf_bits + (1ull << ix.fgeom.shift) - 1) >> ix.fgeom.shift;
+    ix.fgeom.n_entries = ix.info.front_entries;
+    if (ix.fgeom.n_entries < ix.fgeom.n_buckets || ix.fgeom.shift < 5 || ix.fgeom.shift > kFrontMaxShift)
+        return fail(ctx, SHK_E_ARG, "inconsistent front table geometry in index info");
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.front, ix.fgeom.n_entries * 16));
+    return SHK_OK;
+}
+
+static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries, const uint16_t *d_csr_ids,
+                       uint32_t *d_tiles, uint32_t *d_scalar)
+{
+    DeviceIndex &ix = ctx->index;
+    front_geometry(ix);
+    const uint64_t nb = ix.fgeom.n_buckets;
+    if (nb >= 0x7FFFFFFFull) return fail(ctx, SHK_E_LIMIT, "front table too large");
+    DevBuf<uint32_t> d_cnt, d_cur, d_rec;
+    SHK_CUDA(ctx, d_cnt.alloc(nb));
+    SHK_CUDA(ctx, d_cur.alloc(nb));
+    SHK_CUDA(ctx, d_rec.alloc(nb + 1));
+    SHK_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, nb * 4, st));
+    SHK_CUDA(ctx, cudaMemsetAsync(d_cur.p, 0, nb * 4, st));
+    const unsigned blocks_s = (unsigned)((ix.geom.n_sectors + 255) / 256);
+    uint32_t n_rec = 0;
+    if (ix.info.n_set_bits > 0) {
+        front_count_kernel<<<blocks_s, 256, 0, st>>>(ix.sectors, ix.geom.n_sectors, d_entries, ix.fgeom, d_cnt.p);
+        ctx->launches += 1;
+        int rc = exclusive_scan(ctx, st, FrontRecordsIn{d_cnt.p}, U32Out{d_rec.p}, nb, d_tiles, d_scalar);
+        if (rc) return rc;
+        SHK_CUDA(ctx, cudaMemcpyAsync(&n_rec, d_scalar, 4, cudaMemcpyDeviceToHost, st));
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    ix.fgeom.n_entries = nb + n_rec;
+    if (ix.fgeom.n_entries >= 0x7FFFFFFFull) return fail(ctx, SHK_E_LIMIT, "front table too large");
+    if (ix.front) cudaFree(ix.front);
+    ix.front = nullptr;
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.front, ix.fgeom.n_entries * 16));
+    SHK_CUDA(ctx, cudaMemsetAsync(ix.front, 0xFF, ix.fgeom.n_entries * 16, st));
+    if (ix.info.n_set_bits > 0) {
+        uint32_t *f32 = reinterpret_cast<uint32_t *>(ix.front);
+        front_place_kernel<<<blocks_s, 256, 0, st>>>(ix.sectors, ix.geom.n_sectors, d_entries, d_csr_ids, ix.fgeom,
+                                                     d_cnt.p, d_rec.p, d_cur.p, f32);
+        front_chain_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(ix.fgeom, d_cnt.p, d_rec.p, f32);
+        ctx->launches += 2;
+        SHK_CUDA(ctx, cudaGetLastError());
+    }
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));  // the temporaries die with this scope
+    ix.info.front_shift = ix.fgeom.shift;
+    ix.info.front_entries = ix.fgeom.n_entries;
     return SHK_OK;
 }
 
@@ -585,15 +710,12 @@ int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *r
     }
     // front table over the finished entries
     ix.info.n_set_bits = n_set;
-    rc = index_alloc_front(ctx);
-    if (rc) return rc;
-    SHK_CUDA(ctx, cudaMemsetAsync(ix.front, 0xFF, ix.fgeom.n_buckets * 16, st));
-    if (n_set > 0) {
-        unsigned blocks_s = (unsigned)((ix.geom.n_sectors + 255) / 256);
-        front_fill_kernel<<<blocks_s, 256, 0, st>>>(ix.sectors, ix.geom.n_sectors, d_entries.p, ix.fgeom,
-                                                    reinterpret_cast<uint32_t *>(ix.front));
-        ctx->launches += 1;
-        SHK_CUDA(ctx, cudaGetLastError());
+    {
+        uint64_t need_tiles = (((ix.geom.bf_bits + 31) >> 5) + kScanTile - 1) / kScanTile + 2;
+        DevBuf<uint32_t> d_tiles2;
+        SHK_CUDA(ctx, d_tiles2.alloc(need_tiles));
+        rc = build_front(ctx, st, d_entries.p, d_csr_ids.p, d_tiles2.p, d_scalars.p + 5);
+        if (rc) return rc;
     }
     SHK_CUDA(ctx, cudaEventRecord(e1, st));
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
@@ -611,7 +733,7 @@ int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *r
     ix.info.tot_ids = tot_ids;
     ix.info.n_windows = h_nwin;
     ix.info.bf_bits = ix.geom.bf_bits;
-    ix.info.device_bytes = sector_bytes + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2 + ix.fgeom.n_buckets * 16;
+    ix.info.device_bytes = sector_bytes + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2 + ix.fgeom.n_entries * 16;
     ix.info.build_ms = ms;
     ix.built = true;
     return SHK_OK;

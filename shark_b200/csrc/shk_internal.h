@@ -74,7 +74,7 @@ struct ReadKernelArgs {
     uint8_t *keep;
 };
 
-constexpr uint32_t kReadsPerTile = 64;  // one CTA of 8 warps x 8 reads
+constexpr uint32_t kReadsPerTile = 128;  // one CTA of the fast kernel: 128 threads = 128 reads
 constexpr uint32_t kMaxFastLen = 1024;  // longer reads take the exact path (32 chunks x 32)
 
 struct Slot {

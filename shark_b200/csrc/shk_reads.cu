@@ -2,11 +2,11 @@
 // and the ordering contract of ReadOutput.  Citations are reference file:line.
 //
 // Kernels of one chunk (all on the slot's stream):
-//   analyze_reads_kernel   one warp per read: mask, 2-bit pack, canonical k-mers, front-table probe
+//   analyze_reads_kernel   one THREAD per read: mask, rolling canonical k-mers, front-table probe
 //                          (one 16-byte load per k-mer), per-gene coverage/hits in a
-//                          register-resident 8-gene table, argmax, threshold
-//   analyze_slow_kernel    exact path for reads the fast path gives up on (more than 8 genes, a
-//                          list longer than 8, or a text longer than 1024 bytes)
+//                          register-resident 4-gene table, argmax, threshold
+//   analyze_slow_kernel    exact warp-per-read path for reads the fast path gives up on (more than
+//                          4 genes, a list longer than 4, or a text longer than 1024 bytes)
 //   scan_tile_sums_kernel  exclusive scan of the per-tile association counts
 //   scatter_assoc_kernel   ordered (read_idx, gene_idx) list + keep flags
 #include "shk_internal.h"
@@ -14,10 +14,6 @@
 
 namespace shk {
 
-constexpr int kSlots = 8;        // genes tracked per read on the fast path
-constexpr int kGroup = 3;        // rounds of 32 windows whose probes are in flight together
-constexpr int kWarpsPerCta = 8;
-constexpr int kReadsPerWarp = kReadsPerTile / kWarpsPerCta;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
@@ -26,62 +22,6 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
     uint32_t hi = __shfl_sync(kFull, (uint32_t)(v >> 32), src);
     return ((uint64_t)hi << 32) | lo;
 }
-
-// Union of the intervals [e-k+1, e] over the set bits e of M (64 positions, bit x = position x):
-// position x is covered iff some e in [x, x+k-1] is set.
-__device__ __forceinline__ uint64_t dilate_down(uint64_t m, int k)
-{
-    int covered = 1;
-    while (covered * 2 <= k) {
-        m |= m >> covered;
-        covered *= 2;
-    }
-    if (covered < k) m |= m >> (k - covered);
-    return m;
-}
-
-// Per-read gene table of the fast path, held in registers of the whole warp:
-//   slot s (0..kSlots-1): gene id lives in lane s of `gene`; its hit bitmask over window end
-//   positions is spread over the lanes - lane c holds the word for positions [32c, 32c+32).
-struct WarpTable {
-    uint32_t gene;
-    uint32_t mask[kSlots];
-    int nslots;
-    bool overflow;
-
-    __device__ __forceinline__ void init()
-    {
-        gene = 0xFFFFFFFFu;
-        nslots = 0;
-        overflow = false;
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) mask[s] = 0;
-    }
-    // all arguments are warp-uniform: gene g was hit by the windows ending at positions
-    // base + i for every set bit i of m
-    __device__ __forceinline__ void update(uint32_t g, uint32_t base, uint32_t m, int lane)
-    {
-        uint32_t found = __ballot_sync(kFull, lane < nslots && gene == g);
-        int idx;
-        if (found) {
-            idx = __ffs(found) - 1;
-        } else {
-            if (nslots == kSlots) {
-                overflow = true;
-                return;
-            }
-            idx = nslots++;
-            if (lane == idx) gene = g;
-        }
-        const uint32_t w0 = base >> 5, sh = base & 31u;
-        uint32_t add = 0;
-        if ((uint32_t)lane == w0) add = m << sh;
-        else if ((uint32_t)lane == w0 + 1 && sh) add = m >> (32u - sh);
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s)
-            if (s == idx) mask[s] |= add;
-    }
-};
 
 // One 32-position chunk of a read text: load, mask (FastqSplitter.hpp:104-109), validity and
 // 2-bit codes (kmer_utils.hpp:29-41), pack to 64 bits, and for the lane's window
@@ -133,32 +73,6 @@ __device__ __forceinline__ bool chunk_window(const ReadKernelArgs &a, uint32_t o
     return wv;
 }
 
-// Adds the hits of one round (windows ending at base + lane) to the table.  H = ballot of hit
-// lanes, e = the lane's entry.
-__device__ __forceinline__ void accumulate_round(const ReadKernelArgs &a, WarpTable &tab, uint32_t base, uint32_t H,
-                                                 bool hit, uint64_t e, int lane)
-{
-    uint32_t rem = H;
-    while (rem && !tab.overflow) {
-        const int leader = __ffs(rem) - 1;
-        const uint64_t el = shfl64(e, leader);
-        const uint32_t grp = __ballot_sync(kFull, hit && e == el);  // lanes with the identical list
-        rem &= ~grp;
-        const uint32_t ln = entry_len(el);
-        if (ln > (uint32_t)kSlots) {
-            tab.overflow = true;
-            break;
-        }
-        tab.update(entry_id0(el), base, grp, lane);
-        if (ln == 2) {
-            tab.update(entry_lo(el), base, grp, lane);
-        } else if (ln >= 3) {
-            const uint32_t b = entry_lo(el);
-            for (uint32_t t = 1; t < ln; ++t) tab.update(a.csr_ids[b + t], base, grp, lane);
-        }
-    }
-}
-
 // Writes the winners (ascending gene id) of a read with >= 2 associations into the tie pool.
 // Returns the pool offset (warp-uniform); sets the overflow flag when the pool is exhausted.
 __device__ __forceinline__ uint32_t pool_reserve(const ReadKernelArgs &a, uint32_t count, int lane)
@@ -186,180 +100,225 @@ __device__ __forceinline__ bool full_probe(const ReadKernelArgs &a, uint64_t p, 
     return true;
 }
 
-template <bool HAS_QUAL, int MOD>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) analyze_reads_kernel(const ReadKernelArgs a)
-{
-    // per warp: packed 2-bit codes and validity masks of the read's 32-byte chunks; index c+1
-    // holds chunk c, index 0 is the all-invalid chunk "-1"
-    __shared__ uint64_t sP[kWarpsPerCta][kMaxFastLen / 32 + 2];
-    __shared__ uint32_t sV[kWarpsPerCta][kMaxFastLen / 32 + 2];
-    __shared__ uint32_t s_assoc[kWarpsPerCta];
-    __shared__ uint32_t s_probes[kWarpsPerCta];
-    __shared__ uint32_t s_hits[kWarpsPerCta];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
-    uint32_t warp_assoc = 0, warp_probes = 0, warp_hits = 0;
-    const int k = a.k;
-    const uint32_t kbits = (1u << k) - 1u;
-    const uint64_t kmask2 = (1ULL << (2 * k)) - 1ULL;
-    if (lane == 0) {
-        sP[warp][0] = 0;
-        sV[warp][0] = 0;
-    }
+// ---------------------------------------------------------------------------------------------
+// Fast path: ONE THREAD PER READ.  The thread walks its read exactly like the reference does
+// (ReadAnalyzer.hpp:50-87): rolling forward / reverse-complement k-mers (kmer_utils.hpp:73-79), a
+// run counter for "k valid bytes in a row" (== build_kmer's restart after a non-ACGT byte,
+// kmer_utils.hpp:57-71), one front-table probe per window, and the reference's own sequential
+// per-gene update `cov += min(k, pos - last); hits += 1; last = pos` in a 4-gene register table.
+// Four consecutive positions (one 32-bit word of text) are processed together so that four
+// probes are in flight per thread.  Reads that need more than 4 genes, or are longer than
+// kMaxFastLen, go to the exact warp-per-read path.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTSlots = 4;
+constexpr int kFastThreads = 128;
+#ifndef SHK_FAST_MIN_BLOCKS
+#define SHK_FAST_MIN_BLOCKS 5
+#endif
+static_assert(kFastThreads == (int)kReadsPerTile, "one CTA of the fast kernel = one scan tile");
 
-    for (int it = 0; it < kReadsPerWarp; ++it) {
-        const uint32_t r = blockIdx.x * kReadsPerTile + (uint32_t)it * kWarpsPerCta + (uint32_t)warp;
-        if (r >= a.n_reads) break;
+struct GeneTable {
+    uint32_t gene[kTSlots], cov[kTSlots], hits[kTSlots], last[kTSlots];
+    int n;
+    bool overflow;
+
+    __device__ __forceinline__ void init()
+    {
+        n = 0;
+        overflow = false;
+#pragma unroll
+        for (int i = 0; i < kTSlots; ++i) gene[i] = 0xFFFFFFFFu, cov[i] = hits[i] = last[i] = 0;
+    }
+    // ReadAnalyzer.hpp:57-61 / 80-85 for one gene id of the window ending at pos.  A fresh
+    // std::map entry has last == 0 and `pos - 0 >= k` for every window, so its coverage is k.
+    __device__ __forceinline__ void hit(uint32_t g, uint32_t pos, uint32_t k)
+    {
+        bool done = false;
+#pragma unroll
+        for (int i = 0; i < kTSlots; ++i) {
+            if (!done && gene[i] == g) {
+                cov[i] += min(k, pos - last[i]);
+                hits[i] += 1;
+                last[i] = pos;
+                done = true;
+            }
+        }
+        if (!done) {
+            if (n == kTSlots) {
+                overflow = true;
+                return;
+            }
+#pragma unroll
+            for (int i = 0; i < kTSlots; ++i) {
+                if (i == n) {
+                    gene[i] = g;
+                    cov[i] = k;
+                    hits[i] = 1;
+                    last[i] = pos;
+                }
+            }
+            ++n;
+        }
+    }
+};
+
+template <bool HAS_QUAL, int MOD>
+__global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_reads_kernel(const ReadKernelArgs a)
+{
+    __shared__ uint32_t s_assoc[kFastThreads / 32];
+    __shared__ uint32_t s_probes[kFastThreads / 32];
+    __shared__ uint32_t s_hits[kFastThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * kFastThreads + threadIdx.x;
+    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
+    const uint32_t k = (uint32_t)a.k;
+    const uint64_t kmask2 = (1ULL << (2 * k)) - 1ULL;
+    const int rc_shift = 2 * (int)k - 2;
+    uint32_t count = 0, payload = 0, my_probes = 0, my_hits = 0;
+    bool slow = false;
+
+    if (r < a.n_reads) {
         const uint32_t off0 = a.off[r];
         const uint32_t n = a.off[r + 1] - off0;
         if (n > kMaxFastLen) {
-            if (lane == 0) {
-                a.rec[r] = make_uint2(0u, 0u);
-                a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
-            }
-            continue;
-        }
-        // ---- phase 1: text -> validity masks + packed codes (FastqSplitter.hpp:104-109,
-        //      kmer_utils.hpp:29-41), number of valid bases (ReadAnalyzer.hpp:46-49)
-        const int nch = (int)((n + 31u) >> 5);
-        uint32_t len = 0;
-        __syncwarp();
-        for (int c = 0; c < nch; ++c) {
-            const uint32_t pos = (uint32_t)c * 32u + (uint32_t)lane;
-            uint32_t ch = 0;
-            if (pos < n) {
-                ch = a.seq[off0 + pos];
-                if (HAS_QUAL) {
-                    int q = (int)(signed char)a.qual[off0 + pos];
-                    if (q < a.mq) ch = (ch - 64u) & 0xFFu;  // seq[i] = seq[i] - 64
-                }
-            }
-            const bool valid = base_valid(ch);
-            const uint32_t V = __ballot_sync(kFull, valid);
-            len += __popc(V);
-            const uint32_t val = valid ? base_code(ch) << (30 - 2 * (lane & 15)) : 0u;
-            const uint32_t hiw = __reduce_or_sync(kFull, lane < 16 ? val : 0u);
-            const uint32_t low = __reduce_or_sync(kFull, lane >= 16 ? val : 0u);
-            if (lane == 0) {
-                sP[warp][c + 1] = ((uint64_t)hiw << 32) | low;
-                sV[warp][c + 1] = V;
-            }
-        }
-        __syncwarp();
-        // ---- phase 2: every candidate window end e = k-1 .. n-1, 32 per round, kGroup rounds of
-        //      front-table loads in flight (ReadAnalyzer.hpp:50-87 without the sequential roll)
-        WarpTable tab;
-        tab.init();
-        const int n_rounds = n >= (uint32_t)k && len >= (uint32_t)k ? (int)((n - (uint32_t)k + 32u) >> 5) : 0;
-        for (int t0 = 0; t0 < n_rounds && !tab.overflow; t0 += kGroup) {
-            uint4 q[kGroup];
-            uint32_t bucket[kGroup], offk[kGroup];
-            bool wv[kGroup];
+            slow = true;
+        } else {
+            GeneTable tab;
+            tab.init();
+            uint64_t fwd = 0, rc = 0;
+            uint32_t run = 0, len = 0;
+            const uint32_t head = off0 & 3u;
+            const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.seq) + (off0 >> 2);
+            const uint32_t *qualw = HAS_QUAL ? reinterpret_cast<const uint32_t *>(a.qual) + (off0 >> 2) : nullptr;
+            const uint32_t n_words = (head + n + 3u) >> 2;
+            for (uint32_t j = 0; j < n_words && !tab.overflow; ++j) {
+                const uint32_t w = ld_text_word(seqw + j, pol_first);
+                uint32_t qw = 0;
+                if (HAS_QUAL) qw = ld_text_word(qualw + j, pol_first);
+                uint32_t bucket[4], offk[4];
+                bool wv[4];
 #pragma unroll
-            for (int j = 0; j < kGroup; ++j) {
-                wv[j] = false;
-                bucket[j] = offk[j] = 0;
-                const uint32_t e = (uint32_t)(k - 1) + 32u * (uint32_t)(t0 + j) + (uint32_t)lane;
-                if (t0 + j < n_rounds && e < n) {
-                    const uint32_t c = e >> 5, i = e & 31u;
-                    const uint64_t VV = (uint64_t)sV[warp][c] | ((uint64_t)sV[warp][c + 1] << 32);
-                    wv[j] = (((uint32_t)(VV >> (33u + i - (uint32_t)k))) & kbits) == kbits;
-                    if (wv[j]) {
-                        const int sh = 2 * (31 - (int)i);
-                        uint64_t fwd = sP[warp][c + 1] >> sh;
-                        if (sh) fwd |= sP[warp][c] << (64 - sh);
-                        fwd &= kmask2;
-                        const uint64_t p = bit_index<MOD>(xxh64_u64(canonical(fwd, k)), a.geom);
-                        bucket[j] = (uint32_t)(p >> a.fgeom.shift);
-                        offk[j] = (uint32_t)p & a.fgeom.off_mask;
+                for (int b = 0; b < 4; ++b) {
+                    wv[b] = false;
+                    bucket[b] = offk[b] = 0;
+                    const uint32_t pos = 4u * j + (uint32_t)b - head;  // wraps for bytes before the read
+                    if (pos < n) {
+                        uint32_t ch = (w >> (8 * b)) & 0xFFu;
+                        if (HAS_QUAL) {
+                            const int q = (int)(signed char)((qw >> (8 * b)) & 0xFFu);
+                            if (q < a.mq) ch = (ch - 64u) & 0xFFu;  // FastqSplitter.hpp:106
+                        }
+                        if (base_valid(ch)) {
+                            const uint64_t code = base_code(ch);
+                            fwd = ((fwd << 2) | code) & kmask2;      // lsappend, kmer_utils.hpp:73-75
+                            rc = (rc >> 2) | ((3ULL - code) << rc_shift);  // rsprepend(reverse_char), 77-79
+                            ++run;
+                            ++len;  // ReadAnalyzer.hpp:46-49
+                        } else {
+                            run = 0;
+                        }
+                        if (run >= k) {
+                            const uint64_t p = bit_index<MOD>(xxh64_u64(fwd < rc ? fwd : rc), a.geom);
+                            bucket[b] = (uint32_t)(p >> a.fgeom.shift);
+                            offk[b] = (uint32_t)p & a.fgeom.off_mask;
+                            wv[b] = true;
+                        }
+                    }
+                }
+                uint4 q[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (wv[b]) q[b] = ld_front(a.front + bucket[b], pol_last);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (wv[b]) {
+                        ++my_probes;
+                        const uint32_t pos = 4u * j + (uint32_t)b - head;
+                        const uint32_t key = front_key(offk[b]);
+                        uint4 qq = q[b];
+                        bool any = false;
+                        for (;;) {  // the bucket, then (rarely) its chain of overflow records
+                            const bool m0 = front_slot_matches(qq.x, key), m1 = front_slot_matches(qq.y, key),
+                                       m2 = front_slot_matches(qq.z, key), m3 = front_slot_matches(qq.w, key);
+                            if (m0 | m1 | m2 | m3) {
+                                any = true;
+                                const uint32_t first = m0 ? qq.x : (m1 ? qq.y : (m2 ? qq.z : qq.w));
+                                if (first & kFrontLongFlag) {
+                                    tab.overflow = true;  // list longer than 4 ids: exact path
+                                } else {
+                                    tab.hit(first & 0xFFFFu, pos, k);
+                                    if ((int)m0 + (int)m1 + (int)m2 + (int)m3 > 1) {  // list of 2..4 ids
+                                        if (m0 && m1) tab.hit(qq.y & 0xFFFFu, pos, k);
+                                        if ((m0 | m1) && m2) tab.hit(qq.z & 0xFFFFu, pos, k);
+                                        if ((m0 | m1 | m2) && m3) tab.hit(qq.w & 0xFFFFu, pos, k);
+                                    }
+                                }
+                            }
+                            if (!front_is_chain(qq.w)) break;
+                            qq = ld_front(a.front + (qq.w & 0x7FFFFFFFu), pol_last);
+                        }
+                        my_hits += any ? 1u : 0u;
                     }
                 }
             }
+            if (tab.overflow) {
+                slow = true;
+            } else {
+                // argmax with ties (ReadAnalyzer.hpp:90-102), threshold and -s (ReadAnalyzer.hpp:104)
+                uint32_t maxc = 0, maxh = 0;
 #pragma unroll
-            for (int j = 0; j < kGroup; ++j)
-                q[j] = wv[j] ? ld_front(a.front + bucket[j], pol_last) : make_uint4(kFrontEmpty, kFrontEmpty, kFrontEmpty, kFrontEmpty);
-#pragma unroll
-            for (int j = 0; j < kGroup; ++j) {
-                if (t0 + j >= n_rounds) break;
-                uint32_t g = 0;
-                uint64_t e = 0;
-                bool hit = false;
-                if (wv[j]) {
-                    const int res = front_lookup(q[j], offk[j], g);
-                    if (res == FRONT_SINGLE) {
-                        hit = true;
-                        e = make_entry(g, 1u, 0u);
-                    } else if (res == FRONT_FULL) {
-                        const uint64_t p = ((uint64_t)bucket[j] << a.fgeom.shift) | offk[j];
-                        hit = full_probe(a, p, pol_first, pol_last, e);
+                for (int i = 0; i < kTSlots; ++i) {
+                    if (i < tab.n && (tab.cov[i] > maxc || (tab.cov[i] == maxc && tab.hits[i] > maxh))) {
+                        maxc = tab.cov[i];
+                        maxh = tab.hits[i];
                     }
                 }
-                warp_probes += __popc(__ballot_sync(kFull, wv[j]));
-                const uint32_t H = __ballot_sync(kFull, hit);
-                if (H) {
-                    warp_hits += __popc(H);
-                    accumulate_round(a, tab, (uint32_t)(k - 1) + 32u * (uint32_t)(t0 + j), H, hit, e, lane);
-                }
-            }
-        }
-        if (tab.overflow) {
-            if (lane == 0) {
-                a.rec[r] = make_uint2(0u, 0u);
-                a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
-            }
-            continue;
-        }
-        // per-gene coverage and hit count (ReadAnalyzer.hpp:58-60,81-83 in closed form)
-        uint32_t mycov = 0, myhits = 0;
+                uint32_t wg[kTSlots];
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-            if (s < tab.nslots) {
-                const uint32_t W = tab.mask[s];
-                uint32_t Wn = __shfl_down_sync(kFull, W, 1);
-                if (lane == 31) Wn = 0;
-                const uint64_t D = dilate_down((uint64_t)W | ((uint64_t)Wn << 32), k);
-                const uint32_t cov = __reduce_add_sync(kFull, (uint32_t)__popc((uint32_t)D));
-                const uint32_t hits = __reduce_add_sync(kFull, (uint32_t)__popc(W));
-                if (lane == s) {
-                    mycov = cov;
-                    myhits = hits;
+                for (int i = 0; i < kTSlots; ++i) {
+                    const bool is = i < tab.n && tab.cov[i] == maxc && tab.hits[i] == maxh;
+                    wg[i] = is ? tab.gene[i] : 0xFFFFFFFFu;
+                    count += is ? 1u : 0u;
+                }
+                const bool pass = count > 0 && (double)maxc >= __dmul_rn(a.c, (double)len) && (!a.single || count == 1);
+                if (!pass) count = 0;
+                if (count == 1) {
+                    payload = min(min(wg[0], wg[1]), min(wg[2], wg[3]));
+                } else if (count >= 2) {
+                    // ascending gene order = std::map order: sort the (at most 4) winners
+#define SHK_CSWAP(x, y) { const uint32_t lo_ = min(wg[x], wg[y]), hi_ = max(wg[x], wg[y]); wg[x] = lo_; wg[y] = hi_; }
+                    SHK_CSWAP(0, 1) SHK_CSWAP(2, 3) SHK_CSWAP(0, 2) SHK_CSWAP(1, 3) SHK_CSWAP(1, 2)
+#undef SHK_CSWAP
+                    payload = atomicAdd(&a.counters->pool_used, count);
+                    if ((uint64_t)payload + count > a.pool_cap) {
+                        a.counters->pool_overflow = 1;
+                        payload = 0xFFFFFFFFu;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kTSlots; ++i)
+                            if ((uint32_t)i < count) a.pool[payload + i] = wg[i];
+                    }
                 }
             }
         }
-        // argmax with ties (ReadAnalyzer.hpp:90-102), threshold and -s (ReadAnalyzer.hpp:104)
-        const bool live = lane < tab.nslots;
-        const uint32_t maxc = __reduce_max_sync(kFull, live ? mycov : 0u);
-        const uint32_t maxh = __reduce_max_sync(kFull, (live && mycov == maxc) ? myhits : 0u);
-        uint32_t win = __ballot_sync(kFull, live && mycov == maxc && myhits == maxh);
-        uint32_t count = (uint32_t)__popc(win);
-        const bool pass = count > 0 && (double)maxc >= __dmul_rn(a.c, (double)len) && (!a.single || count == 1);
-        if (!pass) count = 0;
-        uint32_t payload = 0;
-        if (count == 1) {
-            payload = __shfl_sync(kFull, tab.gene, __ffs(win) - 1);
-        } else if (count >= 2) {
-            payload = pool_reserve(a, count, lane);
-            if (payload != 0xFFFFFFFFu) {
-                for (uint32_t t = 0; t < count; ++t) {  // ascending gene order = std::map order
-                    const bool in = (win >> lane) & 1u;
-                    const uint32_t gmin = __reduce_min_sync(kFull, in ? tab.gene : 0xFFFFFFFFu);
-                    if (lane == 0) a.pool[payload + t] = gmin;
-                    win &= ~__ballot_sync(kFull, in && tab.gene == gmin);
-                }
-            }
+        if (slow) {
+            count = 0;
+            payload = 0;
+            a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
         }
-        if (lane == 0) a.rec[r] = make_uint2(count, payload);
-        warp_assoc += count;
+        a.rec[r] = make_uint2(count, payload);
     }
+    const uint32_t wa = __reduce_add_sync(kFull, count), wp = __reduce_add_sync(kFull, my_probes),
+                   wh = __reduce_add_sync(kFull, my_hits);
     if (lane == 0) {
-        s_assoc[warp] = warp_assoc;
-        s_probes[warp] = warp_probes;
-        s_hits[warp] = warp_hits;
+        s_assoc[warp] = wa;
+        s_probes[warp] = wp;
+        s_hits[warp] = wh;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t ta = 0, tp = 0, th = 0;
-        for (int w = 0; w < kWarpsPerCta; ++w) ta += s_assoc[w], tp += s_probes[w], th += s_hits[w];
+        for (int w = 0; w < kFastThreads / 32; ++w) ta += s_assoc[w], tp += s_probes[w], th += s_hits[w];
         a.tile_sums[blockIdx.x] = ta;
         if (tp) atomicAdd(&a.counters->n_probes, (unsigned long long)tp);
         if (th) atomicAdd(&a.counters->n_hits, (unsigned long long)th);
@@ -529,7 +488,7 @@ scatter_assoc_kernel(const ReadKernelArgs a, uint64_t assoc_cap, const uint32_t 
 template <bool HAS_QUAL, int MOD>
 static void launch_typed(const ReadKernelArgs &a, cudaStream_t st, unsigned tiles, unsigned slow_blocks, cudaEvent_t ev_ka)
 {
-    analyze_reads_kernel<HAS_QUAL, MOD><<<tiles, kWarpsPerCta * 32, 0, st>>>(a);
+    analyze_reads_kernel<HAS_QUAL, MOD><<<tiles, kFastThreads, 0, st>>>(a);
     if (ev_ka) cudaEventRecord(ev_ka, st);
     analyze_slow_kernel<HAS_QUAL, MOD><<<slow_blocks, 128, 0, st>>>(a);
 }
