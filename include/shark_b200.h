@@ -135,6 +135,9 @@ typedef struct shk_index_views {
 int shk_index_views_get(shk_ctx *ctx, shk_index_views *views);
 int shk_index_adopt(shk_ctx *ctx, const shk_index_info *info);
 int shk_index_finalize(shk_ctx *ctx);
+/* Same replication for two contexts of ONE process (the multi-GPU CLI): adopt + peer copies over
+ * NVLink (cudaMemcpyPeerAsync) + finalize. */
+int shk_index_replicate(shk_ctx *src, shk_ctx *dst);
 
 /* ---- probe (test / roofline entry) ---------------------------------------------------- */
 

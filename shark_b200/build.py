@@ -14,7 +14,7 @@ CLI = os.path.join(HERE, "shark-b200")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU_SOURCES = ["shk_capi.cu", "shk_index.cu", "shk_reads.cu"]
-HOST_SOURCES = ["host/fastx.cpp", "host/shark_main.cpp"]
+HOST_SOURCES = ["host/shark_main.cpp"]
 
 
 def _newer(target, deps):
@@ -44,8 +44,8 @@ def build(force=False, verbose=False):
         subprocess.check_call([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"])
     host = [os.path.join(CSRC, s) for s in HOST_SOURCES]
     if all(os.path.exists(h) for h in host) and (force or _newer(CLI, deps + [LIB])):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(HERE, "..", "include"),
-                               *host, "-o", CLI, "-L", HERE, "-lshark_b200", "-Wl,-rpath,$ORIGIN", "-lz"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", *host, "-o", CLI, "-L", HERE,
+                               "-lshark_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link,/usr/local/cuda/lib64", "-lz"])
     return LIB
 
 

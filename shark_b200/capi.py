@@ -17,7 +17,7 @@ STATUS = {0: "SHK_OK", -1: "SHK_E_ARG", -2: "SHK_E_CUDA", -3: "SHK_E_STATE", -4:
 
 EXPORTED = [
     "shk_abi_version", "shk_create", "shk_destroy", "shk_last_error", "shk_index_build", "shk_index_info_get",
-    "shk_index_export", "shk_index_views_get", "shk_index_adopt", "shk_index_finalize", "shk_probe", "shk_probe_bench",
+    "shk_index_export", "shk_index_views_get", "shk_index_adopt", "shk_index_finalize", "shk_index_replicate", "shk_probe", "shk_probe_bench",
     "shk_random_sector_bench", "shk_alloc_pinned", "shk_free_pinned", "shk_reads_submit", "shk_reads_collect",
     "shk_reads_upload", "shk_reads_analyze_resident", "shk_kernel_launches",
 ]
@@ -80,6 +80,7 @@ def load():
     L.shk_index_views_get.argtypes = [vp, C.POINTER(IndexViews)]
     L.shk_index_adopt.argtypes = [vp, C.POINTER(IndexInfo)]
     L.shk_index_finalize.argtypes = [vp]
+    L.shk_index_replicate.argtypes = [vp, vp]
     L.shk_probe.argtypes = [vp, vp, C.c_uint64, vp, vp, vp]
     L.shk_probe_bench.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     L.shk_random_sector_bench.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_float)]

@@ -361,6 +361,32 @@ int shk_index_finalize(shk_ctx *ctx)
     return ensure_slow_table(ctx);
 }
 
+int shk_index_replicate(shk_ctx *src, shk_ctx *dst)
+{
+    if (!src || !dst || src == dst) return fail(dst, SHK_E_ARG, "bad contexts");
+    if (!src->index.built) return fail(dst, SHK_E_STATE, "source context has no index");
+    int rc = shk_index_adopt(dst, &src->index.info);
+    if (rc) return rc;
+    shk_index_views vs, vd;
+    if ((rc = shk_index_views_get(src, &vs)) != 0) return rc;
+    if ((rc = shk_index_views_get(dst, &vd)) != 0) return rc;
+    SHK_CUDA(dst, cudaSetDevice(dst->device));
+    int can = 0;
+    if (src->device != dst->device && cudaDeviceCanAccessPeer(&can, dst->device, src->device) == cudaSuccess && can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else cudaGetLastError();
+    }
+    for (int i = 0; i < SHK_INDEX_N_VIEWS; ++i) {
+        if (!vs.bytes[i]) continue;
+        if (vs.bytes[i] != vd.bytes[i]) return fail(dst, SHK_E_STATE, "index view %d size mismatch", i);
+        SHK_CUDA(dst, cudaMemcpyPeerAsync(vd.dev_ptr[i], dst->device, vs.dev_ptr[i], src->device, vs.bytes[i],
+                                          dst->build_stream));
+    }
+    SHK_CUDA(dst, cudaStreamSynchronize(dst->build_stream));
+    return shk_index_finalize(dst);
+}
+
 int shk_probe(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int64_t *rank, uint32_t *begin, uint32_t *len)
 {
     if (!ctx || (n && (!kmers || !rank || !begin || !len))) return fail(ctx, SHK_E_ARG, "NULL argument");
