@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -169,7 +169,7 @@ def reference_arm_run(wl, sample_reads, workdir, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -221,6 +221,10 @@ def main():
         return 0
 
     # ---------------------------------------------------------------- our arm
+    # libraries (NCCL's version banner, ...) may write to fd 1: keep the real stdout for the ONE
+    # JSON line and send everything else to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from shark_b200.engine import Shark
@@ -374,7 +378,8 @@ def main():
                       "build_ms": info.build_ms, "broadcast_ms": bcast_ms, "device_bytes": info.device_bytes},
             "associations_per_step": sums.tolist()[2] / args.steps / world, "slow_reads_per_step": n_slow / args.steps,
         }
-        print(json.dumps(out))
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
     sh.close()
     if world > 1:
         dist.destroy_process_group()
