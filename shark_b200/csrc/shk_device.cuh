@@ -179,36 +179,43 @@ __device__ __forceinline__ uint32_t entry_lo(uint64_t e) { return (uint32_t)e; }
 // uniformly distributed hash values, which makes "bucket = position >> shift" a perfect
 // bucketing: bucket b describes positions [b << shift, (b+1) << shift) with four 32-bit slots
 //     bit  31     : 0
-//     bits 30..17 : position - (b << shift)                       (shift <= 14)
+//     bits 30..18 : position - (b << shift)                       (shift <= 13)
+//     bit  17     : the position's list has 3 or 4 ids (set on each of its slots)
 //     bit  16     : 0 = (position, gene id in bits 15..0); a position whose list has L <= 4
-//                       ids owns L such slots
+//                       ids owns L such slots (contiguous, ascending gene id)
 //                   1 = the position is set but its list is longer than 4 ids (the fast path
 //                       cannot hold it anyway and hands the read to the exact path)
 // 0xFFFFFFFF = empty slot.  A bucket that needs more than 4 slots keeps 3 and stores in slot 3 a
 // chain pointer (bit 31 set, low 31 bits = index of a 16-byte overflow record with the same
 // layout, appended to the same array).  One 16-byte load therefore answers "definitely not set"
 // / "set, genes g.." for almost every probe, the rest follows a short chain that is L2-resident
-// too - no probe of the fast path touches DRAM-sized structures.  The table is derived from the
-// bit vector + rank + CSR (the reference-shaped index), so results are identical by construction.
+// too - no probe of the fast path touches DRAM-sized structures.  `slot ^ key` is below 2^18 iff
+// the slot describes the probed position, and then equals the gene id when no flag is set: the
+// fast kernel finds the (up to two) ids of a position with a min/max network, no branches.
+// The table is derived from the bit vector + rank + CSR (the reference-shaped index), so results
+// are identical by construction.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kFrontEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kFrontLongFlag = 0x10000u;
+constexpr uint32_t kFrontMultiFlag = 0x20000u;
+constexpr uint32_t kFrontKeyShift = 18;
+constexpr uint32_t kFrontLim = 1u << kFrontKeyShift;  // slot ^ key < kFrontLim <=> same position
 constexpr uint32_t kFrontChainBit = 0x80000000u;
-constexpr uint32_t kFrontMaxShift = 14;
+constexpr uint32_t kFrontMaxShift = 13;
 constexpr uint32_t kFrontInlineMax = 4;  // longest gene list stored inline
 
 struct FrontGeom {
-    uint32_t shift;     // log2(positions per bucket), 5..14
+    uint32_t shift;     // log2(positions per bucket), 5..13
     uint32_t off_mask;  // (1 << shift) - 1
     uint64_t n_buckets;
     uint64_t n_entries;  // buckets + overflow records
 };
 
-__device__ __forceinline__ uint32_t front_key(uint32_t off) { return off << 17; }
+__device__ __forceinline__ uint32_t front_key(uint32_t off) { return off << kFrontKeyShift; }
 // key slot of offset `off` (either kind)?
 __device__ __forceinline__ bool front_slot_matches(uint32_t slot, uint32_t key)
 {
-    return (slot & 0xFFFE0000u) == key;  // bit 31 clear and offset equal (EMPTY and chains have bit 31 set)
+    return (slot ^ key) < kFrontLim;  // bit 31 clear and offset equal (EMPTY and chains have bit 31 set)
 }
 __device__ __forceinline__ bool front_is_chain(uint32_t slot) { return (slot & kFrontChainBit) && slot != kFrontEmpty; }
 

@@ -451,7 +451,7 @@ front_place_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, con
         } else {
             for (uint32_t i = 0; i < ln; ++i) {
                 uint32_t g = i == 0 ? entry_id0(e) : (ln == 2 ? entry_lo(e) : (uint32_t)csr_ids[entry_lo(e) + i]);
-                *front_slot_ptr(front, bkt, total, t0 + i, fg.n_buckets, rb) = key | g;
+                *front_slot_ptr(front, bkt, total, t0 + i, fg.n_buckets, rb) = key | (ln >= 3 ? kFrontMultiFlag : 0u) | g;
             }
         }
     });
@@ -504,8 +504,8 @@ static void free_index_arrays(DeviceIndex &ix)
 
 // Front table geometry: at most ~0.7 keys per 4-slot bucket (C2: 64 MB for 2.8 M keys; measured
 // faster than 1.5 keys/bucket = 32 MB because chains are rarer, profiles/analyze_r1_v3.md), at
-// least 32 positions per bucket (the table is then at most 4x the plain bit vector), at most 2^14
-// (14-bit offsets).  SHK_FRONT_LOAD overrides the 0.7 (tuning).
+// least 32 positions per bucket (the table is then at most 4x the plain bit vector), at most 2^13
+// (13-bit offsets).  SHK_FRONT_LOAD overrides the 0.7 (tuning).
 static void front_geometry(DeviceIndex &ix)
 {
     double load = 0.7;

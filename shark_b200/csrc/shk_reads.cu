@@ -112,220 +112,11 @@ __device__ __forceinline__ bool full_probe(const ReadKernelArgs &a, uint64_t p, 
 // probes are in flight per thread.  Reads that need more than 4 genes, or are longer than
 // kMaxFastLen, go to the exact warp-per-read path.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTSlots = 4;
 constexpr int kFastThreads = 128;
 #ifndef SHK_FAST_MIN_BLOCKS
 #define SHK_FAST_MIN_BLOCKS 5
 #endif
 static_assert(kFastThreads == (int)kReadsPerTile, "one CTA of the fast kernel = one scan tile");
-
-struct GeneTable {
-    uint32_t gene[kTSlots], cov[kTSlots], hits[kTSlots], last[kTSlots];
-    int n;
-    bool overflow;
-
-    __device__ __forceinline__ void init()
-    {
-        n = 0;
-        overflow = false;
-#pragma unroll
-        for (int i = 0; i < kTSlots; ++i) gene[i] = 0xFFFFFFFFu, cov[i] = hits[i] = last[i] = 0;
-    }
-    // ReadAnalyzer.hpp:57-61 / 80-85 for one gene id of the window ending at pos.  A fresh
-    // std::map entry has last == 0 and `pos - 0 >= k` for every window, so its coverage is k.
-    __device__ __forceinline__ void hit(uint32_t g, uint32_t pos, uint32_t k)
-    {
-        bool done = false;
-#pragma unroll
-        for (int i = 0; i < kTSlots; ++i) {
-            if (!done && gene[i] == g) {
-                cov[i] += min(k, pos - last[i]);
-                hits[i] += 1;
-                last[i] = pos;
-                done = true;
-            }
-        }
-        if (!done) {
-            if (n == kTSlots) {
-                overflow = true;
-                return;
-            }
-#pragma unroll
-            for (int i = 0; i < kTSlots; ++i) {
-                if (i == n) {
-                    gene[i] = g;
-                    cov[i] = k;
-                    hits[i] = 1;
-                    last[i] = pos;
-                }
-            }
-            ++n;
-        }
-    }
-};
-
-template <bool HAS_QUAL, int MOD>
-__global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_reads_v3_kernel(const ReadKernelArgs a)
-{
-    __shared__ uint32_t s_assoc[kFastThreads / 32];
-    __shared__ uint32_t s_probes[kFastThreads / 32];
-    __shared__ uint32_t s_hits[kFastThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t r = blockIdx.x * kFastThreads + threadIdx.x;
-    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
-    const uint32_t k = (uint32_t)a.k;
-    const uint64_t kmask2 = (1ULL << (2 * k)) - 1ULL;
-    const int rc_shift = 2 * (int)k - 2;
-    uint32_t count = 0, payload = 0, my_probes = 0, my_hits = 0;
-    bool slow = false;
-
-    if (r < a.n_reads) {
-        const uint32_t off0 = a.off[r];
-        const uint32_t n = a.off[r + 1] - off0;
-        if (n > kMaxFastLen) {
-            slow = true;
-        } else {
-            GeneTable tab;
-            tab.init();
-            uint64_t fwd = 0, rc = 0;
-            uint32_t run = 0, len = 0;
-            const uint32_t head = off0 & 3u;
-            const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.seq) + (off0 >> 2);
-            const uint32_t *qualw = HAS_QUAL ? reinterpret_cast<const uint32_t *>(a.qual) + (off0 >> 2) : nullptr;
-            const uint32_t n_words = (head + n + 3u) >> 2;
-            for (uint32_t j = 0; j < n_words && !tab.overflow; ++j) {
-                const uint32_t w = ld_text_word(seqw + j, pol_first);
-                uint32_t qw = 0;
-                if (HAS_QUAL) qw = ld_text_word(qualw + j, pol_first);
-                uint32_t bucket[4], offk[4];
-                bool wv[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    wv[b] = false;
-                    bucket[b] = offk[b] = 0;
-                    const uint32_t pos = 4u * j + (uint32_t)b - head;  // wraps for bytes before the read
-                    if (pos < n) {
-                        uint32_t ch = (w >> (8 * b)) & 0xFFu;
-                        if (HAS_QUAL) {
-                            const int q = (int)(signed char)((qw >> (8 * b)) & 0xFFu);
-                            if (q < a.mq) ch = (ch - 64u) & 0xFFu;  // FastqSplitter.hpp:106
-                        }
-                        if (base_valid(ch)) {
-                            const uint64_t code = base_code(ch);
-                            fwd = ((fwd << 2) | code) & kmask2;      // lsappend, kmer_utils.hpp:73-75
-                            rc = (rc >> 2) | ((3ULL - code) << rc_shift);  // rsprepend(reverse_char), 77-79
-                            ++run;
-                            ++len;  // ReadAnalyzer.hpp:46-49
-                        } else {
-                            run = 0;
-                        }
-                        if (run >= k) {
-                            const uint64_t p = bit_index<MOD>(xxh64_u64(fwd < rc ? fwd : rc), a.geom);
-                            bucket[b] = (uint32_t)(p >> a.fgeom.shift);
-                            offk[b] = (uint32_t)p & a.fgeom.off_mask;
-                            wv[b] = true;
-                        }
-                    }
-                }
-                uint4 q[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (wv[b]) q[b] = ld_front(a.front + bucket[b], pol_last);
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if (wv[b]) {
-                        ++my_probes;
-                        const uint32_t pos = 4u * j + (uint32_t)b - head;
-                        const uint32_t key = front_key(offk[b]);
-                        uint4 qq = q[b];
-                        bool any = false;
-                        for (;;) {  // the bucket, then (rarely) its chain of overflow records
-                            const bool m0 = front_slot_matches(qq.x, key), m1 = front_slot_matches(qq.y, key),
-                                       m2 = front_slot_matches(qq.z, key), m3 = front_slot_matches(qq.w, key);
-                            if (m0 | m1 | m2 | m3) {
-                                any = true;
-                                const uint32_t first = m0 ? qq.x : (m1 ? qq.y : (m2 ? qq.z : qq.w));
-                                if (first & kFrontLongFlag) {
-                                    tab.overflow = true;  // list longer than 4 ids: exact path
-                                } else {
-                                    tab.hit(first & 0xFFFFu, pos, k);
-                                    if ((int)m0 + (int)m1 + (int)m2 + (int)m3 > 1) {  // list of 2..4 ids
-                                        if (m0 && m1) tab.hit(qq.y & 0xFFFFu, pos, k);
-                                        if ((m0 | m1) && m2) tab.hit(qq.z & 0xFFFFu, pos, k);
-                                        if ((m0 | m1 | m2) && m3) tab.hit(qq.w & 0xFFFFu, pos, k);
-                                    }
-                                }
-                            }
-                            if (!front_is_chain(qq.w)) break;
-                            qq = ld_front(a.front + (qq.w & 0x7FFFFFFFu), pol_last);
-                        }
-                        my_hits += any ? 1u : 0u;
-                    }
-                }
-            }
-            if (tab.overflow) {
-                slow = true;
-            } else {
-                // argmax with ties (ReadAnalyzer.hpp:90-102), threshold and -s (ReadAnalyzer.hpp:104)
-                uint32_t maxc = 0, maxh = 0;
-#pragma unroll
-                for (int i = 0; i < kTSlots; ++i) {
-                    if (i < tab.n && (tab.cov[i] > maxc || (tab.cov[i] == maxc && tab.hits[i] > maxh))) {
-                        maxc = tab.cov[i];
-                        maxh = tab.hits[i];
-                    }
-                }
-                uint32_t wg[kTSlots];
-#pragma unroll
-                for (int i = 0; i < kTSlots; ++i) {
-                    const bool is = i < tab.n && tab.cov[i] == maxc && tab.hits[i] == maxh;
-                    wg[i] = is ? tab.gene[i] : 0xFFFFFFFFu;
-                    count += is ? 1u : 0u;
-                }
-                const bool pass = count > 0 && (double)maxc >= __dmul_rn(a.c, (double)len) && (!a.single || count == 1);
-                if (!pass) count = 0;
-                if (count == 1) {
-                    payload = min(min(wg[0], wg[1]), min(wg[2], wg[3]));
-                } else if (count >= 2) {
-                    // ascending gene order = std::map order: sort the (at most 4) winners
-#define SHK_CSWAP(x, y) { const uint32_t lo_ = min(wg[x], wg[y]), hi_ = max(wg[x], wg[y]); wg[x] = lo_; wg[y] = hi_; }
-                    SHK_CSWAP(0, 1) SHK_CSWAP(2, 3) SHK_CSWAP(0, 2) SHK_CSWAP(1, 3) SHK_CSWAP(1, 2)
-#undef SHK_CSWAP
-                    payload = atomicAdd(&a.counters->pool_used, count);
-                    if ((uint64_t)payload + count > a.pool_cap) {
-                        a.counters->pool_overflow = 1;
-                        payload = 0xFFFFFFFFu;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < kTSlots; ++i)
-                            if ((uint32_t)i < count) a.pool[payload + i] = wg[i];
-                    }
-                }
-            }
-        }
-        if (slow) {
-            count = 0;
-            payload = 0;
-            a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
-        }
-        a.rec[r] = make_uint2(count, payload);
-    }
-    const uint32_t wa = __reduce_add_sync(kFull, count), wp = __reduce_add_sync(kFull, my_probes),
-                   wh = __reduce_add_sync(kFull, my_hits);
-    if (lane == 0) {
-        s_assoc[warp] = wa;
-        s_probes[warp] = wp;
-        s_hits[warp] = wh;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t ta = 0, tp = 0, th = 0;
-        for (int w = 0; w < kFastThreads / 32; ++w) ta += s_assoc[w], tp += s_probes[w], th += s_hits[w];
-        a.tile_sums[blockIdx.x] = ta;
-        if (tp) atomicAdd(&a.counters->n_probes, (unsigned long long)tp);
-        if (th) atomicAdd(&a.counters->n_hits, (unsigned long long)th);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Fast path, version 4: still one thread per read, restructured around instruction issue (the v3
@@ -419,6 +210,184 @@ struct Mru4 {
 };
 
 template <bool HAS_QUAL, int MOD>
+__global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_reads_v4_kernel(const ReadKernelArgs a)
+{
+    __shared__ uint32_t s_assoc[kFastThreads / 32];
+    __shared__ uint32_t s_probes[kFastThreads / 32];
+    __shared__ uint32_t s_hits[kFastThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * kFastThreads + threadIdx.x;
+    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
+    const uint32_t k = (uint32_t)a.k;
+    const uint64_t kmask2 = (1ULL << (2 * k)) - 1ULL;
+    const int rc_shift = 2 * (int)k - 2;
+    const uint32_t fshift = a.fgeom.shift, fmask = a.fgeom.off_mask;
+    const uint32_t mq4b = (0x01010101u * (uint32_t)(a.mq & 0xFF)) ^ kH4;
+    uint32_t count = 0, payload = 0, my_probes = 0, my_hits = 0;
+    bool slow = false;
+
+    if (r < a.n_reads) {
+        const uint32_t off0 = a.off[r];
+        const uint32_t n = a.off[r + 1] - off0;
+        if (n > kMaxFastLen) {
+            slow = true;
+        } else {
+            Mru4 tab;
+            tab.init();
+            uint64_t fwd = 0, rc = 0;
+            uint32_t run = 0, len = 0;
+            const uint32_t head = off0 & 3u;
+            const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.seq) + (off0 >> 2);
+            const uint32_t *qualw = HAS_QUAL ? reinterpret_cast<const uint32_t *>(a.qual) + (off0 >> 2) : nullptr;
+            const uint32_t n_words = (head + n + 3u) >> 2;
+            uint32_t w_next = 0, q_next = 0;
+            if (n_words) {
+                w_next = ld_text_word(seqw, pol_first);
+                if (HAS_QUAL) q_next = ld_text_word(qualw, pol_first);
+            }
+            for (uint32_t j = 0; j < n_words && !tab.overflow; ++j) {
+                uint32_t w = w_next;
+                const uint32_t qw = q_next;
+                if (j + 1 < n_words) {
+                    w_next = ld_text_word(seqw + j + 1, pol_first);
+                    if (HAS_QUAL) q_next = ld_text_word(qualw + j + 1, pol_first);
+                }
+                if (HAS_QUAL) w = sub_bytes4(w, qual_mask4(qw, mq4b));
+                uint32_t code4, x;
+                codes4(w, code4, x);
+                const uint32_t pos0 = 4u * j - head;  // position of byte 0 (wraps before the read)
+                if (j == 0 || j + 1 == n_words) {     // bytes outside the read are not bases
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (pos0 + (uint32_t)b >= n) x |= 0xFFu << (8 * b);
+                }
+                uint32_t bucket[4], key[4];
+                bool wv[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const bool valid = ((x >> (8 * b)) & 0xFFu) == 0u;
+                    const uint64_t code = (code4 >> (8 * b)) & 3u;
+                    fwd = ((fwd << 2) | code) & kmask2;            // lsappend, kmer_utils.hpp:73-75
+                    rc = (rc >> 2) | ((3ULL ^ code) << rc_shift);  // rsprepend(reverse_char), 77-79
+                    run = valid ? run + 1u : 0u;                   // build_kmer restart, 57-71
+                    len += valid ? 1u : 0u;                        // ReadAnalyzer.hpp:46-49
+                    wv[b] = run >= k;
+                    const uint64_t p = bit_index<MOD>(xxh64_u64(fwd < rc ? fwd : rc), a.geom);
+                    bucket[b] = (uint32_t)(p >> fshift);
+                    key[b] = front_key((uint32_t)p & fmask);
+                }
+                uint4 q[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    q[b] = make_uint4(kFrontEmpty, kFrontEmpty, kFrontEmpty, kFrontEmpty);
+                    if (wv[b]) q[b] = ld_front(a.front + bucket[b], pol_last);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    my_probes += wv[b] ? 1u : 0u;
+                    const uint32_t pos = pos0 + (uint32_t)b;
+                    uint4 qq = q[b];
+                    for (;;) {  // the bucket, then (rarely) its chain of overflow records
+                        const bool m0 = (qq.x ^ key[b]) < kFrontLim, m1 = (qq.y ^ key[b]) < kFrontLim,
+                                   m2 = (qq.z ^ key[b]) < kFrontLim, m3 = (qq.w ^ key[b]) < kFrontLim;
+                        if (m0 | m1 | m2 | m3) {
+                            my_hits += 1u;
+                            const uint32_t first = m0 ? qq.x : (m1 ? qq.y : (m2 ? qq.z : qq.w));
+                            if (first & kFrontLongFlag) {
+                                tab.overflow = true;  // list longer than 4 ids: exact path
+                            } else {
+                                tab.hit(first & 0xFFFFu, pos, k);
+                                if ((int)m0 + (int)m1 + (int)m2 + (int)m3 > 1) {  // list of 2..4 ids
+                                    if (m0 && m1) tab.hit(qq.y & 0xFFFFu, pos, k);
+                                    if ((m0 | m1) && m2) tab.hit(qq.z & 0xFFFFu, pos, k);
+                                    if ((m0 | m1 | m2) && m3) tab.hit(qq.w & 0xFFFFu, pos, k);
+                                }
+                            }
+                        }
+                        if (!front_is_chain(qq.w)) break;
+                        qq = ld_front(a.front + (qq.w & 0x7FFFFFFFu), pol_last);
+                    }
+                }
+            }
+            if (tab.overflow) {
+                slow = true;
+            } else {
+                // argmax with ties (ReadAnalyzer.hpp:90-102), threshold and -s (ReadAnalyzer.hpp:104)
+                const uint32_t tg[4] = {tab.g0, tab.g1, tab.g2, tab.g3}, tc[4] = {tab.c0, tab.c1, tab.c2, tab.c3},
+                               th[4] = {tab.h0, tab.h1, tab.h2, tab.h3};
+                uint32_t maxc = 0, maxh = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if ((uint32_t)i < tab.n && (tc[i] > maxc || (tc[i] == maxc && th[i] > maxh))) {
+                        maxc = tc[i];
+                        maxh = th[i];
+                    }
+                }
+                uint32_t wg[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool is = (uint32_t)i < tab.n && tc[i] == maxc && th[i] == maxh;
+                    wg[i] = is ? tg[i] : 0xFFFFFFFFu;
+                    count += is ? 1u : 0u;
+                }
+                const bool pass = count > 0 && (double)maxc >= __dmul_rn(a.c, (double)len) && (!a.single || count == 1);
+                if (!pass) count = 0;
+                if (count == 1) {
+                    payload = min(min(wg[0], wg[1]), min(wg[2], wg[3]));
+                } else if (count >= 2) {
+                    // ascending gene order = std::map order: sort the (at most 4) winners
+#define SHK_CSWAP(x, y) { const uint32_t lo_ = min(wg[x], wg[y]), hi_ = max(wg[x], wg[y]); wg[x] = lo_; wg[y] = hi_; }
+                    SHK_CSWAP(0, 1) SHK_CSWAP(2, 3) SHK_CSWAP(0, 2) SHK_CSWAP(1, 3) SHK_CSWAP(1, 2)
+#undef SHK_CSWAP
+                    payload = atomicAdd(&a.counters->pool_used, count);
+                    if ((uint64_t)payload + count > a.pool_cap) {
+                        a.counters->pool_overflow = 1;
+                        payload = 0xFFFFFFFFu;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if ((uint32_t)i < count) a.pool[payload + i] = wg[i];
+                    }
+                }
+            }
+        }
+        if (slow) {
+            count = 0;
+            payload = 0;
+            a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
+        }
+        a.rec[r] = make_uint2(count, payload);
+    }
+    const uint32_t wa = __reduce_add_sync(kFull, count), wp = __reduce_add_sync(kFull, my_probes),
+                   wh = __reduce_add_sync(kFull, my_hits);
+    if (lane == 0) {
+        s_assoc[warp] = wa;
+        s_probes[warp] = wp;
+        s_hits[warp] = wh;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t ta = 0, tp = 0, th = 0;
+        for (int w = 0; w < kFastThreads / 32; ++w) ta += s_assoc[w], tp += s_probes[w], th += s_hits[w];
+        a.tile_sums[blockIdx.x] = ta;
+        if (tp) atomicAdd(&a.counters->n_probes, (unsigned long long)tp);
+        if (th) atomicAdd(&a.counters->n_hits, (unsigned long long)th);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path, version 5 = version 4 with a branch-free common case for the table update.  The v4
+// profile (profiles/analyze_r1_v4.md) showed 212 instructions per base, of which ~90 are the
+// hashing half, and 22 of 32 lanes active: most warps contain a read from a region shared by two
+// genes, so the "more than one id" branch ran for nearly every position with one or two lanes.
+// Here a min/max network over `slot ^ key` yields the position's smallest two ids A <= B (a
+// non-matching slot gives a value >= kFrontLim, a flagged slot a value >= 2^16, so `A == g0`
+// alone proves "matching slot, plain id, gene g0"); positions whose ids are all in table slots
+// 0/1 - the two most recent genes - are applied with predicated arithmetic.  Everything else (a
+// gene entering the table, lists of 3-4 ids, long lists, chained buckets) takes the generic
+// path, which for a typical read runs once or twice.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_QUAL, int MOD>
 __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_reads_kernel(const ReadKernelArgs a)
 {
     __shared__ uint32_t s_assoc[kFastThreads / 32];
@@ -483,7 +452,7 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                     wv[b] = run >= k;
                     const uint64_t p = bit_index<MOD>(xxh64_u64(fwd < rc ? fwd : rc), a.geom);
                     bucket[b] = (uint32_t)(p >> fshift);
-                    key[b] = ((uint32_t)p & fmask) << 17;
+                    key[b] = front_key((uint32_t)p & fmask);
                 }
                 uint4 q[4];
 #pragma unroll
@@ -495,26 +464,47 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                 for (int b = 0; b < 4; ++b) {
                     my_probes += wv[b] ? 1u : 0u;
                     const uint32_t pos = pos0 + (uint32_t)b;
-                    uint4 qq = q[b];
-                    for (;;) {  // the bucket, then (rarely) its chain of overflow records
-                        const bool m0 = (qq.x ^ key[b]) < 0x20000u, m1 = (qq.y ^ key[b]) < 0x20000u,
-                                   m2 = (qq.z ^ key[b]) < 0x20000u, m3 = (qq.w ^ key[b]) < 0x20000u;
-                        if (m0 | m1 | m2 | m3) {
-                            my_hits += 1u;
-                            const uint32_t first = m0 ? qq.x : (m1 ? qq.y : (m2 ? qq.z : qq.w));
-                            if (first & kFrontLongFlag) {
-                                tab.overflow = true;  // list longer than 4 ids: exact path
-                            } else {
-                                tab.hit(first & 0xFFFFu, pos, k);
-                                if ((int)m0 + (int)m1 + (int)m2 + (int)m3 > 1) {  // list of 2..4 ids
-                                    if (m0 && m1) tab.hit(qq.y & 0xFFFFu, pos, k);
-                                    if ((m0 | m1) && m2) tab.hit(qq.z & 0xFFFFu, pos, k);
-                                    if ((m0 | m1 | m2) && m3) tab.hit(qq.w & 0xFFFFu, pos, k);
+                    const uint32_t kb = key[b];
+                    const uint32_t d0 = q[b].x ^ kb, d1 = q[b].y ^ kb, d2 = q[b].z ^ kb, d3 = q[b].w ^ kb;
+                    const uint32_t lo01 = min(d0, d1), hi01 = max(d0, d1), lo23 = min(d2, d3), hi23 = max(d2, d3);
+                    const uint32_t A = min(lo01, lo23);                          // smallest
+                    const uint32_t B = min(max(lo01, lo23), min(hi01, hi23));    // second smallest
+                    const bool anyA = A < kFrontLim, anyB = B < kFrontLim;
+                    const bool a0 = A == tab.g0, a1 = A == tab.g1, b0 = B == tab.g0, b1 = B == tab.g1;
+                    const bool chained = (int32_t)q[b].w < -1;  // chain pointer: bit 31 set, not EMPTY
+                    my_hits += anyA ? 1u : 0u;
+                    if ((!anyA | a0 | a1) & (!anyB | b0 | b1) & !chained) {
+                        if (a0 | b0) {
+                            tab.c0 += min(k, pos - tab.l0);
+                            tab.h0 += 1;
+                            tab.l0 = pos;
+                        }
+                        if (a1 | b1) {
+                            tab.c1 += min(k, pos - tab.l1);
+                            tab.h1 += 1;
+                            tab.l1 = pos;
+                        }
+                    } else {
+                        // generic: every slot of the bucket and of its chain, in list order
+                        uint4 qq = q[b];
+                        bool counted = anyA;
+                        for (;;) {
+#pragma unroll 1
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t sl = i == 0 ? qq.x : (i == 1 ? qq.y : (i == 2 ? qq.z : qq.w));
+                                const uint32_t d = sl ^ kb;
+                                if (d < kFrontLim) {
+                                    if (!counted) {
+                                        my_hits += 1u;
+                                        counted = true;
+                                    }
+                                    if (d & kFrontLongFlag) tab.overflow = true;  // list longer than 4 ids: exact path
+                                    else tab.hit(d & 0xFFFFu, pos, k);
                                 }
                             }
+                            if (!front_is_chain(qq.w)) break;
+                            qq = ld_front(a.front + (qq.w & 0x7FFFFFFFu), pol_last);
                         }
-                        if (!front_is_chain(qq.w)) break;
-                        qq = ld_front(a.front + (qq.w & 0x7FFFFFFFu), pol_last);
                     }
                 }
             }
@@ -747,8 +737,8 @@ scatter_assoc_kernel(const ReadKernelArgs a, uint64_t assoc_cap, const uint32_t 
 template <bool HAS_QUAL, int MOD>
 static void launch_typed(const ReadKernelArgs &a, cudaStream_t st, unsigned tiles, unsigned slow_blocks, cudaEvent_t ev_ka)
 {
-    static const int variant = getenv("SHK_FAST_VARIANT") ? atoi(getenv("SHK_FAST_VARIANT")) : 4;
-    if (variant == 3) analyze_reads_v3_kernel<HAS_QUAL, MOD><<<tiles, kFastThreads, 0, st>>>(a);
+    static const int variant = getenv("SHK_FAST_VARIANT") ? atoi(getenv("SHK_FAST_VARIANT")) : 5;
+    if (variant == 4) analyze_reads_v4_kernel<HAS_QUAL, MOD><<<tiles, kFastThreads, 0, st>>>(a);
     else analyze_reads_kernel<HAS_QUAL, MOD><<<tiles, kFastThreads, 0, st>>>(a);
     if (ev_ka) cudaEventRecord(ev_ka, st);
     analyze_slow_kernel<HAS_QUAL, MOD><<<slow_blocks, 128, 0, st>>>(a);
