@@ -405,23 +405,33 @@ __device__ __forceinline__ uint32_t front_slots_of(uint64_t e)
     return ln <= kFrontInlineMax ? ln : 1u;
 }
 
+// Per-bucket counter: low 16 bits = slots (at most 2^13 positions x 4), high 16 bits = number of
+// 2-id lists.  In a chained bucket a 2-id list never straddles two records (the fast kernel
+// relies on it: a plain id found in a record has its partner in the same record), which can
+// waste one slot per such list - the record budget counts it.
+__device__ __forceinline__ uint32_t front_cnt_slots(uint32_t c) { return c & 0xFFFFu; }
+__device__ __forceinline__ uint32_t front_cnt_records(uint32_t c)
+{
+    const uint32_t slots = c & 0xFFFFu;
+    return slots <= 4 ? 0u : (slots + (c >> 16) - 3u + 2u) / 3u;
+}
+
 __global__ void __launch_bounds__(256)
 front_count_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, const uint64_t *__restrict__ entries,
                    FrontGeom fg, uint32_t *cnt)
 {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_sectors) return;
-    for_each_set_bit(sectors, s, [&](uint64_t p, uint32_t r) { atomicAdd(&cnt[p >> fg.shift], front_slots_of(entries[r])); });
+    for_each_set_bit(sectors, s, [&](uint64_t p, uint32_t r) {
+        const uint32_t L = front_slots_of(entries[r]);
+        atomicAdd(&cnt[p >> fg.shift], L + (L == 2 ? 0x10000u : 0u));
+    });
 }
 
-// overflow records needed by a bucket with c slots: 3 stay in the bucket, the rest in records of 3
+// overflow records needed by a bucket: 3 slots stay in the bucket, the rest in records of 3
 struct FrontRecordsIn {
     const uint32_t *cnt;
-    __device__ __forceinline__ uint32_t operator()(uint64_t i) const
-    {
-        uint32_t c = cnt[i];
-        return c <= 4 ? 0u : (c - 3u + 2u) / 3u;
-    }
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return front_cnt_records(cnt[i]); }
 };
 
 __device__ __forceinline__ uint32_t *front_slot_ptr(uint32_t *front, uint64_t bucket, uint32_t total, uint32_t t,
@@ -444,8 +454,19 @@ front_place_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, con
         const uint64_t bkt = p >> fg.shift;
         const uint32_t key = front_key((uint32_t)p & fg.off_mask);
         const uint32_t ln = entry_len(e), L = front_slots_of(e);
-        const uint32_t total = cnt[bkt], rb = rec_base[bkt];
-        const uint32_t t0 = atomicAdd(&cur[bkt], L);
+        const uint32_t total = front_cnt_slots(cnt[bkt]), rb = rec_base[bkt];
+        uint32_t t0;
+        if (total <= 4 || L != 2) {
+            t0 = atomicAdd(&cur[bkt], L);
+        } else {  // chained bucket, 2-id list: both slots in one record (logical slots 3i..3i+2)
+            uint32_t seen = cur[bkt];
+            for (;;) {
+                t0 = seen + (seen % 3u == 2u ? 1u : 0u);
+                const uint32_t prev = atomicCAS(&cur[bkt], seen, t0 + 2u);
+                if (prev == seen) break;
+                seen = prev;
+            }
+        }
         if (ln > kFrontInlineMax) {
             *front_slot_ptr(front, bkt, total, t0, fg.n_buckets, rb) = key | kFrontLongFlag;
         } else {
@@ -462,9 +483,8 @@ front_chain_kernel(FrontGeom fg, const uint32_t *__restrict__ cnt, const uint32_
 {
     uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= fg.n_buckets) return;
-    const uint32_t c = cnt[b];
-    if (c <= 4) return;
-    const uint32_t nrec = (c - 3u + 2u) / 3u, rb = rec_base[b];
+    const uint32_t nrec = front_cnt_records(cnt[b]), rb = rec_base[b];
+    if (nrec == 0) return;
     front[b * 4 + 3] = kFrontChainBit | (uint32_t)(fg.n_buckets + rb);
     for (uint32_t i = 0; i + 1 < nrec; ++i)
         front[(fg.n_buckets + rb + i) * 4 + 3] = kFrontChainBit | (uint32_t)(fg.n_buckets + rb + i + 1);

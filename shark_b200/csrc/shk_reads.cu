@@ -465,15 +465,22 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                     my_probes += wv[b] ? 1u : 0u;
                     const uint32_t pos = pos0 + (uint32_t)b;
                     const uint32_t kb = key[b];
-                    const uint32_t d0 = q[b].x ^ kb, d1 = q[b].y ^ kb, d2 = q[b].z ^ kb, d3 = q[b].w ^ kb;
-                    const uint32_t lo01 = min(d0, d1), hi01 = max(d0, d1), lo23 = min(d2, d3), hi23 = max(d2, d3);
-                    const uint32_t A = min(lo01, lo23);                          // smallest
-                    const uint32_t B = min(max(lo01, lo23), min(hi01, hi23));    // second smallest
+                    uint4 qq = q[b];
+                    uint32_t A, B;
+                    for (;;) {
+                        const uint32_t d0 = qq.x ^ kb, d1 = qq.y ^ kb, d2 = qq.z ^ kb, d3 = qq.w ^ kb;
+                        const uint32_t lo01 = min(d0, d1), hi01 = max(d0, d1), lo23 = min(d2, d3), hi23 = max(d2, d3);
+                        A = min(lo01, lo23);                        // smallest
+                        B = min(max(lo01, lo23), min(hi01, hi23));  // second smallest
+                        // not in this record and the bucket goes on (chain pointer: bit 31 set, not
+                        // EMPTY): look at the next record.  A 2-id list never straddles records.
+                        if (A < kFrontLim || (int32_t)qq.w >= -1) break;
+                        qq = ld_front(a.front + (qq.w & 0x7FFFFFFFu), pol_last);
+                    }
                     const bool anyA = A < kFrontLim, anyB = B < kFrontLim;
                     const bool a0 = A == tab.g0, a1 = A == tab.g1, b0 = B == tab.g0, b1 = B == tab.g1;
-                    const bool chained = (int32_t)q[b].w < -1;  // chain pointer: bit 31 set, not EMPTY
                     my_hits += anyA ? 1u : 0u;
-                    if ((!anyA | a0 | a1) & (!anyB | b0 | b1) & !chained) {
+                    if ((!anyA | a0 | a1) & (!anyB | b0 | b1)) {
                         if (a0 | b0) {
                             tab.c0 += min(k, pos - tab.l0);
                             tab.h0 += 1;
@@ -486,18 +493,13 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                         }
                     } else {
                         // generic: every slot of the bucket and of its chain, in list order
-                        uint4 qq = q[b];
-                        bool counted = anyA;
+                        qq = q[b];
                         for (;;) {
 #pragma unroll 1
                             for (int i = 0; i < 4; ++i) {
                                 const uint32_t sl = i == 0 ? qq.x : (i == 1 ? qq.y : (i == 2 ? qq.z : qq.w));
                                 const uint32_t d = sl ^ kb;
                                 if (d < kFrontLim) {
-                                    if (!counted) {
-                                        my_hits += 1u;
-                                        counted = true;
-                                    }
                                     if (d & kFrontLongFlag) tab.overflow = true;  // list longer than 4 ids: exact path
                                     else tab.hit(d & 0xFFFFu, pos, k);
                                 }
