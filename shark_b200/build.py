@@ -31,6 +31,19 @@ def _deps():
     return out
 
 
+def build_variant(name, flags):
+    """Tuning only: libshark_b200_<name>.so built with extra nvcc flags (picked up via SHK_LIB)."""
+    out = os.path.join(HERE, "libshark_b200_%s.so" % name)
+    objs = []
+    for src in CU_SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".%s.o" % name))
+        subprocess.check_call([NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *flags, "-c",
+                               os.path.join(CSRC, src), "-o", obj])
+        objs.append(obj)
+    subprocess.check_call([NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart"])
+    return out
+
+
 def build(force=False, verbose=False):
     deps = _deps()
     if force or _newer(LIB, deps):
@@ -50,5 +63,9 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:  # build.py --variant NAME -DFOO=1 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

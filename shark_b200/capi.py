@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libshark_b200.so")
+# SHK_LIB: tuning builds (shark_b200/build.py --variant); the product is libshark_b200.so
+LIB_PATH = os.environ.get("SHK_LIB") or os.path.join(_HERE, "libshark_b200.so")
 
 SHK_OK = 0
 STATUS = {0: "SHK_OK", -1: "SHK_E_ARG", -2: "SHK_E_CUDA", -3: "SHK_E_STATE", -4: "SHK_E_CAPACITY", -5: "SHK_E_LIMIT",

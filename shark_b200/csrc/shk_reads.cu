@@ -116,6 +116,9 @@ constexpr int kFastThreads = 128;
 #ifndef SHK_FAST_MIN_BLOCKS
 #define SHK_FAST_MIN_BLOCKS 5
 #endif
+#ifndef SHK_SKIP_WORDS
+#define SHK_SKIP_WORDS 1
+#endif
 static_assert(kFastThreads == (int)kReadsPerTile, "one CTA of the fast kernel = one scan tile");
 
 // ---------------------------------------------------------------------------------------------
@@ -209,172 +212,6 @@ struct Mru4 {
     }
 };
 
-template <bool HAS_QUAL, int MOD>
-__global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_reads_v4_kernel(const ReadKernelArgs a)
-{
-    __shared__ uint32_t s_assoc[kFastThreads / 32];
-    __shared__ uint32_t s_probes[kFastThreads / 32];
-    __shared__ uint32_t s_hits[kFastThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t r = blockIdx.x * kFastThreads + threadIdx.x;
-    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
-    const uint32_t k = (uint32_t)a.k;
-    const uint64_t kmask2 = (1ULL << (2 * k)) - 1ULL;
-    const int rc_shift = 2 * (int)k - 2;
-    const uint32_t fshift = a.fgeom.shift, fmask = a.fgeom.off_mask;
-    const uint32_t mq4b = (0x01010101u * (uint32_t)(a.mq & 0xFF)) ^ kH4;
-    uint32_t count = 0, payload = 0, my_probes = 0, my_hits = 0;
-    bool slow = false;
-
-    if (r < a.n_reads) {
-        const uint32_t off0 = a.off[r];
-        const uint32_t n = a.off[r + 1] - off0;
-        if (n > kMaxFastLen) {
-            slow = true;
-        } else {
-            Mru4 tab;
-            tab.init();
-            uint64_t fwd = 0, rc = 0;
-            uint32_t run = 0, len = 0;
-            const uint32_t head = off0 & 3u;
-            const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.seq) + (off0 >> 2);
-            const uint32_t *qualw = HAS_QUAL ? reinterpret_cast<const uint32_t *>(a.qual) + (off0 >> 2) : nullptr;
-            const uint32_t n_words = (head + n + 3u) >> 2;
-            uint32_t w_next = 0, q_next = 0;
-            if (n_words) {
-                w_next = ld_text_word(seqw, pol_first);
-                if (HAS_QUAL) q_next = ld_text_word(qualw, pol_first);
-            }
-            for (uint32_t j = 0; j < n_words && !tab.overflow; ++j) {
-                uint32_t w = w_next;
-                const uint32_t qw = q_next;
-                if (j + 1 < n_words) {
-                    w_next = ld_text_word(seqw + j + 1, pol_first);
-                    if (HAS_QUAL) q_next = ld_text_word(qualw + j + 1, pol_first);
-                }
-                if (HAS_QUAL) w = sub_bytes4(w, qual_mask4(qw, mq4b));
-                uint32_t code4, x;
-                codes4(w, code4, x);
-                const uint32_t pos0 = 4u * j - head;  // position of byte 0 (wraps before the read)
-                if (j == 0 || j + 1 == n_words) {     // bytes outside the read are not bases
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (pos0 + (uint32_t)b >= n) x |= 0xFFu << (8 * b);
-                }
-                uint32_t bucket[4], key[4];
-                bool wv[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const bool valid = ((x >> (8 * b)) & 0xFFu) == 0u;
-                    const uint64_t code = (code4 >> (8 * b)) & 3u;
-                    fwd = ((fwd << 2) | code) & kmask2;            // lsappend, kmer_utils.hpp:73-75
-                    rc = (rc >> 2) | ((3ULL ^ code) << rc_shift);  // rsprepend(reverse_char), 77-79
-                    run = valid ? run + 1u : 0u;                   // build_kmer restart, 57-71
-                    len += valid ? 1u : 0u;                        // ReadAnalyzer.hpp:46-49
-                    wv[b] = run >= k;
-                    const uint64_t p = bit_index<MOD>(xxh64_u64(fwd < rc ? fwd : rc), a.geom);
-                    bucket[b] = (uint32_t)(p >> fshift);
-                    key[b] = front_key((uint32_t)p & fmask);
-                }
-                uint4 q[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    q[b] = make_uint4(kFrontEmpty, kFrontEmpty, kFrontEmpty, kFrontEmpty);
-                    if (wv[b]) q[b] = ld_front(a.front + bucket[b], pol_last);
-                }
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    my_probes += wv[b] ? 1u : 0u;
-                    const uint32_t pos = pos0 + (uint32_t)b;
-                    uint4 qq = q[b];
-                    for (;;) {  // the bucket, then (rarely) its chain of overflow records
-                        const bool m0 = (qq.x ^ key[b]) < kFrontLim, m1 = (qq.y ^ key[b]) < kFrontLim,
-                                   m2 = (qq.z ^ key[b]) < kFrontLim, m3 = (qq.w ^ key[b]) < kFrontLim;
-                        if (m0 | m1 | m2 | m3) {
-                            my_hits += 1u;
-                            const uint32_t first = m0 ? qq.x : (m1 ? qq.y : (m2 ? qq.z : qq.w));
-                            if (first & kFrontLongFlag) {
-                                tab.overflow = true;  // list longer than 4 ids: exact path
-                            } else {
-                                tab.hit(first & 0xFFFFu, pos, k);
-                                if ((int)m0 + (int)m1 + (int)m2 + (int)m3 > 1) {  // list of 2..4 ids
-                                    if (m0 && m1) tab.hit(qq.y & 0xFFFFu, pos, k);
-                                    if ((m0 | m1) && m2) tab.hit(qq.z & 0xFFFFu, pos, k);
-                                    if ((m0 | m1 | m2) && m3) tab.hit(qq.w & 0xFFFFu, pos, k);
-                                }
-                            }
-                        }
-                        if (!front_is_chain(qq.w)) break;
-                        qq = ld_front(a.front + (qq.w & 0x7FFFFFFFu), pol_last);
-                    }
-                }
-            }
-            if (tab.overflow) {
-                slow = true;
-            } else {
-                // argmax with ties (ReadAnalyzer.hpp:90-102), threshold and -s (ReadAnalyzer.hpp:104)
-                const uint32_t tg[4] = {tab.g0, tab.g1, tab.g2, tab.g3}, tc[4] = {tab.c0, tab.c1, tab.c2, tab.c3},
-                               th[4] = {tab.h0, tab.h1, tab.h2, tab.h3};
-                uint32_t maxc = 0, maxh = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if ((uint32_t)i < tab.n && (tc[i] > maxc || (tc[i] == maxc && th[i] > maxh))) {
-                        maxc = tc[i];
-                        maxh = th[i];
-                    }
-                }
-                uint32_t wg[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const bool is = (uint32_t)i < tab.n && tc[i] == maxc && th[i] == maxh;
-                    wg[i] = is ? tg[i] : 0xFFFFFFFFu;
-                    count += is ? 1u : 0u;
-                }
-                const bool pass = count > 0 && (double)maxc >= __dmul_rn(a.c, (double)len) && (!a.single || count == 1);
-                if (!pass) count = 0;
-                if (count == 1) {
-                    payload = min(min(wg[0], wg[1]), min(wg[2], wg[3]));
-                } else if (count >= 2) {
-                    // ascending gene order = std::map order: sort the (at most 4) winners
-#define SHK_CSWAP(x, y) { const uint32_t lo_ = min(wg[x], wg[y]), hi_ = max(wg[x], wg[y]); wg[x] = lo_; wg[y] = hi_; }
-                    SHK_CSWAP(0, 1) SHK_CSWAP(2, 3) SHK_CSWAP(0, 2) SHK_CSWAP(1, 3) SHK_CSWAP(1, 2)
-#undef SHK_CSWAP
-                    payload = atomicAdd(&a.counters->pool_used, count);
-                    if ((uint64_t)payload + count > a.pool_cap) {
-                        a.counters->pool_overflow = 1;
-                        payload = 0xFFFFFFFFu;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if ((uint32_t)i < count) a.pool[payload + i] = wg[i];
-                    }
-                }
-            }
-        }
-        if (slow) {
-            count = 0;
-            payload = 0;
-            a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
-        }
-        a.rec[r] = make_uint2(count, payload);
-    }
-    const uint32_t wa = __reduce_add_sync(kFull, count), wp = __reduce_add_sync(kFull, my_probes),
-                   wh = __reduce_add_sync(kFull, my_hits);
-    if (lane == 0) {
-        s_assoc[warp] = wa;
-        s_probes[warp] = wp;
-        s_hits[warp] = wh;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t ta = 0, tp = 0, th = 0;
-        for (int w = 0; w < kFastThreads / 32; ++w) ta += s_assoc[w], tp += s_probes[w], th += s_hits[w];
-        a.tile_sums[blockIdx.x] = ta;
-        if (tp) atomicAdd(&a.counters->n_probes, (unsigned long long)tp);
-        if (th) atomicAdd(&a.counters->n_hits, (unsigned long long)th);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Fast path, version 5 = version 4 with a branch-free common case for the table update.  The v4
 // profile (profiles/analyze_r1_v4.md) showed 212 instructions per base, of which ~90 are the
@@ -439,6 +276,20 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                     for (int b = 0; b < 4; ++b)
                         if (pos0 + (uint32_t)b >= n) x |= 0xFFu << (8 * b);
                 }
+#if SHK_SKIP_WORDS
+                if (run + 4u < k) {  // no window can complete in this word (start of a mate): roll only
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const bool valid = ((x >> (8 * b)) & 0xFFu) == 0u;
+                        const uint64_t code = (code4 >> (8 * b)) & 3u;
+                        fwd = ((fwd << 2) | code) & kmask2;
+                        rc = (rc >> 2) | ((3ULL ^ code) << rc_shift);
+                        run = valid ? run + 1u : 0u;
+                        len += valid ? 1u : 0u;
+                    }
+                    continue;
+                }
+#endif
                 uint32_t bucket[4], key[4];
                 bool wv[4];
 #pragma unroll
@@ -739,9 +590,7 @@ scatter_assoc_kernel(const ReadKernelArgs a, uint64_t assoc_cap, const uint32_t 
 template <bool HAS_QUAL, int MOD>
 static void launch_typed(const ReadKernelArgs &a, cudaStream_t st, unsigned tiles, unsigned slow_blocks, cudaEvent_t ev_ka)
 {
-    static const int variant = getenv("SHK_FAST_VARIANT") ? atoi(getenv("SHK_FAST_VARIANT")) : 5;
-    if (variant == 4) analyze_reads_v4_kernel<HAS_QUAL, MOD><<<tiles, kFastThreads, 0, st>>>(a);
-    else analyze_reads_kernel<HAS_QUAL, MOD><<<tiles, kFastThreads, 0, st>>>(a);
+    analyze_reads_kernel<HAS_QUAL, MOD><<<tiles, kFastThreads, 0, st>>>(a);
     if (ev_ka) cudaEventRecord(ev_ka, st);
     analyze_slow_kernel<HAS_QUAL, MOD><<<slow_blocks, 128, 0, st>>>(a);
 }
