@@ -105,6 +105,8 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     // `const char mq = min_quality + 33` with min_quality a (signed) char: FastqSplitter.hpp:75
     a.mq = (int)(signed char)(unsigned char)((ctx->params.min_quality & 0xFF) + 33);
     a.single = ctx->params.single ? 1 : 0;
+    a.pol_first = ctx->pol_first;
+    a.pol_last = ctx->pol_last;
     a.rec = s.d_rec;
     a.pool = s.d_pool;
     a.pool_cap = s.pool_cap;
@@ -246,6 +248,11 @@ int shk_create(const shk_params *p, shk_ctx **out)
     if (ctx->max_bytes >= (1ull << 32)) return bail(fail(nullptr, SHK_E_LIMIT, "max_bytes_per_chunk must be < 4 GiB"));
     if (cudaStreamCreateWithFlags(&ctx->build_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(nullptr, SHK_E_CUDA, "cudaStreamCreate failed"));
+    rc = fetch_cache_policies(ctx);
+    if (rc) {
+        set_global_error(ctx->err);
+        return bail(rc);
+    }
     // BF bloom(opt::bf_size): the filter, zero-initialised (bloomfilter.h:48-53)
     e = cudaMalloc((void **)&ctx->index.sectors, n_sectors * 32);
     if (e != cudaSuccess)

@@ -57,6 +57,9 @@ struct ReadKernelArgs {
     double c;
     int mq;  // (signed char)(min_quality + 33), FastqSplitter.hpp:75
     int single;
+    // L2 cache-hint descriptors (createpolicy results, fetched once per context): as kernel
+    // parameters they reach the loads through uniform registers without per-load moves
+    uint64_t pol_first, pol_last;
     // outputs
     uint2 *rec;              // per read: x = association count, y = gene id (count==1) or pool offset
     uint32_t *pool;          // winners of reads with >= 2 associations, ascending gene id
@@ -121,6 +124,7 @@ struct shk_ctx {
     uint32_t n_slow_slabs = 0;
     std::atomic<uint64_t> launches{0};
     cudaStream_t build_stream = nullptr;
+    uint64_t pol_first = 0, pol_last = 0;  // createpolicy evict_first / evict_last descriptors
     char err[512] = {0};
 };
 
@@ -150,5 +154,6 @@ int random_sector_bench_device(shk_ctx *ctx, uint64_t n_loads, uint64_t span_byt
 int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st, cudaEvent_t ev_k0,
                         cudaEvent_t ev_ka, cudaEvent_t ev_k1);
 int launch_scatter(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st);
+int fetch_cache_policies(shk_ctx *ctx);
 
 }  // namespace shk

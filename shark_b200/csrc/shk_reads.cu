@@ -119,6 +119,9 @@ constexpr int kFastThreads = 128;
 #ifndef SHK_SKIP_WORDS
 #define SHK_SKIP_WORDS 1
 #endif
+#ifndef SHK_POLICY_ARGS
+#define SHK_POLICY_ARGS 1
+#endif
 static_assert(kFastThreads == (int)kReadsPerTile, "one CTA of the fast kernel = one scan tile");
 
 // ---------------------------------------------------------------------------------------------
@@ -232,7 +235,11 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
     __shared__ uint32_t s_hits[kFastThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kFastThreads + threadIdx.x;
+#if SHK_POLICY_ARGS
+    const uint64_t pol_first = a.pol_first, pol_last = a.pol_last;
+#else
     const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
+#endif
     const uint32_t k = (uint32_t)a.k;
     const uint64_t kmask2 = (1ULL << (2 * k)) - 1ULL;
     const int rc_shift = 2 * (int)k - 2;
@@ -619,6 +626,25 @@ int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_ca
     else if (ev_ka) cudaEventRecord(ev_ka, st);
     if (ev_k1) cudaEventRecord(ev_k1, st);
     return launched;
+}
+
+__global__ void fetch_policies_kernel(uint64_t *out)
+{
+    out[0] = make_policy_evict_first();
+    out[1] = make_policy_evict_last();
+}
+
+int fetch_cache_policies(shk_ctx *ctx)
+{
+    uint64_t *d = nullptr, h[2] = {0, 0};
+    SHK_CUDA(ctx, cudaMalloc((void **)&d, 16));
+    fetch_policies_kernel<<<1, 1>>>(d);
+    cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    SHK_CUDA(ctx, e);
+    ctx->pol_first = h[0];
+    ctx->pol_last = h[1];
+    return SHK_OK;
 }
 
 // Re-runs only the scatter (after the host grew the association buffer).
