@@ -119,6 +119,9 @@ constexpr int kFastThreads = 128;
 #ifndef SHK_SKIP_WORDS
 #define SHK_SKIP_WORDS 1
 #endif
+#ifndef SHK_SLOT_SUB
+#define SHK_SLOT_SUB 1
+#endif
 #ifndef SHK_POLICY_ARGS
 #define SHK_POLICY_ARGS 1
 #endif
@@ -326,7 +329,11 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                     uint4 qq = q[b];
                     uint32_t A, B;
                     for (;;) {
+                        #if SHK_SLOT_SUB  // slot - key: same test and same id (the key's low 18 bits are 0), but an add the FMA pipe can take
+                        const uint32_t d0 = qq.x - kb, d1 = qq.y - kb, d2 = qq.z - kb, d3 = qq.w - kb;
+#else
                         const uint32_t d0 = qq.x ^ kb, d1 = qq.y ^ kb, d2 = qq.z ^ kb, d3 = qq.w ^ kb;
+#endif
                         const uint32_t lo01 = min(d0, d1), hi01 = max(d0, d1), lo23 = min(d2, d3), hi23 = max(d2, d3);
                         A = min(lo01, lo23);                        // smallest
                         B = min(max(lo01, lo23), min(hi01, hi23));  // second smallest
