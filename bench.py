@@ -175,7 +175,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="override reads per GPU (testing)")
     ap.add_argument("--cpu-sample", type=int, default=0,
-                    help="reads given to the CPU reference (0 = max(1M, 50k x cores), at most 4M)")
+                    help="reads given to the CPU reference (0 = 6M for the cpu_baseline leg, about 10 s on 16 cores; "
+                         "2M per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -185,8 +186,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if not args.cpu_sample:
-        # the reference hands out batches of 50 000 reads to its threads (main.cpp:215)
-        args.cpu_sample = min(4_000_000, max(1_000_000, 50_000 * cores))
+        # the reference hands out batches of 50 000 reads to its threads (main.cpp:215): both samples keep every
+        # thread busy; the cpu_baseline leg is one run of ~10 s, the reference arm repeats a shorter one K+W times
+        args.cpu_sample = 2_000_000 if args.impl == "reference" else 6_000_000
     config = {"workload": wl["desc"], "reads_per_gpu": n_reads, "read_len": wl["L"], "paired": wl["paired"], "k": wl["k"],
               "bf_gib": wl["b"], "min_quality": wl["q"], "single": wl["single"], "chunk_reads": CHUNK_READS,
               "sharding": "reads sharded by rank, index replicated (NCCL broadcast)" if world > 1 else "single GPU",
@@ -352,15 +354,20 @@ def main():
                                 "sample": "first %d reads of the workload, oracle/_ref/shark -t %d, sample stage %.2fs "
                                           "(whole run %.2fs)" % (sample, cores, r[0], r[1])}
                 # parity on the same prefix: identical read->gene pairs after sorting (north star)
-                if sample <= chunks[0][3]:
-                    c0 = chunks[0]
-                    res = sh.analyze_chunks([(c0[0][: sample * W], None if c0[1] is None else c0[1][: sample * W],
-                                              c0[2][: sample + 1], sample)])[0]
-                    ref_lines = sorted(open(r[2], "rb").read().split(b"\n"))
-                    ours = sorted([b"r%09d %s" % (int(a), names[int(g)])
-                                   for a, g in zip(res["read_idx"], res["gene_idx"])] + [b""])
-                    cpu_baseline["parity_on_sample"] = bool(ours == ref_lines)
-                    cpu_baseline["ssv_lines"] = len(ref_lines) - 1
+                pref, left = [], sample
+                for c0 in chunks:
+                    if left <= 0:
+                        break
+                    m = min(left, c0[3])
+                    pref.append((c0[0][: m * W], None if c0[1] is None else c0[1][: m * W], c0[2][: m + 1], m))
+                    left -= m
+                ours, base = [b""], 0
+                for res, c0 in zip(sh.analyze_chunks(pref), pref):
+                    ours += [b"r%09d %s" % (base + int(a), names[int(g)]) for a, g in zip(res["read_idx"], res["gene_idx"])]
+                    base += c0[3]
+                ref_lines = sorted(open(r[2], "rb").read().split(b"\n"))
+                cpu_baseline["parity_on_sample"] = bool(sorted(ours) == ref_lines)
+                cpu_baseline["ssv_lines"] = len(ref_lines) - 1
             else:
                 cpu_baseline = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference",
                                 "sample": "oracle/_ref/shark is not built"}
