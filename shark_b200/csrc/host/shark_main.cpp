@@ -6,10 +6,14 @@
 // output (ReadOutput.hpp); everything between goes through shk_index_build / shk_reads_submit /
 // shk_reads_collect.  Extensions (not in the reference): --gpus N, --chunk-reads N.
 //
-// Pipeline: a parser thread fills chunk buffers; the main thread submits chunk i+1 to a free
-// slot before it collects chunk i (double buffering per GPU, chunks round-robin over GPUs) and
-// writes results in chunk order, which reproduces the reference's `-t 1` output order.
+// Pipeline (pipeline.hpp, ingest.hpp): one scanner thread per input file turns 8 MiB blocks into
+// record outcomes without copying; a batcher thread packs whole 50 000-read batches into pinned
+// chunk buffers; the main thread submits chunk i+1 to a free slot before it collects chunk i
+// (double buffering per GPU, chunks round-robin over GPUs); a writer thread prints results in
+// chunk order, which reproduces the reference's `-t 1` output order.
+#include <fcntl.h>
 #include <getopt.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -29,6 +33,7 @@
 
 #include "../../../include/shark_b200.h"
 #include "fastx.hpp"
+#include "pipeline.hpp"
 
 namespace {
 
@@ -167,236 +172,58 @@ void pelapsed(const std::string &s)  // main.cpp:49-54
               << std::chrono::duration_cast<std::chrono::milliseconds>(now_t - start_t).count() / 1000 << std::endl;
 }
 
+// SHK_TIMING=1: millisecond stamps of the host stages on stderr (not part of the reference's output)
+const bool g_timing = getenv("SHK_TIMING") != nullptr;
+void tstamp(const char *what)
+{
+    if (!g_timing) return;
+    auto now_t = std::chrono::high_resolution_clock::now();
+    fprintf(stderr, "[shark-b200/timing] %-28s %8.1f ms\n", what,
+            std::chrono::duration_cast<std::chrono::microseconds>(now_t - start_t).count() / 1000.0);
+}
+
 [[noreturn]] void die(const std::string &msg)
 {
     std::cerr << "shark: " << msg << std::endl;
-    exit(EXIT_FAILURE);
+    fflush(nullptr);
+    _exit(EXIT_FAILURE);  // worker threads may be running: no static destructors under their feet
 }
 
-constexpr unsigned kBatch = 50000;  // FastqSplitter batch (main.cpp:215): ReadOutput's dedup resets per batch
+using shkhost::kBatch;
 
-// Pinned buffer from the library (falls back to nothing: allocation failure is fatal).
-struct Pinned {
-    uint8_t *p = nullptr;
-    size_t cap = 0;
-    void reserve(size_t n)
+// Staging memory of the chunks.  The files are parsed at ~2 GB/s per input file, far below what
+// even a pageable host-to-device copy sustains, while CUDA start-up takes 1-2 s on these boxes: the
+// chunks therefore live in ordinary memory, so that scanning and packing run from the first
+// millisecond, concurrently with the creation of the device context and the index build
+// (SHK_PINNED=1 switches to the library's pinned allocator; bench.py measures that path).
+struct PinnedAlloc {
+    static bool pinned()
     {
-        if (n <= cap) return;
-        size_t want = cap ? cap : (1u << 20);
-        while (want < n) want *= 2;
+        static const bool p = getenv("SHK_PINNED") != nullptr;
+        return p;
+    }
+    static void *alloc(size_t n)
+    {
         void *q = nullptr;
-        if (shk_alloc_pinned(&q, want) != SHK_OK) die(std::string("cannot allocate pinned memory: ") + shk_last_error(nullptr));
-        if (p) {
-            memcpy(q, p, cap);
-            shk_free_pinned(p);
+        if (pinned()) {
+            if (shk_alloc_pinned(&q, n) != SHK_OK) die(std::string("cannot allocate pinned memory: ") + shk_last_error(nullptr));
+        } else if (posix_memalign(&q, 4096, n) != 0) {
+            die("out of memory");
         }
-        p = (uint8_t *)q;
-        cap = want;
+        return q;
     }
-    ~Pinned()
+    static void free(void *p)
     {
-        if (p) shk_free_pinned(p);
+        if (pinned()) shk_free_pinned(p);
+        else ::free(p);
     }
 };
+using Chunk = shkhost::Chunk<PinnedAlloc>;
+using Batcher = shkhost::Batcher<PinnedAlloc>;
+using Writer = shkhost::Writer<PinnedAlloc>;
+static_assert(sizeof(shkhost::AssocPair) == sizeof(shk_assoc), "AssocPair mirrors shk_assoc");
 
-// One chunk of reads in the SoA layout of shk_reads_submit plus what ReadOutput needs.
-struct Chunk {
-    Pinned seq, qual, off;              // text (mate1 [+ 'N' + mate2]), qualities (+ 0x1B), uint32 offsets
-    std::vector<char> host_qual;        // qualities when they are not sent to the GPU (min_quality == 0)
-    std::vector<uint64_t> qual_pos;     // per read: start of its quality text in host_qual
-    std::string names;                  // name1 '\0' [name2 '\0'] per read
-    std::vector<uint64_t> name_pos;     // per read: start in names
-    std::vector<uint32_t> len1;         // per read: length of mate 1 (mate 2 = total - len1 - 1)
-    std::vector<uint32_t> batch_start;  // read indices where a 50 000-read batch begins
-    uint32_t n = 0;
-    uint64_t bytes = 0;
-    bool last = false;
-    uint64_t index = 0;
-    void clear()
-    {
-        host_qual.clear();
-        qual_pos.clear();
-        names.clear();
-        name_pos.clear();
-        len1.clear();
-        batch_start.clear();
-        n = 0;
-        bytes = 0;
-        last = false;
-    }
-};
-
-// FastqSplitter::operator() called until it returns an empty batch (main.cpp:66-77,
-// FastqSplitter.hpp:47-93): a failed kseq_read ends the CURRENT batch only.  Fills one chunk with
-// whole batches; returns false when the input is exhausted (the chunk may still hold reads).
-class Batcher {
-public:
-    Batcher(const Options &o) : opt_(o), r1_(o.sample1_path.c_str()), with_qual_gpu_(o.min_quality != 0)
-    {
-        if (o.paired) r2_.reset(new shkhost::FastxReader(o.sample2_path.c_str()));
-    }
-    bool files_ok() const { return r1_.ok() && (!r2_ || r2_->ok()); }
-
-    bool fill(Chunk &ch, unsigned max_reads, uint64_t max_bytes)
-    {
-        ch.clear();
-        uint64_t last_batch_bytes = 0;
-        while ((ch.n + kBatch <= max_reads && ch.bytes + last_batch_bytes + last_batch_bytes / 4 <= max_bytes) || ch.n == 0) {
-            ch.batch_start.push_back(ch.n);
-            const uint64_t bytes0 = ch.bytes;
-            unsigned got = 0;
-            while (got < kBatch) {
-                if (r1_.read(n1_, s1_, q1_) < 0) break;
-                if (r2_ && r2_->read(n2_, s2_, q2_) < 0) break;  // mate 1 is dropped (FastqSplitter.hpp:61)
-                append(ch);
-                ++got;
-            }
-            if (got == 0) {
-                ch.batch_start.pop_back();
-                return false;  // empty batch: the reference's worker returns (main.cpp:70)
-            }
-            last_batch_bytes = ch.bytes - bytes0;
-        }
-        return true;
-    }
-
-private:
-    // C-string semantics of the reference (FastqSplitter.hpp:56: `seq1->seq.s` as const char*)
-    static size_t clen(const std::string &s)
-    {
-        size_t z = s.find('\0');
-        return z == std::string::npos ? s.size() : z;
-    }
-    void append(Chunk &ch)
-    {
-        const size_t l1 = clen(s1_), l2 = r2_ ? clen(s2_) : 0;
-        const size_t total = r2_ ? l1 + 1 + l2 : l1;
-        ch.off.reserve(((size_t)ch.n + 2) * 4);
-        uint32_t *off = (uint32_t *)ch.off.p;
-        if (ch.n == 0) off[0] = 0;
-        ch.seq.reserve(ch.bytes + total + 8);
-        uint8_t *d = ch.seq.p + ch.bytes;
-        memcpy(d, s1_.data(), l1);
-        if (r2_) {
-            d[l1] = 'N';  // FastqSplitter.hpp:63,83
-            memcpy(d + l1 + 1, s2_.data(), l2);
-        }
-        // qualities: mask_seq walks the QUAL string (FastqSplitter.hpp:104-108); positions it does
-        // not reach are never masked -> pad with 0x7f, which is not < any mq
-        const size_t ql1 = clen(q1_), ql2 = r2_ ? clen(q2_) : 0;
-        if (with_qual_gpu_) {
-            ch.qual.reserve(ch.bytes + total + 8);
-            uint8_t *q = ch.qual.p + ch.bytes;
-            memset(q, 0x7f, total);
-            if (!r2_) {
-                memcpy(q, q1_.data(), ql1 < total ? ql1 : total);
-            } else {
-                // string(qual1) + "\33" + string(qual2), FastqSplitter.hpp:84
-                std::string j;
-                j.reserve(ql1 + 1 + ql2);
-                j.append(q1_.data(), ql1).push_back('\33');
-                j.append(q2_.data(), ql2);
-                memcpy(q, j.data(), j.size() < total ? j.size() : total);
-            }
-        }
-        // what ReadOutput prints: names, original sequences (from ch.seq) and quality strings
-        ch.name_pos.push_back(ch.names.size());
-        ch.names.append(n1_.c_str());
-        ch.names.push_back('\0');
-        if (r2_) {
-            ch.names.append(n2_.c_str());
-            ch.names.push_back('\0');
-        }
-        ch.qual_pos.push_back(ch.host_qual.size());
-        ch.host_qual.insert(ch.host_qual.end(), q1_.data(), q1_.data() + ql1);
-        ch.host_qual.push_back('\0');
-        if (r2_) {
-            ch.host_qual.insert(ch.host_qual.end(), q2_.data(), q2_.data() + ql2);
-            ch.host_qual.push_back('\0');
-        }
-        ch.len1.push_back((uint32_t)l1);
-        ch.bytes += total;
-        ++ch.n;
-        off[ch.n] = (uint32_t)ch.bytes;
-    }
-
-    const Options &opt_;
-    shkhost::FastxReader r1_;
-    std::unique_ptr<shkhost::FastxReader> r2_;
-    bool with_qual_gpu_;
-    std::string n1_, s1_, q1_, n2_, s2_, q2_;
-};
-
-// ReadOutput::operator() (ReadOutput.hpp:37-50) for one chunk's associations.
-class Writer {
-public:
-    Writer(const Options &o, const std::vector<std::string> &legend) : legend_(legend), paired_(o.paired)
-    {
-        if (!o.out1_path.empty()) out1_ = fopen(o.out1_path.c_str(), "w");
-        if (o.paired && !o.out2_path.empty()) out2_ = fopen(o.out2_path.c_str(), "w");
-        if (out1_) setvbuf(out1_, nullptr, _IOFBF, 1 << 22);
-        if (out2_) setvbuf(out2_, nullptr, _IOFBF, 1 << 22);
-        setvbuf(stdout, nullptr, _IOFBF, 1 << 22);
-    }
-    ~Writer()
-    {
-        if (out1_) fclose(out1_);
-        if (out2_) fclose(out2_);
-        fflush(stdout);
-    }
-    void write(const Chunk &ch, const shk_chunk_result &res)
-    {
-        const uint32_t *off = (const uint32_t *)ch.off.p;
-        size_t next_batch = 0;
-        const char *previd = "";  // `string previd = ""` per ReadOutput call = per batch
-        for (uint64_t i = 0; i < res.n_assoc; ++i) {
-            const uint32_t r = res.assoc[i].read_idx, g = res.assoc[i].gene_idx;
-            while (next_batch < ch.batch_start.size() && ch.batch_start[next_batch] <= r) {
-                previd = "";
-                ++next_batch;
-            }
-            const char *id1 = ch.names.data() + ch.name_pos[r];
-            const char *gene = g < legend_.size() ? legend_[g].c_str() : "";
-            fputs(id1, stdout);
-            fputc(' ', stdout);
-            fputs(gene, stdout);
-            fputc('\n', stdout);
-            if (strcmp(previd, id1) != 0) {
-                const char *s = (const char *)ch.seq.p + off[r];
-                const char *q1 = ch.host_qual.data() + ch.qual_pos[r];
-                if (out1_) {
-                    fputc('@', out1_);
-                    fputs(id1, out1_);
-                    fputc('\n', out1_);
-                    fwrite(s, 1, ch.len1[r], out1_);
-                    fputs("\n+\n", out1_);
-                    fputs(q1, out1_);
-                    fputc('\n', out1_);
-                }
-                if (out2_ && paired_) {
-                    const char *id2 = id1 + strlen(id1) + 1;
-                    const char *q2 = q1 + strlen(q1) + 1;
-                    const uint32_t l2 = off[r + 1] - off[r] - ch.len1[r] - 1;
-                    fputc('@', out2_);
-                    fputs(id2, out2_);
-                    fputc('\n', out2_);
-                    fwrite(s + ch.len1[r] + 1, 1, l2, out2_);
-                    fputs("\n+\n", out2_);
-                    fputs(q2, out2_);
-                    fputc('\n', out2_);
-                }
-            }
-            previd = id1;
-        }
-    }
-
-private:
-    const std::vector<std::string> &legend_;
-    bool paired_;
-    FILE *out1_ = nullptr, *out2_ = nullptr;
-};
-
-// Simple blocking queue for the parser -> device hand-off.
+// Simple blocking queue for the hand-offs between the pipeline threads.
 template <class T>
 class Channel {
 public:
@@ -444,6 +271,33 @@ int main(int argc, char *argv[])
         std::cerr << std::endl;
     }
 
+    // The sample files are scanned ahead by their own threads from the start (they run into a
+    // bounded queue while the index is being built).
+    Batcher batcher(opt.sample1_path.c_str(), opt.paired ? opt.sample2_path.c_str() : nullptr, opt.min_quality != 0);
+    if (batcher.files_ok()) batcher.start();
+    else die("cannot open sample file(s)");
+    const unsigned chunk_reads = std::max(kBatch, opt.chunk_reads / kBatch * kBatch);
+    // slot buffers are sized by this; a chunk is closed early when its text would not fit
+    const uint64_t max_chunk_bytes = std::min<uint64_t>(0xF0000000ull, std::max<uint64_t>((uint64_t)chunk_reads * 640, 256ull << 20));
+    const size_t n_bufs = (size_t)opt.gpus * 2 + 3;
+    std::vector<std::unique_ptr<Chunk>> pool;
+    Channel<Chunk *> free_q, ready_q, write_q;
+    for (size_t i = 0; i < n_bufs; ++i) {
+        pool.emplace_back(new Chunk);
+        free_q.push(pool.back().get());
+    }
+    std::thread parser([&] {  // packs chunks while the device context and the index are being set up
+        uint64_t idx = 0;
+        for (;;) {
+            Chunk *ch = free_q.pop();
+            const bool more = batcher.fill(*ch, chunk_reads, max_chunk_bytes);
+            ch->index = idx++;
+            ch->last = !more;
+            ready_q.push(ch);
+            if (!more) break;
+        }
+    });
+
     // ---- reference: FastaSplitter (FastaSplitter.hpp:42-54) -> legend_ID + concatenated records.
     // Unlike the reference (which ignores open failures and later segfaults) we fail cleanly.
     std::vector<std::string> legend_ID;
@@ -461,9 +315,7 @@ int main(int argc, char *argv[])
         }
     }
 
-    const unsigned chunk_reads = std::max(kBatch, opt.chunk_reads / kBatch * kBatch);
-    // slot buffers are sized by this; a chunk is closed early when its text would not fit
-    const uint64_t max_chunk_bytes = std::min<uint64_t>(0xF0000000ull, std::max<uint64_t>((uint64_t)chunk_reads * 640, 256ull << 20));
+    tstamp("reference parsed");
     std::vector<shk_ctx *> ctxs((size_t)opt.gpus, nullptr);
     for (int g = 0; g < opt.gpus; ++g) {
         shk_params p;
@@ -479,8 +331,10 @@ int main(int argc, char *argv[])
         p.max_bytes_per_chunk = max_chunk_bytes;
         if (shk_create(&p, &ctxs[g]) != SHK_OK) die(std::string("shk_create: ") + shk_last_error(nullptr));
     }
+    tstamp("contexts created");
     shk_index_info info;
     SHK_TRY(ctxs[0], shk_index_build(ctxs[0], ref_bases.data(), rec_off.data(), (uint32_t)legend_ID.size(), &info));
+    tstamp("index built");
     pelapsed("Transcript file processed");
     pelapsed("First switch performed");
     pelapsed("BF created from transcripts (" + std::to_string(info.n_genes) + " genes)");
@@ -488,28 +342,20 @@ int main(int argc, char *argv[])
     pelapsed("Second switch performed");
     std::vector<uint8_t>().swap(ref_bases);
 
-    // ---- sample stage
-    Batcher batcher(opt);
-    if (!batcher.files_ok()) die("cannot open sample file(s)");
-    Writer writer(opt, legend_ID);
+    // ---- sample stage: scanners -> batcher thread -> (this thread: submit / collect) -> writer thread
+    const int fd1 = opt.out1_path.empty() ? -1 : open(opt.out1_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    const int fd2 = (!opt.paired || opt.out2_path.empty()) ? -1 : open(opt.out2_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    Writer writer(STDOUT_FILENO, fd1, fd2, legend_ID, opt.paired);
 
-    const size_t n_bufs = (size_t)opt.gpus * 2 + 2;
-    std::vector<std::unique_ptr<Chunk>> pool;
-    Channel<Chunk *> free_q, ready_q;
-    for (size_t i = 0; i < n_bufs; ++i) {
-        pool.emplace_back(new Chunk);
-        free_q.push(pool.back().get());
-    }
-    std::thread parser([&] {
-        uint64_t idx = 0;
+    std::thread writer_thread([&] {
         for (;;) {
-            Chunk *ch = free_q.pop();
-            const bool more = batcher.fill(*ch, chunk_reads, max_chunk_bytes);
-            ch->index = idx++;
-            ch->last = !more;
-            ready_q.push(ch);
-            if (!more) break;
+            Chunk *ch = write_q.pop();
+            if (!ch) break;
+            writer.write(*ch);
+            ch->clear();  // releases the scanner blocks
+            free_q.push(ch);
         }
+        writer.flush();
     });
 
     struct InFlight {
@@ -525,16 +371,20 @@ int main(int argc, char *argv[])
         inflight.pop_front();
         shk_chunk_result res;
         SHK_TRY(ctxs[f.gpu], shk_reads_collect(ctxs[f.gpu], f.slot, &res));
-        writer.write(*f.ch, res);
-        free_q.push(f.ch);
+        // the slot's result buffers are reused by its next submit: take the list with the chunk
+        const shkhost::AssocPair *as = reinterpret_cast<const shkhost::AssocPair *>(res.assoc);
+        f.ch->assoc.assign(as, as + res.n_assoc);
+        write_q.push(f.ch);
     };
     for (bool done = false; !done;) {
         Chunk *ch = ready_q.pop();
         done = ch->last;
         if (ch->n == 0) {
+            ch->clear();
             free_q.push(ch);
             continue;
         }
+        if (submitted == 0) tstamp("first chunk packed");
         if (inflight.size() == max_inflight) drain_one();
         const int gpu = (int)(submitted % (uint64_t)opt.gpus);
         const uint32_t slot = (uint32_t)((submitted / (uint64_t)opt.gpus) % 2);
@@ -544,7 +394,15 @@ int main(int argc, char *argv[])
         ++submitted;
     }
     while (!inflight.empty()) drain_one();
+    tstamp("last chunk collected");
     parser.join();
+    write_q.push(nullptr);
+    writer_thread.join();
+    if (fd1 >= 0) close(fd1);
+    if (fd2 >= 0) close(fd2);
+    tstamp("output written");
+    pool.clear();  // pinned staging goes back before the contexts do
+    tstamp("staging freed");
     pelapsed("Sample completed");
     for (auto *c : ctxs) shk_destroy(c);
     pelapsed("Association done");

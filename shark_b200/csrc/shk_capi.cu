@@ -1,4 +1,7 @@
 // C ABI of libshark_b200.so (include/shark_b200.h): contexts, slots, streams, copies.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -53,6 +56,16 @@ static void free_slot(Slot &s)
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot{};
+}
+
+// SHK_TIMING=1: stderr stamps of the start-up steps (diagnostics only)
+static void tmark(const char *what)
+{
+    static const bool on = getenv("SHK_TIMING") != nullptr;
+    static const auto t0 = std::chrono::steady_clock::now();
+    if (on)
+        fprintf(stderr, "[libshark_b200/timing] %-24s +%8.1f ms\n", what,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 }
 
 static int alloc_slot(shk_ctx *ctx, Slot &s)
@@ -212,8 +225,10 @@ int shk_create(const shk_params *p, shk_ctx **out)
     if (n_sectors * 8 > 0xFFFFFFFFull)
         return fail(nullptr, SHK_E_LIMIT, "bf_bits=%llu: filters above ~2^36.8 bits (-b 14) are not supported",
                     (unsigned long long)p->bf_bits);
+    tmark("shk_create enter");
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
+    tmark("device count");
     if (e != cudaSuccess || n_dev == 0)
         return fail(nullptr, SHK_E_CUDA, "no CUDA device (%s); this library has no CPU fallback",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
@@ -228,6 +243,8 @@ int shk_create(const shk_params *p, shk_ctx **out)
         return code;
     };
     if (cudaSetDevice(ctx->device) != cudaSuccess) return bail(fail(nullptr, SHK_E_CUDA, "cudaSetDevice failed"));
+    cudaFree(nullptr);
+    tmark("primary context");
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     FilterGeom &g = ctx->index.geom;
@@ -259,6 +276,7 @@ int shk_create(const shk_params *p, shk_ctx **out)
         return bail(fail(nullptr, SHK_E_NOMEM, "cannot allocate %llu bytes for the filter: %s",
                          (unsigned long long)(n_sectors * 32), cudaGetErrorString(e)));
     cudaMemset(ctx->index.sectors, 0, n_sectors * 32);
+    tmark("filter allocated");
     ctx->slots = new (std::nothrow) Slot[ctx->n_slots];
     if (!ctx->slots) return bail(fail(nullptr, SHK_E_NOMEM, "out of host memory"));
     for (uint32_t i = 0; i < ctx->n_slots; ++i) {
@@ -268,6 +286,7 @@ int shk_create(const shk_params *p, shk_ctx **out)
             return bail(rc);
         }
     }
+    tmark("slots allocated");
     *out = ctx;
     return SHK_OK;
 }
