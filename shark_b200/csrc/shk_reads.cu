@@ -233,10 +233,7 @@ struct Mru4 {
 template <bool HAS_QUAL, int MOD>
 __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_reads_kernel(const ReadKernelArgs a)
 {
-    __shared__ uint32_t s_assoc[kFastThreads / 32];
-    __shared__ uint32_t s_probes[kFastThreads / 32];
-    __shared__ uint32_t s_hits[kFastThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * kFastThreads + threadIdx.x;
 #if SHK_POLICY_ARGS
     const uint64_t pol_first = a.pol_first, pol_last = a.pol_last;
@@ -424,20 +421,14 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
         }
         a.rec[r] = make_uint2(count, payload);
     }
+    // every warp retires on its own (tile_sums is zeroed before the launch): no warp of a CTA
+    // waits at a barrier for its slowest sibling
     const uint32_t wa = __reduce_add_sync(kFull, count), wp = __reduce_add_sync(kFull, my_probes),
                    wh = __reduce_add_sync(kFull, my_hits);
     if (lane == 0) {
-        s_assoc[warp] = wa;
-        s_probes[warp] = wp;
-        s_hits[warp] = wh;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t ta = 0, tp = 0, th = 0;
-        for (int w = 0; w < kFastThreads / 32; ++w) ta += s_assoc[w], tp += s_probes[w], th += s_hits[w];
-        a.tile_sums[blockIdx.x] = ta;
-        if (tp) atomicAdd(&a.counters->n_probes, (unsigned long long)tp);
-        if (th) atomicAdd(&a.counters->n_hits, (unsigned long long)th);
+        if (wa) atomicAdd(&a.tile_sums[blockIdx.x], wa);
+        if (wp) atomicAdd(&a.counters->n_probes, (unsigned long long)wp);
+        if (wh) atomicAdd(&a.counters->n_hits, (unsigned long long)wh);
     }
 }
 
@@ -618,6 +609,7 @@ int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_ca
         const unsigned tiles = (a.n_reads + kReadsPerTile - 1) / kReadsPerTile;
         const unsigned slow_blocks = (a.n_slow_slabs + 3) / 4;
         const bool q = a.qual != nullptr;
+        cudaMemsetAsync(a.tile_sums, 0, (size_t)tiles * 4, st);  // the classification kernels add to it
         switch (a.geom.mod_kind) {
         case MOD_POW2: q ? launch_typed<true, MOD_POW2>(a, st, tiles, slow_blocks, ev_ka) : launch_typed<false, MOD_POW2>(a, st, tiles, slow_blocks, ev_ka); break;
         case MOD_B33: q ? launch_typed<true, MOD_B33>(a, st, tiles, slow_blocks, ev_ka) : launch_typed<false, MOD_B33>(a, st, tiles, slow_blocks, ev_ka); break;
