@@ -178,6 +178,8 @@ def main():
                     help="reads given to the CPU reference (0 = 6M for the cpu_baseline leg, about 10 s on 16 cores; "
                          "2M per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extend", default="auto", choices=["auto", "on", "off"],
+                    help="anchor-and-extend: automatic (on for DRAM-sized front tables), or forced (A/B runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     n_reads = args.reads or wl["reads"]
@@ -244,7 +246,8 @@ def main():
     names, bases, rec_off, chunks, keep_alive, W = make_workload(wl, rank, n_reads)
     n_chunks = len(chunks)
     sh = Shark(k=wl["k"], c=wl["c"], bf_bits=wl["b"] << 33, min_quality=wl["q"], single=wl["single"], device=local_rank,
-               n_slots=max(n_chunks, 2), max_reads_per_chunk=CHUNK_READS, max_bytes_per_chunk=CHUNK_READS * W)
+               n_slots=max(n_chunks, 2), max_reads_per_chunk=CHUNK_READS, max_bytes_per_chunk=CHUNK_READS * W,
+               extend={"auto": None, "on": True, "off": False}[args.extend])
     # index: build on rank 0, replicate over NVLink
     bcast_ms = 0.0
     if rank == 0:
@@ -277,15 +280,19 @@ def main():
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    n_probes = n_hits = n_assoc = n_slow = 0
+    sh.timer_start()  # device stopwatch (CUDA events over all slot streams); the host clock is the cross-check
+    n_probes = n_hits = n_assoc = n_slow = n_ext = n_loads = 0
     for _ in range(args.steps):
         for r in resident_step():
             n_probes += r["n_probes"]
             n_hits += r["n_hits"]
             n_assoc += r["n_assoc"]
             n_slow += r["n_slow_reads"]
+            n_ext += r["n_extended"]
+            n_loads += r["n_table_loads"]
+    t_res = sh.timer_stop() * 1e-3
     barrier()
-    t_res = time.perf_counter() - t0
+    t_res_wall = time.perf_counter() - t0
     launches_res = sh.kernel_launches() - launches0
 
     # ---- roofline pass: the same launches one at a time (no overlap between the slots' streams),
@@ -308,19 +315,21 @@ def main():
         sh2.analyze_chunks(chunks, copy=False, on_result=lambda r: None)
     barrier()
     t0 = time.perf_counter()
+    sh2.timer_start()
     for _ in range(args.steps):
         sh2.analyze_chunks(chunks, copy=False, on_result=on_result)
+    t_e2e = sh2.timer_stop() * 1e-3
     barrier()
-    t_e2e = time.perf_counter() - t0
+    t_e2e_wall = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    # max over ranks
-    times = torch.tensor([t_res, t_e2e, probe_ms], dtype=torch.float64, device="cuda")
+    # max over ranks (device times; the wall-clock figures ride along as a cross-check)
+    times = torch.tensor([t_res, t_e2e, probe_ms, t_res_wall, t_e2e_wall], dtype=torch.float64, device="cuda")
     sums = torch.tensor([float(n_probes), float(n_hits), float(n_assoc)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    t_res_max, t_e2e_max, probe_ms_max = times.tolist()
+    t_res_max, t_e2e_max, probe_ms_max, t_res_wall_max, t_e2e_wall_max = times.tolist()
     total_reads = n_reads * world * args.steps
     value = total_reads / t_res_max
     e2e_value = total_reads / t_e2e_max
@@ -342,6 +351,8 @@ def main():
                 "algorithmic_bytes_per_launch": 32.0 * probes_per_launch, "probes_per_launch": probes_per_launch,
                 "kernel_ms_per_launch": probe_ms_per_launch, "launches_per_step": launches_per_step,
                 "hit_fraction": n_hits / max(n_probes, 1),
+                "extend": bool(info.extend), "extended_fraction": n_ext / max(n_probes, 1),
+                "table_loads_per_probe": (n_loads / max(n_probes, 1)) if info.extend else 1.0,
                 "random_sector_ceiling_gbs": rs_gbs, "frac_of_random_sector_ceiling": achieved / rs_gbs if rs_gbs else None}
 
     cpu_baseline = None
@@ -375,11 +386,13 @@ def main():
     if rank == 0:
         out = {
             "metric": "reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_res_max / args.steps * 1e3, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": t_res_max / args.steps * 1e3,
+            "timing": "CUDA events over all slot streams (shk_device_timer_*), max over ranks",
+            "wall_ms_per_step": t_res_wall_max / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": n_reads * W * (2 if wl["q"] else 1)
                     + n_chunks * (CHUNK_READS + 1) * 4, "d2h_bytes_per_step": d2h[0] // max(args.steps, 1),
-                    "ms_per_step": t_e2e_max / args.steps * 1e3},
+                    "ms_per_step": t_e2e_max / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall_max / args.steps * 1e3},
             "gpu_launches": int(launches_res), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "index": {"n_genes": info.n_genes, "n_set_bits": info.n_set_bits, "tot_ids": info.tot_ids,
                       "build_ms": info.build_ms, "broadcast_ms": bcast_ms, "device_bytes": info.device_bytes},

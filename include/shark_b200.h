@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SHK_ABI_VERSION 1
+#define SHK_ABI_VERSION 2
 
 typedef enum shk_status {
     SHK_OK = 0,
@@ -51,8 +51,14 @@ typedef struct shk_params {
     uint32_t n_slots;             /* chunk slots for double buffering (0 -> 2)                     */
     uint32_t max_reads_per_chunk; /* slot capacity in reads   (0 -> 1<<20)                         */
     uint64_t max_bytes_per_chunk; /* slot capacity in sequence bytes (0 -> 320 * max_reads)        */
-    uint32_t reserved[8];         /* must be zero                                                  */
+    uint32_t flags;               /* SHK_F_*; 0 = defaults                                         */
+    uint32_t reserved[7];         /* must be zero                                                  */
 } shk_params;
+
+/* shk_params.flags.  Anchor-and-extend: results are identical either way; by default
+ * it is switched on when the front table is too large to stay in L2. */
+#define SHK_F_EXTEND_ON 1u  /* always build and use the extension structures                       */
+#define SHK_F_EXTEND_OFF 2u /* never                                                               */
 
 typedef struct shk_index_info {
     uint32_t n_records;  /* FASTA records given (= legend_ID.size(), FastaSplitter.hpp:48)         */
@@ -64,7 +70,11 @@ typedef struct shk_index_info {
     uint64_t device_bytes; /* HBM held by the index                                               */
     float build_ms;        /* device time of the whole build (CUDA events)                         */
     uint32_t front_shift;  /* front table: log2(positions per bucket)                              */
-    uint64_t front_entries; /* front table: 16-byte entries (buckets + overflow records)          */
+    uint64_t front_entries; /* front table: entries (buckets + overflow records)                  */
+    uint64_t ref_bases;    /* bases of the concatenated reference (extension structures)           */
+    uint32_t extend;       /* 1 = the index carries the anchor-and-extend structures: front-table
+                              entries are 32 bytes (slots + anchors), views 5-7 are present        */
+    uint32_t coarse_shift; /* log2(filter positions per bit of the coarse miss filter)             */
 } shk_index_info;
 
 /* One association = one line of the reference's stdout (ReadOutput.hpp:43): read `read_idx`
@@ -89,6 +99,9 @@ typedef struct shk_chunk_result {
     float total_ms;         /* device time H2D + kernels + D2H of counters                         */
     uint32_t kernel_launches;
     float probe_kernel_ms;  /* device time of the dominant kernel alone (analyze_reads_kernel)     */
+    uint64_t n_extended;    /* probes resolved by anchor-and-extend, without a table access        */
+    uint64_t n_table_loads; /* front-table entries the fast kernel loaded (extension mode only;
+                               the rest of the probes were answered by the coarse miss filter)     */
 } shk_chunk_result;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -125,10 +138,12 @@ int shk_index_export(shk_ctx *ctx, uint64_t *set_bit_pos, uint32_t *offsets, uin
  * (ncclBroadcast over NVLink, cudaMemcpyPeer): call shk_index_views on the source context,
  * shk_index_adopt (allocates same-sized buffers) + shk_index_views on each destination, copy
  * every view, then shk_index_finalize on the destinations. */
-#define SHK_INDEX_N_VIEWS 5
+#define SHK_INDEX_N_VIEWS 8
 typedef struct shk_index_views {
     void *dev_ptr[SHK_INDEX_N_VIEWS]; /* 0 filter sectors, 1 per-bit entries, 2 CSR offsets, 3 CSR ids,
-                                         4 front table */
+                                         4 front table; when info.extend: 5 reference stream (base +
+                                         extension flags per position), 6 2-bit packed reference,
+                                         7 coarse miss filter (bytes = 0 otherwise) */
     uint64_t bytes[SHK_INDEX_N_VIEWS];
     shk_index_info info;
 } shk_index_views;
@@ -183,6 +198,13 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *result);
 int shk_reads_upload(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint8_t *qual,
                      const uint32_t *read_offsets, uint32_t n_reads);
 int shk_reads_analyze_resident(shk_ctx *ctx, uint32_t slot);
+
+/* Device-side stopwatch over ALL slots of a context (CUDA events, no host clock): start records
+ * an event after everything enqueued so far; stop records one after everything enqueued since, on
+ * every slot stream, waits for it and returns the elapsed device time.  bench.py times its steps
+ * with this pair. */
+int shk_device_timer_start(shk_ctx *ctx);
+int shk_device_timer_stop(shk_ctx *ctx, float *ms);
 
 /* Kernel launches issued by this context so far (for bench accounting). */
 uint64_t shk_kernel_launches(const shk_ctx *ctx);

@@ -20,7 +20,8 @@ EXPORTED = [
     "shk_abi_version", "shk_create", "shk_destroy", "shk_last_error", "shk_index_build", "shk_index_info_get",
     "shk_index_export", "shk_index_views_get", "shk_index_adopt", "shk_index_finalize", "shk_index_replicate", "shk_probe", "shk_probe_bench",
     "shk_random_sector_bench", "shk_alloc_pinned", "shk_free_pinned", "shk_reads_submit", "shk_reads_collect",
-    "shk_reads_upload", "shk_reads_analyze_resident", "shk_kernel_launches",
+    "shk_reads_upload", "shk_reads_analyze_resident", "shk_kernel_launches", "shk_device_timer_start",
+    "shk_device_timer_stop",
 ]
 
 
@@ -33,17 +34,22 @@ class SharkError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("k", C.c_uint32), ("c", C.c_double), ("bf_bits", C.c_uint64), ("min_quality", C.c_int32),
                 ("single", C.c_int32), ("device", C.c_int32), ("n_slots", C.c_uint32),
-                ("max_reads_per_chunk", C.c_uint32), ("max_bytes_per_chunk", C.c_uint64), ("reserved", C.c_uint32 * 8)]
+                ("max_reads_per_chunk", C.c_uint32), ("max_bytes_per_chunk", C.c_uint64), ("flags", C.c_uint32),
+                ("reserved", C.c_uint32 * 7)]
+
+
+F_EXTEND_ON, F_EXTEND_OFF = 1, 2
 
 
 class IndexInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint32), ("n_genes", C.c_uint32), ("n_set_bits", C.c_uint64), ("tot_ids", C.c_uint64),
                 ("n_windows", C.c_uint64), ("bf_bits", C.c_uint64), ("device_bytes", C.c_uint64), ("build_ms", C.c_float),
-                ("front_shift", C.c_uint32), ("front_entries", C.c_uint64)]
+                ("front_shift", C.c_uint32), ("front_entries", C.c_uint64), ("ref_bases", C.c_uint64),
+                ("extend", C.c_uint32), ("coarse_shift", C.c_uint32)]
 
 
 class IndexViews(C.Structure):
-    _fields_ = [("dev_ptr", C.c_void_p * 5), ("bytes", C.c_uint64 * 5), ("info", IndexInfo)]
+    _fields_ = [("dev_ptr", C.c_void_p * 8), ("bytes", C.c_uint64 * 8), ("info", IndexInfo)]
 
 
 class Assoc(C.Structure):
@@ -54,7 +60,7 @@ class ChunkResult(C.Structure):
     _fields_ = [("n_assoc", C.c_uint64), ("assoc", C.POINTER(Assoc)), ("keep", C.POINTER(C.c_uint8)),
                 ("n_reads", C.c_uint32), ("n_slow_reads", C.c_uint32), ("n_probes", C.c_uint64), ("n_hits", C.c_uint64),
                 ("analyze_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
-                ("probe_kernel_ms", C.c_float)]
+                ("probe_kernel_ms", C.c_float), ("n_extended", C.c_uint64), ("n_table_loads", C.c_uint64)]
 
 
 _lib = None
@@ -91,6 +97,8 @@ def load():
     L.shk_reads_collect.argtypes = [vp, C.c_uint32, C.POINTER(ChunkResult)]
     L.shk_reads_upload.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32]
     L.shk_reads_analyze_resident.argtypes = [vp, C.c_uint32]
+    L.shk_device_timer_start.argtypes = [vp]
+    L.shk_device_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.shk_kernel_launches.argtypes = [vp]
     L.shk_kernel_launches.restype = C.c_uint64
     for name in EXPORTED:

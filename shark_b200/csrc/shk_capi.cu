@@ -112,6 +112,11 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     a.geom = ctx->index.geom;
     a.front = ctx->index.front;
     a.fgeom = ctx->index.fgeom;
+    a.estream = ctx->index.estream;
+    a.ref2 = ctx->index.ref2;
+    a.coarse = ctx->index.coarse;
+    a.coarse_rel = ctx->index.egeom.enabled ? ctx->index.fgeom.shift - ctx->index.egeom.coarse_shift : 0;
+    a.coarse_key_shift = kFrontKeyShift + ctx->index.egeom.coarse_shift;
     a.n_genes = ctx->index.info.n_genes;
     a.k = (int)ctx->params.k;
     a.c = ctx->params.c;
@@ -220,6 +225,9 @@ int shk_create(const shk_params *p, shk_ctx **out)
     if (p->k == 0 || p->k > 31) return fail(nullptr, SHK_E_ARG, "k must be in the range [1, 31]");
     if (!(p->c >= 0.0 && p->c <= 1.0)) return fail(nullptr, SHK_E_ARG, "c must be in the range [0, 1]");
     if (p->bf_bits < 64) return fail(nullptr, SHK_E_ARG, "bf_bits must be >= 64");
+    if ((p->flags & SHK_F_EXTEND_ON) && (p->flags & SHK_F_EXTEND_OFF))
+        return fail(nullptr, SHK_E_ARG, "SHK_F_EXTEND_ON and SHK_F_EXTEND_OFF are exclusive");
+    if (p->flags & ~(SHK_F_EXTEND_ON | SHK_F_EXTEND_OFF)) return fail(nullptr, SHK_E_ARG, "unknown flag bits");
     const uint64_t n_words = (p->bf_bits + 31) / 32;
     const uint64_t n_sectors = (n_words + kWordsPerSector - 1) / kWordsPerSector;
     if (n_sectors * 8 > 0xFFFFFFFFull)
@@ -305,7 +313,14 @@ void shk_destroy(shk_ctx *ctx)
     cudaFree(ctx->index.csr_off);
     cudaFree(ctx->index.csr_ids);
     cudaFree(ctx->index.front);
+    cudaFree(ctx->index.estream);
+    cudaFree(ctx->index.ref2);
+    cudaFree(ctx->index.coarse);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->timer_stream) cudaStreamDestroy(ctx->timer_stream);
     delete ctx;
 }
 
@@ -353,7 +368,14 @@ int shk_index_views_get(shk_ctx *ctx, shk_index_views *v)
     v->dev_ptr[3] = ix.csr_ids;
     v->bytes[3] = std::max<uint64_t>(ix.info.tot_ids, 1) * 2;
     v->dev_ptr[4] = ix.front;
-    v->bytes[4] = ix.fgeom.n_entries * 16;
+    v->bytes[4] = ix.fgeom.n_entries * 16 * ix.fgeom.stride;
+    const bool ext = ix.egeom.enabled != 0;
+    v->dev_ptr[5] = ext ? ix.estream : nullptr;
+    v->bytes[5] = ext ? ix.egeom.estream_words * 8 : 0;
+    v->dev_ptr[6] = ext ? ix.ref2 : nullptr;
+    v->bytes[6] = ext ? ix.egeom.ref2_words * 8 : 0;
+    v->dev_ptr[7] = ext ? ix.coarse : nullptr;
+    v->bytes[7] = ext ? ix.egeom.coarse_words * 4 : 0;
     v->info = ix.info;
     return SHK_OK;
 }
@@ -556,7 +578,51 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
     out->probe_kernel_ms = p_ms;
     out->total_ms = t_ms;
     out->kernel_launches = s.launches;
+    out->n_extended = c.n_extended;
+    out->n_table_loads = c.n_table_loads;
     s.pending = false;
+    return SHK_OK;
+}
+
+// second ? ev_t1 : ev_t0 <- a point after everything enqueued so far on every slot stream (and the
+// build stream)
+static int timer_mark(shk_ctx *ctx, bool second)
+{
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->timer_stream) {
+        SHK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->timer_stream, cudaStreamNonBlocking));
+        SHK_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
+        SHK_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
+        SHK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    cudaEvent_t ev = second ? ctx->ev_t1 : ctx->ev_t0;
+    for (uint32_t i = 0; i <= ctx->n_slots; ++i) {
+        cudaStream_t st = i < ctx->n_slots ? ctx->slots[i].stream : ctx->build_stream;
+        SHK_CUDA(ctx, cudaEventRecord(ctx->ev_join, st));
+        SHK_CUDA(ctx, cudaStreamWaitEvent(ctx->timer_stream, ctx->ev_join, 0));
+    }
+    SHK_CUDA(ctx, cudaEventRecord(ev, ctx->timer_stream));
+    return SHK_OK;
+}
+
+int shk_device_timer_start(shk_ctx *ctx)
+{
+    if (!ctx) return SHK_E_ARG;
+    int rc = timer_mark(ctx, false);
+    if (rc) return rc;
+    // work enqueued from now on must not start before the mark
+    for (uint32_t i = 0; i < ctx->n_slots; ++i) SHK_CUDA(ctx, cudaStreamWaitEvent(ctx->slots[i].stream, ctx->ev_t0, 0));
+    return SHK_OK;
+}
+
+int shk_device_timer_stop(shk_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return SHK_E_ARG;
+    if (!ctx->ev_t0) return fail(ctx, SHK_E_STATE, "shk_device_timer_start was not called");
+    int rc = timer_mark(ctx, true);
+    if (rc) return rc;
+    SHK_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+    SHK_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
     return SHK_OK;
 }
 

@@ -209,7 +209,39 @@ struct FrontGeom {
     uint32_t off_mask;  // (1 << shift) - 1
     uint64_t n_buckets;
     uint64_t n_entries;  // buckets + overflow records
+    uint32_t stride;     // uint4s per entry: 1 = slots only, 2 = slots + anchors (extension)
+    uint32_t pad;
 };
+
+// ---------------------------------------------------------------------------------------------
+// Anchor-and-extend (exact; used when the front table is DRAM-sized).  Consecutive windows of a
+// read that follows the reference need no hashing or table access to be resolved:
+//   * every front-table entry becomes 32 bytes = one DRAM sector: its four slots + four anchors;
+//     the anchor of a slot is the END position e (in the concatenated reference) of the first
+//     reference window whose k-mer maps to the slot's filter position;
+//   * ref2 holds the reference 2 bits per base (base x at bits 62-2*(x&31) of word (x>>5)+1), so
+//     that the kernel can check that the read window IS that reference window (a read k-mer that
+//     merely collides with the filter bit fails this test and is never extended);
+//   * estream holds, per reference position t, a nibble {code:2, F0:1, F1:1} (position t at bits
+//     4*(t&15) of word (t>>4)+1; word 0 and the tail are zero).  With E[e] = "the windows ending at
+//     e-1 and e are both valid and their filter bits carry the same gene-id list":
+//         F0[t] = E[t]      forward strand: the window ending at t-1 extends to the one ending at t
+//         F1[t] = E[t+k]    reverse strand: the window starting at t+1 extends to the one starting at t
+//     An anchored thread therefore resolves its next window with one nibble: base equal (or
+//     complementary) and flag set => same k-mer as the next reference window => same filter bit
+//     => same list as the window before.  Anything else falls back to the table lookup.
+//   * coarse: one bit per 2^coarse_shift filter positions, set iff some position in the group is
+//     set; L2-sized, so most misses never touch the DRAM-sized table.
+// ---------------------------------------------------------------------------------------------
+struct ExtGeom {
+    uint64_t total;         // reference bases
+    uint64_t estream_words; // total/16 + 3
+    uint64_t ref2_words;    // total/32 + 3
+    uint64_t coarse_words;  // ((bf_bits >> coarse_shift) + 31)/32 + 1
+    uint32_t coarse_shift;
+    uint32_t enabled;
+};
+
 
 __device__ __forceinline__ uint32_t front_key(uint32_t off) { return off << kFrontKeyShift; }
 // key slot of offset `off` (either kind)?
@@ -218,6 +250,18 @@ __device__ __forceinline__ bool front_slot_matches(uint32_t slot, uint32_t key)
     return (slot ^ key) < kFrontLim;  // bit 31 clear and offset equal (EMPTY and chains have bit 31 set)
 }
 __device__ __forceinline__ bool front_is_chain(uint32_t slot) { return (slot & kFrontChainBit) && slot != kFrontEmpty; }
+
+// k-mer (MSB-first, like the rolling forward k-mer) of the reference window ending at e
+__device__ __forceinline__ uint64_t ref2_window(const uint64_t *ref2, uint32_t e, uint64_t kmask2, uint64_t pol)
+{
+    const uint32_t w = (e >> 5) + 1u, r = e & 31u;
+    uint64_t lo, hi;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(lo) : "l"(ref2 + w), "l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(hi) : "l"(ref2 + w - 1), "l"(pol));
+    uint64_t v = lo >> (62u - 2u * r);
+    if (r != 31u) v |= hi << (2u * r + 2u);
+    return v & kmask2;
+}
 
 __device__ __forceinline__ uint4 ld_front(const uint4 *p, uint64_t pol)
 {

@@ -434,18 +434,22 @@ struct FrontRecordsIn {
     __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return front_cnt_records(cnt[i]); }
 };
 
-__device__ __forceinline__ uint32_t *front_slot_ptr(uint32_t *front, uint64_t bucket, uint32_t total, uint32_t t,
-                                                    uint64_t n_buckets, uint32_t rec_base)
+// word index (in 32-bit words from the start of the table) of logical slot t of a bucket; an entry
+// is 4 words (slots), or 8 with anchors: slots in words 0-3, anchors in words 4-7
+__device__ __forceinline__ uint64_t front_slot_word(const FrontGeom &fg, uint64_t bucket, uint32_t total, uint32_t t,
+                                                    uint32_t rec_base)
 {
-    if (total <= 4 || t < 3) return front + bucket * 4 + t;
+    const uint64_t wpe = 4ull * fg.stride;
+    if (total <= 4 || t < 3) return bucket * wpe + t;
     const uint32_t u = t - 3;
-    return front + (n_buckets + rec_base + u / 3) * 4 + (u % 3);
+    return (fg.n_buckets + rec_base + u / 3) * wpe + (u % 3);
 }
 
 __global__ void __launch_bounds__(256)
 front_place_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, const uint64_t *__restrict__ entries,
                    const uint16_t *__restrict__ csr_ids, FrontGeom fg, const uint32_t *__restrict__ cnt,
-                   const uint32_t *__restrict__ rec_base, uint32_t *cur, uint32_t *front)
+                   const uint32_t *__restrict__ rec_base, uint32_t *cur, uint32_t *front,
+                   const uint32_t *__restrict__ anchor_of_rank)
 {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_sectors) return;
@@ -467,12 +471,15 @@ front_place_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, con
                 seen = prev;
             }
         }
+        const uint32_t anchor = fg.stride == 2 ? anchor_of_rank[r] : 0u;
         if (ln > kFrontInlineMax) {
-            *front_slot_ptr(front, bkt, total, t0, fg.n_buckets, rb) = key | kFrontLongFlag;
+            front[front_slot_word(fg, bkt, total, t0, rb)] = key | kFrontLongFlag;
         } else {
             for (uint32_t i = 0; i < ln; ++i) {
                 uint32_t g = i == 0 ? entry_id0(e) : (ln == 2 ? entry_lo(e) : (uint32_t)csr_ids[entry_lo(e) + i]);
-                *front_slot_ptr(front, bkt, total, t0 + i, fg.n_buckets, rb) = key | (ln >= 3 ? kFrontMultiFlag : 0u) | g;
+                const uint64_t w = front_slot_word(fg, bkt, total, t0 + i, rb);
+                front[w] = key | (ln >= 3 ? kFrontMultiFlag : 0u) | g;
+                if (fg.stride == 2) front[w + 4] = anchor;
             }
         }
     });
@@ -485,9 +492,90 @@ front_chain_kernel(FrontGeom fg, const uint32_t *__restrict__ cnt, const uint32_
     if (b >= fg.n_buckets) return;
     const uint32_t nrec = front_cnt_records(cnt[b]), rb = rec_base[b];
     if (nrec == 0) return;
-    front[b * 4 + 3] = kFrontChainBit | (uint32_t)(fg.n_buckets + rb);
+    const uint64_t wpe = 4ull * fg.stride;
+    front[b * wpe + 3] = kFrontChainBit | (uint32_t)(fg.n_buckets + rb);
     for (uint32_t i = 0; i + 1 < nrec; ++i)
-        front[(fg.n_buckets + rb + i) * 4 + 3] = kFrontChainBit | (uint32_t)(fg.n_buckets + rb + i + 1);
+        front[(fg.n_buckets + rb + i) * wpe + 3] = kFrontChainBit | (uint32_t)(fg.n_buckets + rb + i + 1);
+}
+
+// =============================================================================================
+// Anchor-and-extend structures (layouts in shk_device.cuh).  `win` is pass 2's per-position array:
+// win[e] = rank of the filter bit of the reference window ENDING at e, or kInvalidPos.
+// =============================================================================================
+__device__ __forceinline__ bool lists_equal(uint64_t e0, uint64_t e1, const uint16_t *__restrict__ csr_ids)
+{
+    const uint32_t n = entry_len(e0);
+    if (n != entry_len(e1) || entry_id0(e0) != entry_id0(e1)) return false;
+    if (n == 1) return true;
+    if (n == 2) return entry_lo(e0) == entry_lo(e1);
+    const uint16_t *a = csr_ids + entry_lo(e0), *b = csr_ids + entry_lo(e1);
+    for (uint32_t i = 1; i < n; ++i)
+        if (a[i] != b[i]) return false;
+    return true;
+}
+
+// E[e] (bit e of ebits) and the anchor of every set bit = the smallest window end that maps to it.
+__global__ void __launch_bounds__(256)
+ext_flags_kernel(const uint64_t *__restrict__ win, uint64_t total, const uint64_t *__restrict__ entries,
+                 const uint16_t *__restrict__ csr_ids, uint32_t *ebits, uint32_t *anchor_of_rank)
+{
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool E = false;
+    if (x < total) {
+        const uint64_t v = win[x];
+        if (v != kInvalidPos) {
+            const uint32_t r = (uint32_t)v;
+            atomicMin(&anchor_of_rank[r], (uint32_t)x);
+            if (x >= 1) {
+                const uint64_t v0 = win[x - 1];
+                if (v0 != kInvalidPos) E = (uint32_t)v0 == r || lists_equal(entries[(uint32_t)v0], entries[r], csr_ids);
+            }
+        }
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, E);
+    if ((threadIdx.x & 31) == 0 && x < total) ebits[x >> 5] = m;
+}
+
+__device__ __forceinline__ uint32_t ebit(const uint32_t *__restrict__ ebits, uint64_t e, uint64_t total)
+{
+    return e < total ? (ebits[e >> 5] >> (e & 31)) & 1u : 0u;
+}
+
+// one thread per 16 reference positions -> one word of estream; per 32 positions -> one word of ref2
+__global__ void __launch_bounds__(256)
+ext_pack_kernel(const uint8_t *__restrict__ bases, uint64_t total, int k, const uint32_t *__restrict__ ebits,
+                uint64_t *estream, uint64_t *ref2)
+{
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t0 = w * 16;
+    if (t0 >= total) return;
+    uint64_t word = 0;
+    uint32_t codes = 0;  // 16 bases, base i at bits 30-2i
+    for (uint32_t i = 0; i < 16; ++i) {
+        const uint64_t t = t0 + i;
+        if (t >= total) break;
+        const uint32_t ch = bases[t];
+        const uint32_t code = base_valid(ch) ? base_code(ch) : 0u;
+        const uint32_t nib = code | (ebit(ebits, t, total) << 2) | (ebit(ebits, t + (uint64_t)k, total) << 3);
+        word |= (uint64_t)nib << (4 * i);
+        codes |= code << (30 - 2 * i);
+    }
+    estream[w + 1] = word;
+    // two threads share a ref2 word: the even one owns the high half
+    uint32_t *r32 = reinterpret_cast<uint32_t *>(ref2 + (w >> 1) + 1);
+    r32[(w & 1) ? 0 : 1] = codes;  // little-endian: word index 1 = bits 63..32
+}
+
+// coarse miss filter: bit (p >> coarse_shift) for every set position p
+__global__ void __launch_bounds__(256)
+coarse_fill_kernel(const uint32_t *__restrict__ sectors, uint64_t n_sectors, uint32_t coarse_shift, uint32_t *coarse)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sectors) return;
+    for_each_set_bit(sectors, s, [&](uint64_t p, uint32_t) {
+        const uint64_t c = p >> coarse_shift;
+        atomicOr(&coarse[c >> 5], 1u << (c & 31));
+    });
 }
 
 // =============================================================================================
@@ -515,11 +603,47 @@ static void free_index_arrays(DeviceIndex &ix)
     if (ix.csr_off) cudaFree(ix.csr_off);
     if (ix.csr_ids) cudaFree(ix.csr_ids);
     if (ix.front) cudaFree(ix.front);
+    if (ix.estream) cudaFree(ix.estream);
+    if (ix.ref2) cudaFree(ix.ref2);
+    if (ix.coarse) cudaFree(ix.coarse);
     ix.front = nullptr;
     ix.entries = nullptr;
     ix.csr_off = nullptr;
     ix.csr_ids = nullptr;
+    ix.estream = nullptr;
+    ix.ref2 = nullptr;
+    ix.coarse = nullptr;
+    ix.egeom = ExtGeom{};
     ix.built = false;
+}
+
+// Sizes of the extension arrays for a reference of `total` bases (egeom.coarse_shift must be set).
+static void ext_geometry(DeviceIndex &ix, uint64_t total)
+{
+    ix.egeom.total = total;
+    ix.egeom.estream_words = total / 16 + 3;
+    ix.egeom.ref2_words = total / 32 + 3;
+    ix.egeom.coarse_words = (((ix.geom.bf_bits >> ix.egeom.coarse_shift) + 32) >> 5) + 1;
+}
+
+static int ext_alloc(shk_ctx *ctx)
+{
+    DeviceIndex &ix = ctx->index;
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.estream, ix.egeom.estream_words * 8));
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.ref2, ix.egeom.ref2_words * 8));
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.coarse, ix.egeom.coarse_words * 4));
+    return SHK_OK;
+}
+
+// Extension on/off: forced by shk_params.flags (or SHK_EXTEND=0/1, tuning), else on when the
+// plain front table (16 bytes per entry) would not stay in L2 next to the streamed reads.
+static bool decide_extend(const shk_ctx *ctx, uint64_t front_entries, uint64_t total)
+{
+    if (total == 0 || total >= 0xFFFFFF00ull) return false;
+    if (ctx->params.flags & SHK_F_EXTEND_ON) return true;
+    if (ctx->params.flags & SHK_F_EXTEND_OFF) return false;
+    if (const char *ev = getenv("SHK_EXTEND")) return atoi(ev) != 0;
+    return front_entries * 16 > (96ull << 20);
 }
 
 // Front table geometry: at most ~0.7 keys per 4-slot bucket (C2: 64 MB for 2.8 M keys; measured
@@ -541,31 +665,51 @@ static void front_geometry(DeviceIndex &ix)
     ix.fgeom.n_buckets = (ix.geom.bf_bits + (1ull << shift) - 1) >> shift;
 }
 
-// Allocates the table for a known geometry (info.front_shift / info.front_entries): used when the
-// index is adopted from another GPU.
+// Allocates the table (and the extension arrays) for a known geometry (info.front_shift /
+// front_entries / extend / ref_bases / coarse_shift): used when the index is adopted from another GPU.
 int index_alloc_front(shk_ctx *ctx)
 {
     DeviceIndex &ix = ctx->index;
     if (ix.front) cudaFree(ix.front);
+    if (ix.estream) cudaFree(ix.estream);
+    if (ix.ref2) cudaFree(ix.ref2);
+    if (ix.coarse) cudaFree(ix.coarse);
     ix.front = nullptr;
+    ix.estream = nullptr, ix.ref2 = nullptr, ix.coarse = nullptr;
+    ix.egeom = ExtGeom{};
     ix.fgeom.shift = ix.info.front_shift;
     ix.fgeom.off_mask = (1u << ix.fgeom.shift) - 1u;
     ix.fgeom.n_buckets = (ix.geom.bf_bits + (1ull << ix.fgeom.shift) - 1) >> ix.fgeom.shift;
     ix.fgeom.n_entries = ix.info.front_entries;
-    if (ix.fgeom.n_entries < ix.fgeom.n_buckets || ix.fgeom.shift < 5 || ix.fgeom.shift > kFrontMaxShift)
+    ix.fgeom.stride = ix.info.extend ? 2u : 1u;
+    if (ix.fgeom.n_entries < ix.fgeom.n_buckets || ix.fgeom.shift < 5 || ix.fgeom.shift > kFrontMaxShift ||
+        (ix.info.extend && ix.info.coarse_shift > ix.fgeom.shift))
         return fail(ctx, SHK_E_ARG, "inconsistent front table geometry in index info");
-    SHK_CUDA(ctx, cudaMalloc((void **)&ix.front, ix.fgeom.n_entries * 16));
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.front, ix.fgeom.n_entries * 16 * ix.fgeom.stride));
+    if (ix.info.extend) {
+        ix.egeom.enabled = 1;
+        ix.egeom.coarse_shift = ix.info.coarse_shift;
+        ext_geometry(ix, ix.info.ref_bases);
+        return ext_alloc(ctx);
+    }
     return SHK_OK;
 }
 
+// Per-build inputs of the extension structures (alive only during index_build_device).
+struct ExtBuildInputs {
+    const uint8_t *d_bases;
+    const uint64_t *d_win;  // per window end: rank of its filter bit, or kInvalidPos
+    uint64_t total;
+};
+
 static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries, const uint16_t *d_csr_ids,
-                       uint32_t *d_tiles, uint32_t *d_scalar)
+                       uint32_t *d_tiles, uint32_t *d_scalar, const ExtBuildInputs &xin)
 {
     DeviceIndex &ix = ctx->index;
     front_geometry(ix);
     const uint64_t nb = ix.fgeom.n_buckets;
     if (nb >= 0x7FFFFFFFull) return fail(ctx, SHK_E_LIMIT, "front table too large");
-    DevBuf<uint32_t> d_cnt, d_cur, d_rec;
+    DevBuf<uint32_t> d_cnt, d_cur, d_rec, d_anchor, d_ebits;
     SHK_CUDA(ctx, d_cnt.alloc(nb));
     SHK_CUDA(ctx, d_cur.alloc(nb));
     SHK_CUDA(ctx, d_rec.alloc(nb + 1));
@@ -583,14 +727,41 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
     }
     ix.fgeom.n_entries = nb + n_rec;
     if (ix.fgeom.n_entries >= 0x7FFFFFFFull) return fail(ctx, SHK_E_LIMIT, "front table too large");
+    const bool ext = ix.info.n_set_bits > 0 && decide_extend(ctx, ix.fgeom.n_entries, xin.total);
+    ix.fgeom.stride = ext ? 2u : 1u;
+    ix.egeom = ExtGeom{};
+    if (ext) {
+        // E flags + anchors, then the packed reference streams and the coarse filter
+        ix.egeom.enabled = 1;
+        uint32_t lg = 0;
+        while (lg < 63 && (1ull << lg) < ix.geom.bf_bits) ++lg;
+        ix.egeom.coarse_shift = std::min<uint32_t>(lg > 28 ? lg - 28 : 0, ix.fgeom.shift);
+        ext_geometry(ix, xin.total);
+        int rc = ext_alloc(ctx);
+        if (rc) return rc;
+        SHK_CUDA(ctx, d_anchor.alloc(ix.info.n_set_bits));
+        SHK_CUDA(ctx, d_ebits.alloc((xin.total + 31) / 32 + 1));
+        SHK_CUDA(ctx, cudaMemsetAsync(d_anchor.p, 0xFF, ix.info.n_set_bits * 4, st));
+        SHK_CUDA(ctx, cudaMemsetAsync(ix.estream, 0, ix.egeom.estream_words * 8, st));
+        SHK_CUDA(ctx, cudaMemsetAsync(ix.ref2, 0, ix.egeom.ref2_words * 8, st));
+        SHK_CUDA(ctx, cudaMemsetAsync(ix.coarse, 0, ix.egeom.coarse_words * 4, st));
+        ext_flags_kernel<<<(unsigned)((xin.total + 255) / 256), 256, 0, st>>>(xin.d_win, xin.total, d_entries, d_csr_ids,
+                                                                              d_ebits.p, d_anchor.p);
+        ext_pack_kernel<<<(unsigned)(((xin.total + 15) / 16 + 255) / 256), 256, 0, st>>>(
+            xin.d_bases, xin.total, (int)ctx->params.k, d_ebits.p, ix.estream, ix.ref2);
+        coarse_fill_kernel<<<blocks_s, 256, 0, st>>>(ix.sectors, ix.geom.n_sectors, ix.egeom.coarse_shift, ix.coarse);
+        ctx->launches += 3;
+        SHK_CUDA(ctx, cudaGetLastError());
+    }
     if (ix.front) cudaFree(ix.front);
     ix.front = nullptr;
-    SHK_CUDA(ctx, cudaMalloc((void **)&ix.front, ix.fgeom.n_entries * 16));
-    SHK_CUDA(ctx, cudaMemsetAsync(ix.front, 0xFF, ix.fgeom.n_entries * 16, st));
+    const uint64_t front_bytes = ix.fgeom.n_entries * 16 * ix.fgeom.stride;
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.front, front_bytes));
+    SHK_CUDA(ctx, cudaMemsetAsync(ix.front, 0xFF, front_bytes, st));
     if (ix.info.n_set_bits > 0) {
         uint32_t *f32 = reinterpret_cast<uint32_t *>(ix.front);
         front_place_kernel<<<blocks_s, 256, 0, st>>>(ix.sectors, ix.geom.n_sectors, d_entries, d_csr_ids, ix.fgeom,
-                                                     d_cnt.p, d_rec.p, d_cur.p, f32);
+                                                     d_cnt.p, d_rec.p, d_cur.p, f32, d_anchor.p);
         front_chain_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(ix.fgeom, d_cnt.p, d_rec.p, f32);
         ctx->launches += 2;
         SHK_CUDA(ctx, cudaGetLastError());
@@ -598,6 +769,9 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
     SHK_CUDA(ctx, cudaStreamSynchronize(st));  // the temporaries die with this scope
     ix.info.front_shift = ix.fgeom.shift;
     ix.info.front_entries = ix.fgeom.n_entries;
+    ix.info.extend = ext ? 1u : 0u;
+    ix.info.ref_bases = xin.total;
+    ix.info.coarse_shift = ix.egeom.coarse_shift;
     return SHK_OK;
 }
 
@@ -734,7 +908,8 @@ int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *r
         uint64_t need_tiles = (((ix.geom.bf_bits + 31) >> 5) + kScanTile - 1) / kScanTile + 2;
         DevBuf<uint32_t> d_tiles2;
         SHK_CUDA(ctx, d_tiles2.alloc(need_tiles));
-        rc = build_front(ctx, st, d_entries.p, d_csr_ids.p, d_tiles2.p, d_scalars.p + 5);
+        rc = build_front(ctx, st, d_entries.p, d_csr_ids.p, d_tiles2.p, d_scalars.p + 5,
+                         ExtBuildInputs{d_bases.p, d_win.p, total});
         if (rc) return rc;
     }
     SHK_CUDA(ctx, cudaEventRecord(e1, st));
@@ -753,7 +928,9 @@ int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *r
     ix.info.tot_ids = tot_ids;
     ix.info.n_windows = h_nwin;
     ix.info.bf_bits = ix.geom.bf_bits;
-    ix.info.device_bytes = sector_bytes + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2 + ix.fgeom.n_entries * 16;
+    ix.info.device_bytes = sector_bytes + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2 +
+                           ix.fgeom.n_entries * 16 * ix.fgeom.stride +
+                           (ix.egeom.enabled ? ix.egeom.estream_words * 8 + ix.egeom.ref2_words * 8 + ix.egeom.coarse_words * 4 : 0);
     ix.info.build_ms = ms;
     ix.built = true;
     return SHK_OK;

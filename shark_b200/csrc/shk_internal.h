@@ -20,8 +20,13 @@ struct DeviceIndex {
     uint64_t *entries = nullptr;  // one per set bit
     uint32_t *csr_off = nullptr;  // n_set + 1
     uint16_t *csr_ids = nullptr;  // tot_ids
-    uint4 *front = nullptr;       // front table, fgeom.n_buckets x 16 bytes
+    uint4 *front = nullptr;       // front table, fgeom.n_entries x 16 bytes (x 32 with anchors)
     FrontGeom fgeom{};
+    // anchor-and-extend structures (only when info.extend; layouts in shk_device.cuh)
+    uint64_t *estream = nullptr;  // 4 bits per reference position: base code + two extension flags
+    uint64_t *ref2 = nullptr;     // 2-bit packed reference, 32 bases per word (anchor verification)
+    uint32_t *coarse = nullptr;   // coarse miss filter: one bit per 2^coarse_shift filter positions
+    ExtGeom egeom{};
     shk_index_info info{};
     bool built = false;
 };
@@ -35,6 +40,8 @@ struct ChunkCounters {
     unsigned int n_slow;      // reads queued for the exact large-table path
     unsigned int pool_overflow;
     unsigned int pad;
+    unsigned long long n_extended;    // windows resolved by extension (no table access)
+    unsigned long long n_table_loads; // front-table entries loaded by the fast kernel (extension mode)
 };
 
 struct ReadKernelArgs {
@@ -51,6 +58,11 @@ struct ReadKernelArgs {
     FilterGeom geom;
     const uint4 *front;
     FrontGeom fgeom;
+    const uint64_t *estream;
+    const uint64_t *ref2;
+    const uint32_t *coarse;
+    uint32_t coarse_rel;        // fgeom.shift - coarse_shift: coarse index = bucket << rel | offset >> coarse_shift
+    uint32_t coarse_key_shift;  // kFrontKeyShift + coarse_shift (the offset sits in the key)
     uint32_t n_genes;
     // options
     int k;
@@ -124,6 +136,8 @@ struct shk_ctx {
     uint32_t n_slow_slabs = 0;
     std::atomic<uint64_t> launches{0};
     cudaStream_t build_stream = nullptr;
+    cudaStream_t timer_stream = nullptr;  // shk_device_timer_*: joins every slot stream
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_join = nullptr;
     uint64_t pol_first = 0, pol_last = 0;  // createpolicy evict_first / evict_last descriptors
     char err[512] = {0};
 };

@@ -230,9 +230,21 @@ struct Mru4 {
 // gene entering the table, lists of 3-4 ids, long lists, chained buckets) takes the generic
 // path, which for a typical read runs once or twice.
 // ---------------------------------------------------------------------------------------------
-template <bool HAS_QUAL, int MOD>
+//
+// EXT = anchor-and-extend (layouts and the exactness argument: shk_device.cuh).  Used when the front
+// table is DRAM-sized: then the kernel is bound by one random DRAM sector per probe, and most probes
+// can be answered without any table access.  A thread that has verified that its current window IS
+// the reference window ending at e ("anchored") resolves the next window from one nibble of the
+// reference stream: next base equal (complementary on the reverse strand) and the "same gene list as
+// the neighbouring reference window" flag set => the window's ids are the previous window's ids.
+// Windows that cannot be extended first ask the L2-resident coarse filter whether anything is set near
+// their filter position, and only then load their front-table entry (32 bytes = one sector: slots +
+// anchors).  Anchors are (re-)established from the last window of a text word.  All of this only
+// decides WHERE the ids of a window come from; the ids, and everything downstream, are unchanged.
+template <bool HAS_QUAL, int MOD, bool EXT>
 __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_reads_kernel(const ReadKernelArgs a)
 {
+    constexpr uint32_t S = EXT ? 2u : 1u;  // uint4s per front-table entry
     const int lane = threadIdx.x & 31;
     const uint32_t r = blockIdx.x * kFastThreads + threadIdx.x;
 #if SHK_POLICY_ARGS
@@ -240,12 +252,14 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
 #else
     const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
 #endif
+    // a DRAM-sized table must not displace the L2-resident streams: its sectors leave first
+    const uint64_t pol_front = EXT ? pol_first : pol_last;
     const uint32_t k = (uint32_t)a.k;
     const uint64_t kmask2 = (1ULL << (2 * k)) - 1ULL;
     const int rc_shift = 2 * (int)k - 2;
     const uint32_t fshift = a.fgeom.shift, fmask = a.fgeom.off_mask;
     const uint32_t mq4b = (0x01010101u * (uint32_t)(a.mq & 0xFF)) ^ kH4;
-    uint32_t count = 0, payload = 0, my_probes = 0, my_hits = 0;
+    uint32_t count = 0, payload = 0, my_probes = 0, my_hits = 0, my_ext = 0, my_loads = 0;
     bool slow = false;
 
     if (r < a.n_reads) {
@@ -258,6 +272,11 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
             tab.init();
             uint64_t fwd = 0, rc = 0;
             uint32_t run = 0, len = 0;
+            // extension state: next reference position to compare, strand, the anchored ids, and
+            // the cached word of the reference stream that holds position anc_t
+            uint32_t anc_t = 0, anc_dir = 0, prevA = kFrontEmpty, prevB = kFrontEmpty;
+            bool anc_on = false;
+            uint64_t ew = 0;
             const uint32_t head = off0 & 3u;
             const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.seq) + (off0 >> 2);
             const uint32_t *qualw = HAS_QUAL ? reinterpret_cast<const uint32_t *>(a.qual) + (off0 >> 2) : nullptr;
@@ -298,7 +317,7 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                 }
 #endif
                 uint32_t bucket[4], key[4];
-                bool wv[4];
+                bool wv[4], ex[4];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const bool valid = ((x >> (8 * b)) & 0xFFu) == 0u;
@@ -308,15 +327,47 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                     run = valid ? run + 1u : 0u;                   // build_kmer restart, 57-71
                     len += valid ? 1u : 0u;                        // ReadAnalyzer.hpp:46-49
                     wv[b] = run >= k;
+                    ex[b] = false;
+                    if (EXT) {
+                        // anchored: does the read go on like the reference (and keep its gene list)?
+                        const uint32_t nib = (uint32_t)(ew >> ((anc_t & 15u) * 4u));
+                        const uint32_t want = (uint32_t)code ^ (anc_dir * 3u);
+                        ex[b] = anc_on && valid && ((nib ^ want) & 3u) == 0u && ((nib >> (2u + anc_dir)) & 1u) != 0u;
+                        anc_on = ex[b];
+                        anc_t += 1u - 2u * anc_dir;
+                        if (ex[b] && ((anc_t + anc_dir) & 15u) == 0u)
+                            ew = ld_u64_hint(a.estream + ((anc_t + 16u) >> 4), pol_last);
+                    }
                     const uint64_t p = bit_index<MOD>(xxh64_u64(fwd < rc ? fwd : rc), a.geom);
                     bucket[b] = (uint32_t)(p >> fshift);
-                    key[b] = front_key((uint32_t)p & fmask);
+                    key[b] = ex[b] ? 0u : front_key((uint32_t)p & fmask);
                 }
                 uint4 q[4];
+                if (EXT) {
+                    uint32_t cw[4], cidx[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    q[b] = make_uint4(kFrontEmpty, kFrontEmpty, kFrontEmpty, kFrontEmpty);
-                    if (wv[b]) q[b] = ld_front(a.front + bucket[b], pol_last);
+                    for (int b = 0; b < 4; ++b) {  // coarse filter word of every window that needs a lookup
+                        cidx[b] = (bucket[b] << a.coarse_rel) | (key[b] >> a.coarse_key_shift);
+                        cw[b] = 0u;
+                        if (wv[b] && !ex[b]) cw[b] = ld_u32_hint(a.coarse + (cidx[b] >> 5), pol_last);
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        q[b] = make_uint4(kFrontEmpty, kFrontEmpty, kFrontEmpty, kFrontEmpty);
+                        if (ex[b]) {
+                            q[b] = make_uint4(prevA, prevB, kFrontEmpty, kFrontEmpty);  // key[b] == 0
+                            ++my_ext;
+                        } else if ((cw[b] >> (cidx[b] & 31u)) & 1u) {
+                            q[b] = ld_front(a.front + (uint64_t)bucket[b] * S, pol_front);
+                            ++my_loads;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        q[b] = make_uint4(kFrontEmpty, kFrontEmpty, kFrontEmpty, kFrontEmpty);
+                        if (wv[b]) q[b] = ld_front(a.front + bucket[b], pol_front);
+                    }
                 }
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
@@ -325,6 +376,7 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                     const uint32_t kb = key[b];
                     uint4 qq = q[b];
                     uint32_t A, B;
+                    uint32_t cur = bucket[b];  // entry that qq came from (anchors)
                     for (;;) {
                         #if SHK_SLOT_SUB  // slot - key: same test and same id (the key's low 18 bits are 0), but an add the FMA pipe can take
                         const uint32_t d0 = qq.x - kb, d1 = qq.y - kb, d2 = qq.z - kb, d3 = qq.w - kb;
@@ -337,8 +389,10 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                         // not in this record and the bucket goes on (chain pointer: bit 31 set, not
                         // EMPTY): look at the next record.  A 2-id list never straddles records.
                         if (A < kFrontLim || (int32_t)qq.w >= -1) break;
-                        qq = ld_front(a.front + (qq.w & 0x7FFFFFFFu), pol_last);
+                        cur = qq.w & 0x7FFFFFFFu;
+                        qq = ld_front(a.front + (uint64_t)cur * S, pol_front);
                     }
+                    const uint4 qfound = qq;  // the record A was found in (anchors)
                     const bool anyA = A < kFrontLim, anyB = B < kFrontLim;
                     const bool a0 = A == tab.g0, a1 = A == tab.g1, b0 = B == tab.g0, b1 = B == tab.g1;
                     my_hits += anyA ? 1u : 0u;
@@ -367,7 +421,29 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                                 }
                             }
                             if (!front_is_chain(qq.w)) break;
-                            qq = ld_front(a.front + (qq.w & 0x7FFFFFFFu), pol_last);
+                            qq = ld_front(a.front + (uint64_t)(qq.w & 0x7FFFFFFFu) * S, pol_front);
+                        }
+                    }
+                    if (EXT && b == 3) {
+                        // (re-)anchor on the word's last window: a looked-up hit with plain ids (list of
+                        // 1 or 2).  The slot's anchor names a reference window with the same filter bit;
+                        // the thread is anchored only if that window IS the read's window (either strand).
+                        if (!anc_on && wv[3] && !ex[3] && A < 0x10000u && (B < 0x10000u || B >= kFrontLim) && !tab.overflow) {
+                            const uint4 an = ld_front(a.front + (uint64_t)cur * S + 1, pol_front);
+                            const uint32_t sa = A + kb;  // the slot that produced A (slot - key == A)
+                            static_assert(SHK_SLOT_SUB, "the anchor lookup assumes slot - key");
+                            const uint32_t e = qfound.x == sa ? an.x : (qfound.y == sa ? an.y : (qfound.z == sa ? an.z : an.w));
+                            const uint64_t rk = ref2_window(a.ref2, e, kmask2, pol_last);
+                            if (rk == fwd) {
+                                anc_on = true, anc_dir = 0u, anc_t = e + 1u;
+                            } else if (rk == rc) {
+                                anc_on = true, anc_dir = 1u, anc_t = e - k;
+                            }
+                            if (anc_on) {
+                                prevA = A;
+                                prevB = B < 0x10000u ? B : kFrontEmpty;
+                                ew = ld_u64_hint(a.estream + ((anc_t + 16u) >> 4), pol_last);
+                            }
                         }
                     }
                 }
@@ -429,6 +505,13 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
         if (wa) atomicAdd(&a.tile_sums[blockIdx.x], wa);
         if (wp) atomicAdd(&a.counters->n_probes, (unsigned long long)wp);
         if (wh) atomicAdd(&a.counters->n_hits, (unsigned long long)wh);
+    }
+    if (EXT) {
+        const uint32_t we = __reduce_add_sync(kFull, my_ext), wl = __reduce_add_sync(kFull, my_loads);
+        if (lane == 0) {
+            if (we) atomicAdd(&a.counters->n_extended, (unsigned long long)we);
+            if (wl) atomicAdd(&a.counters->n_table_loads, (unsigned long long)wl);
+        }
     }
 }
 
@@ -595,7 +678,8 @@ scatter_assoc_kernel(const ReadKernelArgs a, uint64_t assoc_cap, const uint32_t 
 template <bool HAS_QUAL, int MOD>
 static void launch_typed(const ReadKernelArgs &a, cudaStream_t st, unsigned tiles, unsigned slow_blocks, cudaEvent_t ev_ka)
 {
-    analyze_reads_kernel<HAS_QUAL, MOD><<<tiles, kFastThreads, 0, st>>>(a);
+    if (a.estream) analyze_reads_kernel<HAS_QUAL, MOD, true><<<tiles, kFastThreads, 0, st>>>(a);
+    else analyze_reads_kernel<HAS_QUAL, MOD, false><<<tiles, kFastThreads, 0, st>>>(a);
     if (ev_ka) cudaEventRecord(ev_ka, st);
     analyze_slow_kernel<HAS_QUAL, MOD><<<slow_blocks, 128, 0, st>>>(a);
 }

@@ -15,11 +15,14 @@ from . import capi
 
 class Shark:
     def __init__(self, k=17, c=0.6, bf_bits=1 << 33, min_quality=0, single=False, device=0, n_slots=2,
-                 max_reads_per_chunk=1 << 20, max_bytes_per_chunk=0):
+                 max_reads_per_chunk=1 << 20, max_bytes_per_chunk=0, extend=None):
+        """extend: None = automatic (anchor-and-extend when the front table is DRAM-sized), True /
+        False = force it on / off (results are identical; tests run both)."""
         self.lib = capi.load()
+        flags = 0 if extend is None else (capi.F_EXTEND_ON if extend else capi.F_EXTEND_OFF)
         self.params = capi.Params(k=k, c=c, bf_bits=bf_bits, min_quality=min_quality, single=int(bool(single)),
                                   device=device, n_slots=n_slots, max_reads_per_chunk=max_reads_per_chunk,
-                                  max_bytes_per_chunk=max_bytes_per_chunk)
+                                  max_bytes_per_chunk=max_bytes_per_chunk, flags=flags)
         self.ctx = C.c_void_p()
         rc = self.lib.shk_create(C.byref(self.params), C.byref(self.ctx))
         if rc:
@@ -141,7 +144,17 @@ class Shark:
         return dict(read_idx=a[:, 0], gene_idx=a[:, 1], keep=keep, n_assoc=int(n), n_reads=res.n_reads,
                     n_slow_reads=res.n_slow_reads, n_probes=res.n_probes, n_hits=res.n_hits,
                     analyze_ms=res.analyze_ms, total_ms=res.total_ms, kernel_launches=res.kernel_launches,
-                    probe_kernel_ms=res.probe_kernel_ms)
+                    probe_kernel_ms=res.probe_kernel_ms, n_extended=res.n_extended, n_table_loads=res.n_table_loads)
+
+    def timer_start(self):
+        """Device stopwatch (CUDA events) over all slot streams of this context."""
+        self._check(self.lib.shk_device_timer_start(self.ctx))
+
+    def timer_stop(self):
+        """-> device milliseconds since timer_start, after everything enqueued in between has finished."""
+        ms = C.c_float()
+        self._check(self.lib.shk_device_timer_stop(self.ctx, C.byref(ms)))
+        return ms.value
 
     def kernel_launches(self):
         return int(self.lib.shk_kernel_launches(self.ctx))
@@ -190,7 +203,8 @@ class Shark:
             raise capi.SharkError(-1, "min_quality != 0 needs qualities")
         keep = np.zeros(n, np.uint8)
         out_r, out_g = [], []
-        stats = dict(n_probes=0, n_hits=0, analyze_ms=0.0, probe_kernel_ms=0.0, n_slow_reads=0, kernel_launches=0, chunks=0)
+        stats = dict(n_probes=0, n_hits=0, analyze_ms=0.0, probe_kernel_ms=0.0, n_slow_reads=0, kernel_launches=0, chunks=0,
+                     n_extended=0, n_table_loads=0)
         chunks = self.plan_chunks(off) if n else []
         pending = []
 
@@ -200,7 +214,8 @@ class Shark:
             keep[first:first + r["n_reads"]] = r["keep"]
             out_r.append(r["read_idx"].astype(np.uint64) + np.uint64(first))
             out_g.append(r["gene_idx"])
-            for key in ("n_probes", "n_hits", "analyze_ms", "probe_kernel_ms", "n_slow_reads", "kernel_launches"):
+            for key in ("n_probes", "n_hits", "analyze_ms", "probe_kernel_ms", "n_slow_reads", "kernel_launches",
+                        "n_extended", "n_table_loads"):
                 stats[key] += r[key]
             stats["chunks"] += 1
 

@@ -18,6 +18,13 @@ def _shark(**kw):
     return Shark(**kw)
 
 
+@pytest.fixture(params=[False, True], ids=["lookup", "extend"])
+def extend(request):
+    """Every classification test runs twice: table lookups only, and with anchor-and-extend forced
+    on (it is automatic only for DRAM-sized tables).  Results must be identical."""
+    return request.param
+
+
 def rnd_genes(rng, n, lo=200, hi=900):
     return [ACGT[rng.integers(0, 4, int(rng.integers(lo, hi)))].tobytes() for _ in range(n)]
 
@@ -161,7 +168,7 @@ CASES = [
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "k%d_c%g_b%d_q%d_%s%s_L%d" % (
     c["k"], c["c"], c["bf_bits"], c["q"], "s" if c["single"] else "m", "pe" if c["paired"] else "se", c["L"]))
-def test_analyze_parity(case):
+def test_analyze_parity(case, extend):
     rng = np.random.default_rng(case["k"] * 7 + case["L"])
     genes = quirky_reference(rng)
     bases, rec_off = po.concat_records(genes)
@@ -177,8 +184,9 @@ def test_analyze_parity(case):
     ref = po.Index(bases, rec_off, case["k"], case["bf_bits"])
     cnt0, ar0, ag0 = ref.analyze(seq, off, case["c"], qual=qual, min_quality=case["q"], single=case["single"])
     with _shark(k=case["k"], c=case["c"], bf_bits=case["bf_bits"], min_quality=case["q"], single=case["single"],
-                max_reads_per_chunk=1024) as sh:   # several chunks -> exercises both slots
-        sh.build_index(bases, rec_off)
+                max_reads_per_chunk=1024, extend=extend) as sh:   # several chunks -> exercises both slots
+        info = sh.build_index(bases, rec_off)
+        assert info.extend == int(extend)
         keep, ar, ag, stats = sh.analyze(seq, off, qual)
     assert np.array_equal(keep, (cnt0 > 0).astype(np.uint8))
     assert np.array_equal(ar, ar0)
@@ -186,9 +194,13 @@ def test_analyze_parity(case):
     assert stats["chunks"] >= 3
     if case["k"] >= 11:
         assert len(ar0) > 500  # the case is not vacuous
+        if extend:  # ... and neither is the extension: a good share of the hits came without a table access
+            assert stats["n_extended"] > 0.1 * stats["n_hits"], (stats["n_extended"], stats["n_hits"])
+    if not extend:
+        assert stats["n_extended"] == 0
 
 
-def test_exact_path_long_reads_and_wide_lists():
+def test_exact_path_long_reads_and_wide_lists(extend):
     """Reads longer than 1024 bytes, reads touching > 8 genes and lists longer than 8 all take
     the exact path and must agree with the oracle."""
     rng = np.random.default_rng(99)
@@ -207,7 +219,7 @@ def test_exact_path_long_reads_and_wide_lists():
         ref = po.Index(bases, rec_off, k, 1 << 28)
         cnt0, ar0, ag0 = ref.analyze(seq, off, c, single=single)
         with _shark(k=k, c=c, bf_bits=1 << 28, single=single, max_reads_per_chunk=256,
-                    max_bytes_per_chunk=1 << 20) as sh:
+                    max_bytes_per_chunk=1 << 20, extend=extend) as sh:
             sh.build_index(bases, rec_off)
             keep, ar, ag, stats = sh.analyze(seq, off)
         assert stats["n_slow_reads"] >= 300
@@ -220,13 +232,13 @@ def test_exact_path_long_reads_and_wide_lists():
 # ------------------------------------------------------------------------------------------
 # golden fixtures: the reference's own example + reference-binary goldens, end to end
 # ------------------------------------------------------------------------------------------
-def run_pipeline(ref_path, s1, s2, k=17, c=0.6, b=1, q=0, single=False, batch=50000):
+def run_pipeline(ref_path, s1, s2, k=17, c=0.6, b=1, q=0, single=False, batch=50000, extend=None):
     """Same host stages as oracle.shark_text.run_shark, but classification on the GPU."""
     legend, seqs = st.load_reference(ref_path)
     bases, rec_off = po.concat_records(seqs)
     pairs, bid = st.load_sample(s1, s2, batch)
     seq, qual, off = st.join_reads(pairs, q > 0)
-    with _shark(k=k, c=c, bf_bits=b << 33, min_quality=q, single=single, max_reads_per_chunk=4096) as sh:
+    with _shark(k=k, c=c, bf_bits=b << 33, min_quality=q, single=single, max_reads_per_chunk=4096, extend=extend) as sh:
         sh.build_index(bases, rec_off)
         keep, ar, ag, _ = sh.analyze(seq, off, qual)
     ssv, o1, o2 = [], [], []
@@ -245,11 +257,11 @@ def run_pipeline(ref_path, s1, s2, k=17, c=0.6, b=1, q=0, single=False, batch=50
 
 
 @pytest.mark.parametrize("case", sorted(example_cases()["cases"]))
-def test_example_goldens(tmp_path, case):
+def test_example_goldens(tmp_path, case, extend):
     info = example_cases()["cases"][case]
     f = stage_example(tmp_path)
     ssv, o1, o2 = run_pipeline(f["ENSG00000277117.fa"], f["sample_1.fq"], f["sample_2.fq"] if info["paired"] else None,
-                               **flags_to_kwargs(info["flags"]))
+                               extend=extend, **flags_to_kwargs(info["flags"]))
     assert ssv.count(b"\n") == info["ssv_lines"]
     assert md5(ssv) == info["ssv_md5"]
     assert md5(o1) == info["o1_md5"]
@@ -263,11 +275,11 @@ def test_example_goldens(tmp_path, case):
 
 
 @pytest.mark.parametrize("scenario,case", [(s, c) for s, cs in sorted(edge_cases().items()) for c in sorted(cs)])
-def test_edge_goldens(tmp_path, scenario, case):
+def test_edge_goldens(tmp_path, scenario, case, extend):
     info = edge_cases()[scenario][case]
     f = stage_edge(tmp_path, scenario)
     ssv, o1, o2 = run_pipeline(f["ref.fa"], f["r1.fq"], f.get("r2.fq") if info["paired"] else None,
-                               **flags_to_kwargs(info["flags"]))
+                               extend=extend, **flags_to_kwargs(info["flags"]))
     d = os.path.join(GOLDEN, "edge", scenario)
     assert ssv == gz_read(os.path.join(d, case + ".ssv.gz"))
     assert o1 == gz_read(os.path.join(d, case + ".o1.fq.gz"))
