@@ -39,6 +39,7 @@ static void free_slot(Slot &s)
     cudaFree(s.d_rec);
     cudaFree(s.d_pool);
     cudaFree(s.d_slow_list);
+    cudaFree(s.d_slow2_list);
     cudaFree(s.d_tile_sums);
     cudaFree(s.d_tile_base);
     cudaFree(s.d_counters);
@@ -85,6 +86,7 @@ static int alloc_slot(shk_ctx *ctx, Slot &s)
     s.pool_cap = (uint32_t)std::max<uint64_t>(R / 2, 4096);
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_pool, (uint64_t)s.pool_cap * 4));
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_slow_list, R * 4));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_slow2_list, R * 4));
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_tile_sums, (tiles + 1) * 4));
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_tile_base, (tiles + 1) * 4));
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_counters, sizeof(ChunkCounters)));
@@ -129,6 +131,7 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     a.pool = s.d_pool;
     a.pool_cap = s.pool_cap;
     a.slow_list = s.d_slow_list;
+    a.slow2_list = s.d_slow2_list;
     a.tile_sums = s.d_tile_sums;
     a.counters = s.d_counters;
     a.slow_table = s.d_slow_table;

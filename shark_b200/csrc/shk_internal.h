@@ -39,7 +39,7 @@ struct ChunkCounters {
     unsigned int pool_used;   // entries of the tie pool in use
     unsigned int n_slow;      // reads queued for the exact large-table path
     unsigned int pool_overflow;
-    unsigned int pad;
+    unsigned int n_slow2;     // reads the middle path handed on to the exact path
     unsigned long long n_extended;    // windows resolved by extension (no table access)
     unsigned long long n_table_loads; // front-table entries loaded by the fast kernel (extension mode)
 };
@@ -76,7 +76,8 @@ struct ReadKernelArgs {
     uint2 *rec;              // per read: x = association count, y = gene id (count==1) or pool offset
     uint32_t *pool;          // winners of reads with >= 2 associations, ascending gene id
     uint32_t pool_cap;
-    uint32_t *slow_list;     // read indices for the exact path
+    uint32_t *slow_list;     // read indices the fast path gave up on (middle path input)
+    uint32_t *slow2_list;    // read indices the middle path gave up on (exact path input)
     uint32_t *tile_sums;     // associations per tile of kReadsPerTile reads
     ChunkCounters *counters;
     // exact-path scratch
@@ -101,7 +102,7 @@ struct Slot {
     uint2 *d_rec = nullptr;
     uint32_t *d_pool = nullptr;
     uint32_t pool_cap = 0;
-    uint32_t *d_slow_list = nullptr;
+    uint32_t *d_slow_list = nullptr, *d_slow2_list = nullptr;
     uint32_t *d_tile_sums = nullptr, *d_tile_base = nullptr;
     ChunkCounters *d_counters = nullptr;
     shk_assoc *d_assoc = nullptr;

@@ -12,6 +12,7 @@
 #include "shk_internal.h"
 #include "shk_scan.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace shk {
@@ -241,8 +242,12 @@ struct Mru4 {
 // their filter position, and only then load their front-table entry (32 bytes = one sector: slots +
 // anchors).  Anchors are (re-)established from the last window of a text word.  All of this only
 // decides WHERE the ids of a window come from; the ids, and everything downstream, are unchanged.
+#ifndef SHK_EXT_MIN_BLOCKS
+#define SHK_EXT_MIN_BLOCKS 6
+#endif
 template <bool HAS_QUAL, int MOD, bool EXT>
-__global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_reads_kernel(const ReadKernelArgs a)
+__global__ void __launch_bounds__(kFastThreads, EXT ? SHK_EXT_MIN_BLOCKS : SHK_FAST_MIN_BLOCKS)
+analyze_reads_kernel(const ReadKernelArgs a)
 {
     constexpr uint32_t S = EXT ? 2u : 1u;  // uint4s per front-table entry
     const int lane = threadIdx.x & 31;
@@ -343,6 +348,7 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                     key[b] = ex[b] ? 0u : front_key((uint32_t)p & fmask);
                 }
                 uint4 q[4];
+                uint4 an3 = make_uint4(0u, 0u, 0u, 0u);  // anchors of the last window's bucket (same sector as its slots)
                 if (EXT) {
                     uint32_t cw[4], cidx[4];
 #pragma unroll
@@ -359,6 +365,7 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                             ++my_ext;
                         } else if ((cw[b] >> (cidx[b] & 31u)) & 1u) {
                             q[b] = ld_front(a.front + (uint64_t)bucket[b] * S, pol_front);
+                            if (b == 3 && !anc_on) an3 = ld_front(a.front + (uint64_t)bucket[b] * S + 1, pol_front);
                             ++my_loads;
                         }
                     }
@@ -429,20 +436,23 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
                         // 1 or 2).  The slot's anchor names a reference window with the same filter bit;
                         // the thread is anchored only if that window IS the read's window (either strand).
                         if (!anc_on && wv[3] && !ex[3] && A < 0x10000u && (B < 0x10000u || B >= kFrontLim) && !tab.overflow) {
-                            const uint4 an = ld_front(a.front + (uint64_t)cur * S + 1, pol_front);
+                            uint4 an = an3;  // loaded with the bucket; a chained record brings its own
+                            if (cur != bucket[3]) an = ld_front(a.front + (uint64_t)cur * S + 1, pol_front);
                             const uint32_t sa = A + kb;  // the slot that produced A (slot - key == A)
                             static_assert(SHK_SLOT_SUB, "the anchor lookup assumes slot - key");
                             const uint32_t e = qfound.x == sa ? an.x : (qfound.y == sa ? an.y : (qfound.z == sa ? an.z : an.w));
+                            // both candidate stream words travel with the two words of the reference window
+                            const uint64_t ew0 = ld_u64_hint(a.estream + ((e + 1u + 16u) >> 4), pol_last);
+                            const uint64_t ew1 = ld_u64_hint(a.estream + ((e - k + 16u) >> 4), pol_last);
                             const uint64_t rk = ref2_window(a.ref2, e, kmask2, pol_last);
                             if (rk == fwd) {
-                                anc_on = true, anc_dir = 0u, anc_t = e + 1u;
+                                anc_on = true, anc_dir = 0u, anc_t = e + 1u, ew = ew0;
                             } else if (rk == rc) {
-                                anc_on = true, anc_dir = 1u, anc_t = e - k;
+                                anc_on = true, anc_dir = 1u, anc_t = e - k, ew = ew1;
                             }
                             if (anc_on) {
                                 prevA = A;
                                 prevB = B < 0x10000u ? B : kFrontEmpty;
-                                ew = ld_u64_hint(a.estream + ((anc_t + 16u) >> 4), pol_last);
                             }
                         }
                     }
@@ -516,6 +526,164 @@ __global__ void __launch_bounds__(kFastThreads, SHK_FAST_MIN_BLOCKS) analyze_rea
 }
 
 // ---------------------------------------------------------------------------------------------
+// Middle path: one WARP per read the fast path gave up on (more than 4 genes, a list longer than 4
+// ids, a text longer than kMaxFastLen), with the per-gene state {gene, cov, hits, last} in a
+// 128-slot open-addressing table in shared memory (one per warp).  Windows are probed 32 at a time
+// through the reference-shaped structures (filter word -> sector rank -> entry -> CSR ids) and
+// applied in read order exactly as ReadAnalyzer.hpp:56-62,79-86 does; the lanes share the (distinct)
+// ids of one list.  Reads that touch more than kMidMaxGenes genes go on to the exact path below.
+// Thousands of such reads run concurrently (the table is 2 KB per warp), where the dense per-warp
+// tables of the exact path allow only a few hundred.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kMidSlots = 128, kMidMaxGenes = 95, kMidWarps = 4;
+
+template <bool HAS_QUAL, int MOD>
+__global__ void __launch_bounds__(kMidWarps * 32) analyze_mid_kernel(const ReadKernelArgs a)
+{
+    __shared__ uint4 tables[kMidWarps][kMidSlots];  // {gene (0xFFFFFFFF = free), cov, hits, last}
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_slow = a.counters->n_slow;
+    const uint32_t total_warps = gridDim.x * kMidWarps;
+    const uint64_t pol_first = a.pol_first, pol_last = a.pol_last;
+    const Sector *sector_base = reinterpret_cast<const Sector *>(a.sectors);
+    uint4 *tab = tables[warp];
+    uint32_t *keys = reinterpret_cast<uint32_t *>(tab);  // key of slot s = keys[4 * s]
+    const uint32_t k = (uint32_t)a.k;
+    unsigned long long probes = 0, hits_total = 0;
+
+    for (uint32_t i = blockIdx.x * kMidWarps + warp; i < n_slow; i += total_warps) {
+        const uint32_t r = a.slow_list[i];
+        const uint32_t off0 = a.off[r];
+        const uint32_t n = a.off[r + 1] - off0;
+        for (uint32_t s = lane; s < kMidSlots; s += 32) tab[s] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+        __syncwarp();
+        uint32_t n_used = 0;
+        bool overflow = false;
+        const int nch = (int)((n + 31u) >> 5);
+        ChunkState cs{0ULL, 0u};
+        uint32_t len = 0;
+        unsigned long long my_probes = 0, my_hits = 0;
+        for (int c = 0; c < nch && !overflow; ++c) {
+            uint32_t pw, bit;
+            const bool wv = chunk_window<HAS_QUAL, MOD>(a, off0, n, c, lane, cs, len, pw, bit);
+            const uint32_t w = wv ? ld_filter_word(a.sectors + pw, pol_first) : 0u;
+            const bool hit = wv && ((w >> bit) & 1u);
+            my_probes += __popc(__ballot_sync(kFull, wv));
+            uint32_t H = __ballot_sync(kFull, hit);
+            uint64_t e = 0;
+            if (hit) {
+                Sector sc = ld_sector(sector_base + (pw >> 3));
+                e = ld_u64_hint(a.entries + sector_rank(sc, pw & 7u, bit), pol_last);
+            }
+            my_hits += __popc(H);
+            while (H && !overflow) {  // windows in read order
+                const int src = __ffs(H) - 1;
+                H &= H - 1;
+                const uint64_t el = shfl64(e, src);
+                const uint32_t epos = (uint32_t)c * 32u + (uint32_t)src;
+                const uint32_t ln = entry_len(el);
+                for (uint32_t t0 = 0; t0 < ln; t0 += 32) {
+                    if (n_used > kMidMaxGenes) {  // at most 32 inserts follow: the table never fills up
+                        overflow = true;
+                        break;
+                    }
+                    const uint32_t t = t0 + (uint32_t)lane;
+                    bool inserted = false;
+                    if (t < ln) {
+                        uint32_t g;
+                        if (t == 0) g = entry_id0(el);
+                        else if (ln == 2) g = entry_lo(el);
+                        else g = a.csr_ids[entry_lo(el) + t];
+                        uint32_t s = (g * 0x9E3779B1u) >> 25;  // 7 bits
+                        for (;;) {
+                            uint32_t key = keys[4 * s];
+                            if (key == 0xFFFFFFFFu) {
+                                key = atomicCAS(&keys[4 * s], 0xFFFFFFFFu, g);
+                                if (key == 0xFFFFFFFFu) {
+                                    // fresh map entry: `pos - 0` >= k for every window, so cov = k
+                                    tab[s] = make_uint4(g, k, 1u, epos);
+                                    inserted = true;
+                                    break;
+                                }
+                            }
+                            if (key == g) {
+                                uint4 ent = tab[s];
+                                ent.y += min(k, epos - ent.w);
+                                ent.z += 1u;
+                                ent.w = epos;
+                                tab[s] = ent;
+                                break;
+                            }
+                            s = (s + 1u) & (kMidSlots - 1u);
+                        }
+                    }
+                    n_used += __popc(__ballot_sync(kFull, inserted));
+                    __syncwarp();
+                }
+            }
+        }
+        if (overflow) {  // more genes than the table holds: exact path
+            if (lane == 0) a.slow2_list[atomicAdd(&a.counters->n_slow2, 1u)] = r;
+            __syncwarp();
+            continue;
+        }
+        probes += my_probes;
+        hits_total += my_hits;
+        // argmax (ReadAnalyzer.hpp:90-102); each lane owns slots lane, lane+32, ...
+        uint32_t maxc = 0, maxh = 0;
+        for (uint32_t s = lane; s < kMidSlots; s += 32) {
+            const uint4 ent = tab[s];
+            if (ent.x != 0xFFFFFFFFu && (ent.y > maxc || (ent.y == maxc && ent.z > maxh))) {
+                maxc = ent.y;
+                maxh = ent.z;
+            }
+        }
+        const uint32_t wmaxc = __reduce_max_sync(kFull, maxc);
+        const uint32_t wmaxh = __reduce_max_sync(kFull, maxc == wmaxc ? maxh : 0u);
+        uint32_t count = 0, first_gene = 0xFFFFFFFFu;
+        for (uint32_t s = lane; s < kMidSlots; s += 32) {
+            const uint4 ent = tab[s];
+            if (ent.x != 0xFFFFFFFFu && ent.y == wmaxc && ent.z == wmaxh) {
+                ++count;
+                first_gene = min(first_gene, ent.x);
+            }
+        }
+        count = __reduce_add_sync(kFull, count);
+        first_gene = __reduce_min_sync(kFull, first_gene);
+        const bool pass = count > 0 && wmaxc > 0 && (double)wmaxc >= __dmul_rn(a.c, (double)len) &&
+                          (!a.single || count == 1);
+        if (!pass) count = 0;
+        uint32_t payload = first_gene;
+        if (count >= 2) {
+            payload = pool_reserve(a, count, lane);
+            if (payload != 0xFFFFFFFFu) {
+                // ascending gene order: a winner's place = number of winners with a smaller id
+                for (uint32_t s = lane; s < kMidSlots; s += 32) {
+                    const uint4 ent = tab[s];
+                    if (ent.x != 0xFFFFFFFFu && ent.y == wmaxc && ent.z == wmaxh) {
+                        uint32_t place = 0;
+                        for (uint32_t u = 0; u < kMidSlots; ++u) {
+                            const uint4 o = tab[u];
+                            place += (o.x < ent.x && o.y == wmaxc && o.z == wmaxh) ? 1u : 0u;  // free slots: x = 0xFFFFFFFF
+                        }
+                        a.pool[payload + place] = ent.x;
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            a.rec[r] = make_uint2(count, payload);
+            if (count) atomicAdd(&a.tile_sums[r / kReadsPerTile], count);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (probes) atomicAdd(&a.counters->n_probes, probes);
+        if (hits_total) atomicAdd(&a.counters->n_hits, hits_total);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Exact path: any number of genes, any read length.  One warp per read; a dense per-warp table
 // indexed by gene id (ids are 16-bit, small_vector.hpp:46) holds {stamp, cov, hits, last} and is
 // updated window by window in read order exactly as ReadAnalyzer.hpp:56-62,79-86 does, the
@@ -527,7 +695,7 @@ __global__ void __launch_bounds__(128) analyze_slow_kernel(const ReadKernelArgs 
     const int lane = threadIdx.x & 31;
     const uint32_t slab = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slab >= a.n_slow_slabs) return;
-    const uint32_t n_slow = a.counters->n_slow;
+    const uint32_t n_slow = a.counters->n_slow2;  // what the middle path could not hold
     if (slab >= n_slow) return;
     const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
     const Sector *sector_base = reinterpret_cast<const Sector *>(a.sectors);
@@ -537,7 +705,7 @@ __global__ void __launch_bounds__(128) analyze_slow_kernel(const ReadKernelArgs 
     unsigned long long probes = 0, hits_total = 0;
 
     for (uint32_t i = slab; i < n_slow; i += a.n_slow_slabs) {
-        const uint32_t r = a.slow_list[i];
+        const uint32_t r = a.slow2_list[i];
         const uint32_t off0 = a.off[r];
         const uint32_t n = a.off[r + 1] - off0;
         if (++stamp == 0) {  // stamp wrapped: clear the slab once
@@ -678,9 +846,12 @@ scatter_assoc_kernel(const ReadKernelArgs a, uint64_t assoc_cap, const uint32_t 
 template <bool HAS_QUAL, int MOD>
 static void launch_typed(const ReadKernelArgs &a, cudaStream_t st, unsigned tiles, unsigned slow_blocks, cudaEvent_t ev_ka)
 {
+    // middle path: a grid-stride loop over the slow list (its length is only known on the device)
+    const unsigned mid_blocks = std::min<unsigned>((tiles * kReadsPerTile + kMidWarps - 1) / kMidWarps, 148u * 8u);
     if (a.estream) analyze_reads_kernel<HAS_QUAL, MOD, true><<<tiles, kFastThreads, 0, st>>>(a);
     else analyze_reads_kernel<HAS_QUAL, MOD, false><<<tiles, kFastThreads, 0, st>>>(a);
     if (ev_ka) cudaEventRecord(ev_ka, st);
+    analyze_mid_kernel<HAS_QUAL, MOD><<<mid_blocks, kMidWarps * 32, 0, st>>>(a);
     analyze_slow_kernel<HAS_QUAL, MOD><<<slow_blocks, 128, 0, st>>>(a);
 }
 
@@ -703,8 +874,8 @@ int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_ca
         cudaMemcpyAsync(a.tile_base, a.tile_sums, (size_t)tiles * 4, cudaMemcpyDeviceToDevice, st);
         scan_tile_sums_kernel<<<1, 1024, 0, st>>>(a.tile_base, tiles, a.tile_base + tiles);
         scatter_assoc_kernel<<<tiles, kReadsPerTile, 0, st>>>(a, assoc_cap, a.tile_base + tiles);
-        launched = 4;
-        ctx->launches += 4;
+        launched = 5;
+        ctx->launches += 5;
     }
     else if (ev_ka) cudaEventRecord(ev_ka, st);
     if (ev_k1) cudaEventRecord(ev_k1, st);
