@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SHK_ABI_VERSION 2
+#define SHK_ABI_VERSION 3
 
 typedef enum shk_status {
     SHK_OK = 0,
@@ -153,6 +153,41 @@ int shk_index_finalize(shk_ctx *ctx);
 /* Same replication for two contexts of ONE process (the multi-GPU CLI): adopt + peer copies over
  * NVLink (cudaMemcpyPeerAsync) + finalize. */
 int shk_index_replicate(shk_ctx *src, shk_ctx *dst);
+
+/* ---- staged index build: the reference's own functor protocol ------------------------- */
+/* The same index, built through the calls the reference's main.cpp makes (seam 2),
+ * so that KmerBuilder / BloomfilterFiller / class BF can be replaced one for one
+ * (include/shark_b200_functors.hpp does exactly that).  A context starts in mode 0 with an empty
+ * filter; shk_index_build above is the one-call equivalent of the whole protocol and may be used
+ * instead, not in between. */
+
+/* KmerBuilder::operator() (KmerBuilder.hpp:40-72): XXH64 (not reduced modulo the filter size) of
+ * every canonical k-mer of the given records, records in order, windows in text order; k is
+ * shk_params.k.  hashes[cap] is a host buffer; *n_hashes is always set to the number of windows;
+ * SHK_E_CAPACITY when cap is too small (cap = total bases always suffices). */
+int shk_kmer_hashes(shk_ctx *ctx, const uint8_t *bases, const uint64_t *rec_offsets, uint32_t n_records,
+                    uint64_t *hashes, uint64_t cap, uint64_t *n_hashes);
+/* BloomfilterFiller::operator() -> BF::add_at (BloomfilterFiller.hpp:38-46, bloomfilter.h:57-59):
+ * `_bf[p % _size] = 1` for n positions (host pointer).  Mode 0 only (SHK_E_STATE otherwise; the
+ * reference would silently corrupt its rank structure). */
+int shk_bf_add_at(shk_ctx *ctx, const uint64_t *positions, uint64_t n);
+/* BF::switch_mode (bloomfilter.h:112-184): 0 -> 1 builds the rank directory, 1 -> 2 flattens the
+ * lists into the CSR (+ entries + front table) and makes the context ready for reads.  Any other
+ * transition returns SHK_E_STATE (the reference returns false).  n_set_bits (may be NULL)
+ * receives num_kmer (bloomfilter.h:122). */
+int shk_bf_switch_mode(shk_ctx *ctx, int new_mode, uint64_t *n_set_bits);
+/* BF::add_to_kmer (bloomfilter.h:61-75): hash % size of n canonical k-mers (host pointer), rank of
+ * each position, gene id `input_idx` appended to that list unless it is already its last
+ * element.  Mode 1 only.  input_idx must be in [0, 65535] (small_vector.hpp:46) and must not
+ * decrease from call to call (the reference's pass 2 counts up, main.cpp:159-187), which makes
+ * "append unless last" the same as "sorted unique". */
+int shk_bf_add_to_kmer(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t input_idx);
+/* Current mode (0, 1, 2); 2 also after shk_index_build / shk_index_finalize. */
+int shk_bf_mode(const shk_ctx *ctx);
+/* ReadAnalyzer's constructor arguments (ReadAnalyzer.hpp:34-35) arrive after BF's: k, c, -s and
+ * the masking threshold may be (re)set while no chunk is in flight.  k may only change before the
+ * first window is hashed. */
+int shk_set_options(shk_ctx *ctx, uint32_t k, double c, int32_t min_quality, int32_t single);
 
 /* ---- probe (test / roofline entry) ---------------------------------------------------- */
 

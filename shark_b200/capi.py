@@ -21,7 +21,8 @@ EXPORTED = [
     "shk_index_export", "shk_index_views_get", "shk_index_adopt", "shk_index_finalize", "shk_index_replicate", "shk_probe", "shk_probe_bench",
     "shk_random_sector_bench", "shk_alloc_pinned", "shk_free_pinned", "shk_reads_submit", "shk_reads_collect",
     "shk_reads_upload", "shk_reads_analyze_resident", "shk_kernel_launches", "shk_device_timer_start",
-    "shk_device_timer_stop",
+    "shk_device_timer_stop", "shk_kmer_hashes", "shk_bf_add_at", "shk_bf_switch_mode", "shk_bf_add_to_kmer", "shk_bf_mode",
+    "shk_set_options",
 ]
 
 
@@ -100,6 +101,12 @@ def load():
     L.shk_device_timer_start.argtypes = [vp]
     L.shk_device_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.shk_kernel_launches.argtypes = [vp]
+    L.shk_kmer_hashes.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.shk_bf_add_at.argtypes = [vp, vp, C.c_uint64]
+    L.shk_bf_switch_mode.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
+    L.shk_bf_add_to_kmer.argtypes = [vp, vp, C.c_uint64, C.c_int32]
+    L.shk_bf_mode.argtypes = [vp]
+    L.shk_set_options.argtypes = [vp, C.c_uint32, C.c_double, C.c_int32, C.c_int32]
     L.shk_kernel_launches.restype = C.c_uint64
     for name in EXPORTED:
         f = getattr(L, name)

@@ -311,6 +311,7 @@ void shk_destroy(shk_ctx *ctx)
         for (uint32_t i = 0; i < ctx->n_slots; ++i) free_slot(ctx->slots[i]);
         delete[] ctx->slots;
     }
+    staged_free(ctx);
     cudaFree(ctx->index.sectors);
     cudaFree(ctx->index.entries);
     cudaFree(ctx->index.csr_off);
@@ -333,8 +334,12 @@ int shk_index_build(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_
     if (!ctx || !rec_offsets) return fail(ctx, SHK_E_ARG, "NULL argument");
     if (rec_offsets[n_records] && !ref_bases) return fail(ctx, SHK_E_ARG, "ref_bases is NULL");
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    staged_free(ctx);
+    ctx->staged.mode = 0;
     int rc = index_build_device(ctx, ref_bases, rec_offsets, n_records);
     if (rc) return rc;
+    ctx->staged.mode = 2;
+    ctx->staged.hashed = true;
     rc = ensure_slow_table(ctx);
     if (rc) return rc;
     if (info) *info = ctx->index.info;
@@ -346,6 +351,57 @@ int shk_index_info_get(const shk_ctx *ctx, shk_index_info *info)
     if (!ctx || !info) return SHK_E_ARG;
     if (!ctx->index.built) return SHK_E_STATE;
     *info = ctx->index.info;
+    return SHK_OK;
+}
+
+// ---- staged build: the reference's functor protocol (shk_index.cu, "Staged build") ----------
+int shk_kmer_hashes(shk_ctx *ctx, const uint8_t *bases, const uint64_t *rec_offsets, uint32_t n_records, uint64_t *hashes,
+                    uint64_t cap, uint64_t *n_hashes)
+{
+    if (!ctx || !rec_offsets || !n_hashes) return fail(ctx, SHK_E_ARG, "NULL argument");
+    if (rec_offsets[n_records] && !bases) return fail(ctx, SHK_E_ARG, "bases is NULL");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return kmer_hashes_device(ctx, bases, rec_offsets, n_records, hashes, cap, n_hashes);
+}
+
+int shk_bf_add_at(shk_ctx *ctx, const uint64_t *positions, uint64_t n)
+{
+    if (!ctx || (n && !positions)) return fail(ctx, SHK_E_ARG, "NULL argument");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return staged_add_at(ctx, positions, n);
+}
+
+int shk_bf_switch_mode(shk_ctx *ctx, int new_mode, uint64_t *n_set_bits)
+{
+    if (!ctx) return fail(ctx, SHK_E_ARG, "NULL argument");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = staged_switch_mode(ctx, new_mode, n_set_bits);
+    if (rc) return rc;
+    return ctx->staged.mode == 2 ? ensure_slow_table(ctx) : SHK_OK;
+}
+
+int shk_bf_add_to_kmer(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t input_idx)
+{
+    if (!ctx || (n && !kmers)) return fail(ctx, SHK_E_ARG, "NULL argument");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return staged_add_to_kmer(ctx, kmers, n, input_idx);
+}
+
+int shk_bf_mode(const shk_ctx *ctx) { return ctx ? ctx->staged.mode : SHK_E_ARG; }
+
+int shk_set_options(shk_ctx *ctx, uint32_t k, double c, int32_t min_quality, int32_t single)
+{
+    if (!ctx) return fail(ctx, SHK_E_ARG, "NULL argument");
+    if (k == 0 || k > 31) return fail(ctx, SHK_E_ARG, "k must be in the range [1, 31]");
+    if (!(c >= 0.0 && c <= 1.0)) return fail(ctx, SHK_E_ARG, "c must be in the range [0, 1]");
+    if (k != ctx->params.k && ctx->staged.hashed)
+        return fail(ctx, SHK_E_STATE, "k cannot change from %u to %u once k-mers have been hashed", ctx->params.k, k);
+    for (uint32_t i = 0; i < ctx->n_slots; ++i)
+        if (ctx->slots[i].pending) return fail(ctx, SHK_E_STATE, "a chunk is in flight on slot %u", i);
+    ctx->params.k = k;
+    ctx->params.c = c;
+    ctx->params.min_quality = min_quality;
+    ctx->params.single = single;
     return SHK_OK;
 }
 
@@ -409,6 +465,8 @@ int shk_index_finalize(shk_ctx *ctx)
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
     SHK_CUDA(ctx, cudaDeviceSynchronize());
     ctx->index.built = true;
+    ctx->staged.mode = 2;
+    ctx->staged.hashed = true;
     return ensure_slow_table(ctx);
 }
 

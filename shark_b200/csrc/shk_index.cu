@@ -775,6 +775,39 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
     return SHK_OK;
 }
 
+// Second half of the list build, shared by the one-call build and the staged protocol: lists that
+// sit unordered (and repeated) at tmp_ids[tmp_off[r] ..] become the sorted unique CSR + entries.
+// d_len (n_set + 1 words) receives the final lengths, d_long / d_n_long queue the long lists.
+static int finish_lists(shk_ctx *ctx, cudaStream_t st, uint32_t n_set, const uint32_t *d_tmp_off, uint16_t *d_tmp_ids,
+                        uint32_t *d_len, uint32_t *d_long, uint32_t *d_n_long, uint32_t *d_tiles, DevBuf<uint32_t> &d_csr_off,
+                        DevBuf<uint16_t> &d_csr_ids, DevBuf<uint64_t> &d_entries, uint64_t &tot_ids)
+{
+    const unsigned blocks_r = (unsigned)(((uint64_t)n_set + 255) / 256);
+    SHK_CUDA(ctx, cudaMemsetAsync(d_n_long, 0, 4, st));
+    sort_unique_kernel<<<blocks_r, 256, 0, st>>>(d_tmp_off, n_set, d_tmp_ids, d_len, d_long, d_n_long);
+    ctx->launches += 1;
+    uint32_t h_long = 0;
+    SHK_CUDA(ctx, cudaMemcpyAsync(&h_long, d_n_long, 4, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_long > 0) {
+        sort_unique_long_kernel<<<h_long, 256, 0, st>>>(d_tmp_off, d_long, d_tmp_ids, d_len);
+        ctx->launches += 1;
+    }
+    int rc = exclusive_scan(ctx, st, U32In{d_len}, U32Out{d_csr_off.p}, (uint64_t)n_set, d_tiles, d_csr_off.p + n_set);
+    if (rc) return rc;
+    uint32_t h_tot = 0;
+    SHK_CUDA(ctx, cudaMemcpyAsync(&h_tot, d_csr_off.p + n_set, 4, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    tot_ids = h_tot;
+    if (tot_ids >= 0x7FFFFFFFull)
+        return fail(ctx, SHK_E_LIMIT, "total id count overflows the reference's int (bloomfilter.h:130)");
+    SHK_CUDA(ctx, d_csr_ids.alloc(tot_ids));
+    finalize_lists_kernel<<<blocks_r, 256, 0, st>>>(d_tmp_off, d_tmp_ids, d_csr_off.p, n_set, d_csr_ids.p, d_entries.p);
+    ctx->launches += 1;
+    SHK_CUDA(ctx, cudaGetLastError());
+    return SHK_OK;
+}
+
 template <int MOD>
 static void launch_enum(shk_ctx *ctx, cudaStream_t st, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec,
                         uint64_t total, uint64_t *win_pos, uint32_t *has_window, unsigned long long *n_windows)
@@ -869,35 +902,16 @@ int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *r
     uint64_t tot_ids = 0;
     if (n_set > 0) {
         unsigned blocks_x = (unsigned)((total + 255) / 256);
-        unsigned blocks_r = (unsigned)(((uint64_t)n_set + 255) / 256);
         rank_count_kernel<<<blocks_x, 256, 0, st>>>(d_win.p, total, ix.sectors, d_cnt.p);
         ctx->launches += 1;
         rc = exclusive_scan(ctx, st, U32In{d_cnt.p}, U32Out{d_tmp_off.p}, (uint64_t)n_set, d_tiles.p, d_tmp_off.p + n_set);
         if (rc) return rc;
         fill_kernel<<<blocks_x, 256, 0, st>>>(d_win.p, total, d_rec_off.p, n_rec, d_nidx.p, d_tmp_off.p, d_fill.p,
                                               d_tmp_ids.p);
-        // d_fill is reused as the final length of each list
-        sort_unique_kernel<<<blocks_r, 256, 0, st>>>(d_tmp_off.p, n_set, d_tmp_ids.p, d_fill.p, d_long.p, d_scalars.p + 4);
-        ctx->launches += 2;
-        SHK_CUDA(ctx, cudaMemcpyAsync(h_scalars, d_scalars.p, sizeof h_scalars, cudaMemcpyDeviceToHost, st));
-        SHK_CUDA(ctx, cudaStreamSynchronize(st));
-        if (h_scalars[4] > 0) {
-            sort_unique_long_kernel<<<h_scalars[4], 256, 0, st>>>(d_tmp_off.p, d_long.p, d_tmp_ids.p, d_fill.p);
-            ctx->launches += 1;
-        }
-        rc = exclusive_scan(ctx, st, U32In{d_fill.p}, U32Out{d_csr_off.p}, (uint64_t)n_set, d_tiles.p, d_csr_off.p + n_set);
-        if (rc) return rc;
-        uint32_t h_tot = 0;
-        SHK_CUDA(ctx, cudaMemcpyAsync(&h_tot, d_csr_off.p + n_set, 4, cudaMemcpyDeviceToHost, st));
-        SHK_CUDA(ctx, cudaStreamSynchronize(st));
-        tot_ids = h_tot;
-        if (tot_ids >= 0x7FFFFFFFull)
-            return fail(ctx, SHK_E_LIMIT, "total id count overflows the reference's int (bloomfilter.h:130)");
-        SHK_CUDA(ctx, d_csr_ids.alloc(tot_ids));
-        finalize_lists_kernel<<<blocks_r, 256, 0, st>>>(d_tmp_off.p, d_tmp_ids.p, d_csr_off.p, n_set, d_csr_ids.p,
-                                                        d_entries.p);
         ctx->launches += 1;
-        SHK_CUDA(ctx, cudaGetLastError());
+        rc = finish_lists(ctx, st, n_set, d_tmp_off.p, d_tmp_ids.p, d_fill.p, d_long.p, d_scalars.p + 4, d_tiles.p, d_csr_off,
+                          d_csr_ids, d_entries, tot_ids);
+        if (rc) return rc;
     } else {
         SHK_CUDA(ctx, cudaMemsetAsync(d_csr_off.p, 0, 4, st));
         SHK_CUDA(ctx, d_csr_ids.alloc(1));
@@ -1151,6 +1165,330 @@ int random_sector_bench_device(shk_ctx *ctx, uint64_t n_loads, uint64_t span_byt
     cudaEventDestroy(e1);
     if (ms) *ms = best;
     return SHK_OK;
+}
+
+// =============================================================================================
+// Staged build = the reference's own functor protocol (seam 2), for callers that keep
+// the reference's main.cpp and replace KmerBuilder / BloomfilterFiller / class BF one for one
+// (include/shark_b200_functors.hpp).  Same device structures, same results as index_build_device.
+// =============================================================================================
+
+// KmerBuilder::operator() (KmerBuilder.hpp:40-72): the hash of every valid window, by window end.
+// Same walk as K1 (8 positions per thread, rolling forward k-mer), but the full 64-bit hash is kept
+// and no bit is set.
+__global__ void __launch_bounds__(256)
+enum_hashes_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ rec_off, uint32_t n_rec, uint64_t total,
+                   int k, uint64_t *win_hash, uint32_t *win_valid)
+{
+    const uint64_t x0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kPosPerThread;
+    if (x0 >= total) return;
+    const uint64_t xend = min(x0 + (uint64_t)kPosPerThread, total);
+    uint64_t s = x0 >= (uint64_t)(k - 1) ? x0 - (k - 1) : 0;
+    uint32_t r = record_of(rec_off, n_rec, s);
+    uint64_t next_b = rec_off[r + 1];
+    const uint64_t kmask = (1ULL << (2 * k)) - 1;
+    uint64_t fwd = 0;
+    int run = 0;
+    for (uint64_t pos = s; pos < xend; ++pos) {
+        while (pos >= next_b) {
+            ++r;
+            next_b = rec_off[r + 1];
+            run = 0;
+        }
+        const uint32_t ch = bases[pos];
+        if (base_valid(ch)) {
+            fwd = ((fwd << 2) | base_code(ch)) & kmask;
+            ++run;
+        } else {
+            run = 0;
+        }
+        if (pos >= x0) {
+            const bool v = run >= k;
+            win_valid[pos] = v ? 1u : 0u;
+            win_hash[pos] = v ? xxh64_u64(canonical(fwd, k)) : 0ULL;  // _get_hash(min(kmer, rckmer))
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+compact_hashes_kernel(const uint64_t *__restrict__ win_hash, const uint32_t *__restrict__ win_valid,
+                      const uint32_t *__restrict__ win_off, uint64_t total, uint64_t *out)
+{
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < total && win_valid[x]) out[win_off[x]] = win_hash[x];
+}
+
+int kmer_hashes_device(shk_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint64_t *hashes,
+                       uint64_t cap, uint64_t *n_hashes)
+{
+    cudaStream_t st = ctx->build_stream;
+    const uint64_t total = rec_off[n_rec];
+    *n_hashes = 0;
+    if (total >= (1ULL << 32)) return fail(ctx, SHK_E_LIMIT, "more than 4 Gbases in one call");
+    for (uint32_t i = 0; i < n_rec; ++i)
+        if (rec_off[i + 1] < rec_off[i]) return fail(ctx, SHK_E_ARG, "rec_offsets must be non-decreasing");
+    if (total == 0) return SHK_OK;
+    DevBuf<uint8_t> d_bases;
+    DevBuf<uint64_t> d_rec_off, d_hash, d_out;
+    DevBuf<uint32_t> d_valid, d_off, d_tiles;
+    SHK_CUDA(ctx, d_bases.alloc(total));
+    SHK_CUDA(ctx, d_rec_off.alloc((uint64_t)n_rec + 1));
+    SHK_CUDA(ctx, d_hash.alloc(total));
+    SHK_CUDA(ctx, d_valid.alloc(total));
+    SHK_CUDA(ctx, d_off.alloc(total + 1));
+    SHK_CUDA(ctx, d_tiles.alloc(total / kScanTile + 2));
+    SHK_CUDA(ctx, cudaMemcpyAsync(d_bases.p, bases, total, cudaMemcpyHostToDevice, st));
+    SHK_CUDA(ctx, cudaMemcpyAsync(d_rec_off.p, rec_off, ((uint64_t)n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    const uint64_t threads = (total + kPosPerThread - 1) / kPosPerThread;
+    enum_hashes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_bases.p, d_rec_off.p, n_rec, total,
+                                                                          (int)ctx->params.k, d_hash.p, d_valid.p);
+    ctx->launches += 1;
+    int rc = exclusive_scan(ctx, st, U32In{d_valid.p}, U32Out{d_off.p}, total, d_tiles.p, d_off.p + total);
+    if (rc) return rc;
+    uint32_t h_n = 0;
+    SHK_CUDA(ctx, cudaMemcpyAsync(&h_n, d_off.p + total, 4, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    *n_hashes = h_n;
+    ctx->staged.hashed = true;
+    if (h_n == 0) return SHK_OK;
+    if (h_n > cap || !hashes) return fail(ctx, SHK_E_CAPACITY, "%u hashes do not fit into a buffer of %llu", h_n,
+                                          (unsigned long long)cap);
+    SHK_CUDA(ctx, d_out.alloc(h_n));
+    compact_hashes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_hash.p, d_valid.p, d_off.p, total, d_out.p);
+    ctx->launches += 1;
+    SHK_CUDA(ctx, cudaGetLastError());
+    SHK_CUDA(ctx, cudaMemcpyAsync(hashes, d_out.p, (uint64_t)h_n * 8, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    return SHK_OK;
+}
+
+// BF::add_at (bloomfilter.h:57-59): `_bf[p % _size] = 1`
+template <int MOD>
+__global__ void __launch_bounds__(256)
+add_at_kernel(const uint64_t *__restrict__ positions, uint64_t n, FilterGeom g, uint32_t *sectors)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t p = bit_index<MOD>(positions[i], g);
+    atomicOr(&sectors[phys_word(p)], 1u << (p & 31));
+}
+
+int staged_add_at(shk_ctx *ctx, const uint64_t *positions, uint64_t n)
+{
+    if (ctx->staged.mode != 0) return fail(ctx, SHK_E_STATE, "add_at is only possible in mode 0 (mode is %d)", ctx->staged.mode);
+    if (n == 0) return SHK_OK;
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    DevBuf<uint64_t> d_pos;
+    SHK_CUDA(ctx, d_pos.alloc(n));
+    SHK_CUDA(ctx, cudaMemcpyAsync(d_pos.p, positions, n * 8, cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    switch (ix.geom.mod_kind) {
+    case MOD_POW2: add_at_kernel<MOD_POW2><<<blocks, 256, 0, st>>>(d_pos.p, n, ix.geom, ix.sectors); break;
+    case MOD_B33: add_at_kernel<MOD_B33><<<blocks, 256, 0, st>>>(d_pos.p, n, ix.geom, ix.sectors); break;
+    default: add_at_kernel<MOD_GENERIC><<<blocks, 256, 0, st>>>(d_pos.p, n, ix.geom, ix.sectors); break;
+    }
+    ctx->launches += 1;
+    SHK_CUDA(ctx, cudaGetLastError());
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));  // positions may be freed by the caller
+    return SHK_OK;
+}
+
+// BF::add_to_kmer (bloomfilter.h:64-70): kmer -> hash % size -> `_brank(bf_idx)` = set bits strictly
+// below the position (whether or not the position itself is set, exactly like the reference).
+template <int MOD>
+__global__ void __launch_bounds__(256)
+kmer_rank_kernel(const uint64_t *__restrict__ kmers, uint64_t n, FilterGeom g, const uint32_t *__restrict__ sectors,
+                 uint32_t n_set, uint16_t gene, uint32_t *pair_rank, uint16_t *pair_gene, uint32_t *cnt)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t p = bit_index<MOD>(xxh64_u64(kmers[i]), g);
+    const uint64_t q = p >> 5;
+    const uint64_t sec = q / kWordsPerSector;
+    const uint32_t slot = (uint32_t)(q - sec * kWordsPerSector);
+    const uint4 *sp = reinterpret_cast<const uint4 *>(sectors + sec * 8);
+    const uint4 a = sp[0], b = sp[1];
+    Sector s;
+    s.w[0] = a.x, s.w[1] = a.y, s.w[2] = a.z, s.w[3] = a.w, s.w[4] = b.x, s.w[5] = b.y, s.w[6] = b.z, s.w[7] = b.w;
+    uint32_t r = sector_rank(s, slot, (uint32_t)(p & 31));
+    if (r >= n_set) r = 0xFFFFFFFFu;  // `_set_index[num_kmer]`: out of bounds in the reference, dropped here
+    else atomicAdd(&cnt[r], 1u);
+    pair_rank[i] = r;
+    pair_gene[i] = gene;
+}
+
+__global__ void __launch_bounds__(256)
+pairs_fill_kernel(const uint32_t *__restrict__ pair_rank, const uint16_t *__restrict__ pair_gene, uint64_t n,
+                  const uint32_t *__restrict__ tmp_off, uint32_t *fill, uint16_t *tmp_ids)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = pair_rank[i];
+    if (r == 0xFFFFFFFFu) return;
+    tmp_ids[tmp_off[r] + atomicAdd(&fill[r], 1u)] = pair_gene[i];
+}
+
+void staged_free(shk_ctx *ctx)
+{
+    StagedBuild &sb = ctx->staged;
+    if (sb.cnt) cudaFree(sb.cnt);
+    if (sb.pair_rank) cudaFree(sb.pair_rank);
+    if (sb.pair_gene) cudaFree(sb.pair_gene);
+    sb.cnt = nullptr, sb.pair_rank = nullptr, sb.pair_gene = nullptr;
+    sb.n_pairs = sb.cap = 0;
+}
+
+int staged_add_to_kmer(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t input_idx)
+{
+    StagedBuild &sb = ctx->staged;
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    if (sb.mode != 1) return SHK_OK;  // `if (_mode != 1) return;` (bloomfilter.h:62-63)
+    if (input_idx < 0 || input_idx > 65535)
+        return fail(ctx, SHK_E_LIMIT, "gene index %d: the reference stores gene ids in 16 bits (small_vector.hpp:46)", input_idx);
+    if (input_idx < sb.last_idx)
+        return fail(ctx, SHK_E_STATE, "add_to_kmer: input_idx %d after %d; indices must not decrease (main.cpp:159-187)",
+                    input_idx, sb.last_idx);
+    sb.last_idx = input_idx;
+    if (n == 0) return SHK_OK;
+    if (sb.n_pairs + n >= 0xFFFFFFFFull) return fail(ctx, SHK_E_LIMIT, "too many k-mer occurrences");
+    if (sb.n_pairs + n > sb.cap) {  // grow geometrically, keep what is there
+        uint64_t cap = std::max<uint64_t>(sb.cap * 2, std::max<uint64_t>(sb.n_pairs + n, 1u << 20));
+        uint32_t *nr = nullptr;
+        uint16_t *ng = nullptr;
+        SHK_CUDA(ctx, cudaMalloc((void **)&nr, cap * 4));
+        cudaError_t e = cudaMalloc((void **)&ng, cap * 2);
+        if (e != cudaSuccess) {
+            cudaFree(nr);
+            SHK_CUDA(ctx, e);
+        }
+        if (sb.n_pairs) {
+            cudaMemcpyAsync(nr, sb.pair_rank, sb.n_pairs * 4, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(ng, sb.pair_gene, sb.n_pairs * 2, cudaMemcpyDeviceToDevice, st);
+            cudaStreamSynchronize(st);
+        }
+        if (sb.pair_rank) cudaFree(sb.pair_rank);
+        if (sb.pair_gene) cudaFree(sb.pair_gene);
+        sb.pair_rank = nr, sb.pair_gene = ng, sb.cap = cap;
+    }
+    DevBuf<uint64_t> d_k;
+    SHK_CUDA(ctx, d_k.alloc(n));
+    SHK_CUDA(ctx, cudaMemcpyAsync(d_k.p, kmers, n * 8, cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    uint32_t *pr = sb.pair_rank + sb.n_pairs;
+    uint16_t *pg = sb.pair_gene + sb.n_pairs;
+    const uint16_t gene = (uint16_t)input_idx;
+    switch (ix.geom.mod_kind) {
+    case MOD_POW2: kmer_rank_kernel<MOD_POW2><<<blocks, 256, 0, st>>>(d_k.p, n, ix.geom, ix.sectors, sb.n_set, gene, pr, pg, sb.cnt); break;
+    case MOD_B33: kmer_rank_kernel<MOD_B33><<<blocks, 256, 0, st>>>(d_k.p, n, ix.geom, ix.sectors, sb.n_set, gene, pr, pg, sb.cnt); break;
+    default: kmer_rank_kernel<MOD_GENERIC><<<blocks, 256, 0, st>>>(d_k.p, n, ix.geom, ix.sectors, sb.n_set, gene, pr, pg, sb.cnt); break;
+    }
+    ctx->launches += 1;
+    SHK_CUDA(ctx, cudaGetLastError());
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    sb.n_pairs += n;
+    return SHK_OK;
+}
+
+int staged_switch_mode(shk_ctx *ctx, int new_mode, uint64_t *n_set_bits)
+{
+    StagedBuild &sb = ctx->staged;
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    if (sb.mode == 0 && new_mode == 1) {
+        // rank directory + num_kmer (bloomfilter.h:121-122); `_set_index.resize(num_kmer)` = cnt
+        DevBuf<uint32_t> d_tiles, d_total;
+        SHK_CUDA(ctx, d_tiles.alloc(ix.geom.n_sectors / kScanTile + 2));
+        SHK_CUDA(ctx, d_total.alloc(1));
+        int rc = exclusive_scan(ctx, st, SectorPopIn{ix.sectors}, SectorRankOut{ix.sectors}, ix.geom.n_sectors, d_tiles.p,
+                                d_total.p);
+        if (rc) return rc;
+        uint32_t n_set = 0;
+        SHK_CUDA(ctx, cudaMemcpyAsync(&n_set, d_total.p, 4, cudaMemcpyDeviceToHost, st));
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+        if (n_set >= 0x7FFFFFFFu) return fail(ctx, SHK_E_LIMIT, "too many set bits");
+        staged_free(ctx);
+        SHK_CUDA(ctx, cudaMalloc((void **)&sb.cnt, ((uint64_t)n_set + 1) * 4));
+        SHK_CUDA(ctx, cudaMemsetAsync(sb.cnt, 0, ((uint64_t)n_set + 1) * 4, st));
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+        sb.n_set = n_set;
+        sb.last_idx = -1;
+        sb.mode = 1;
+        if (n_set_bits) *n_set_bits = n_set;
+        return SHK_OK;
+    }
+    if (sb.mode == 1 && new_mode == 2) {
+        free_index_arrays(ix);
+        cudaEvent_t e0, e1;
+        SHK_CUDA(ctx, cudaEventCreate(&e0));
+        SHK_CUDA(ctx, cudaEventCreate(&e1));
+        SHK_CUDA(ctx, cudaEventRecord(e0, st));
+        const uint32_t n_set = sb.n_set;
+        DevBuf<uint32_t> d_fill, d_tmp_off, d_long, d_scalars, d_tiles, d_csr_off;
+        DevBuf<uint16_t> d_tmp_ids, d_csr_ids;
+        DevBuf<uint64_t> d_entries;
+        SHK_CUDA(ctx, d_fill.alloc((uint64_t)n_set + 1));
+        SHK_CUDA(ctx, d_tmp_off.alloc((uint64_t)n_set + 1));
+        SHK_CUDA(ctx, d_long.alloc((uint64_t)n_set + 1));
+        SHK_CUDA(ctx, d_scalars.alloc(8));
+        SHK_CUDA(ctx, d_tiles.alloc((uint64_t)n_set / kScanTile + 2));
+        SHK_CUDA(ctx, d_tmp_ids.alloc(sb.n_pairs + 1));
+        SHK_CUDA(ctx, d_csr_off.alloc((uint64_t)n_set + 1));
+        SHK_CUDA(ctx, d_entries.alloc((uint64_t)n_set + 1));
+        SHK_CUDA(ctx, cudaMemsetAsync(d_fill.p, 0, ((uint64_t)n_set + 1) * 4, st));
+        SHK_CUDA(ctx, cudaMemsetAsync(d_scalars.p, 0, 32, st));
+        uint64_t tot_ids = 0;
+        if (n_set > 0) {
+            int rc = exclusive_scan(ctx, st, U32In{sb.cnt}, U32Out{d_tmp_off.p}, (uint64_t)n_set, d_tiles.p, d_tmp_off.p + n_set);
+            if (rc) return rc;
+            if (sb.n_pairs) {
+                pairs_fill_kernel<<<(unsigned)((sb.n_pairs + 255) / 256), 256, 0, st>>>(sb.pair_rank, sb.pair_gene, sb.n_pairs,
+                                                                                        d_tmp_off.p, d_fill.p, d_tmp_ids.p);
+                ctx->launches += 1;
+            }
+            rc = finish_lists(ctx, st, n_set, d_tmp_off.p, d_tmp_ids.p, d_fill.p, d_long.p, d_scalars.p + 4, d_tiles.p,
+                              d_csr_off, d_csr_ids, d_entries, tot_ids);
+            if (rc) return rc;
+        } else {
+            SHK_CUDA(ctx, cudaMemsetAsync(d_csr_off.p, 0, 4, st));
+            SHK_CUDA(ctx, d_csr_ids.alloc(1));
+        }
+        ix.info = shk_index_info{};
+        ix.info.n_set_bits = n_set;
+        {
+            const uint64_t need_tiles = (((ix.geom.bf_bits + 31) >> 5) + kScanTile - 1) / kScanTile + 2;
+            DevBuf<uint32_t> d_tiles2;
+            SHK_CUDA(ctx, d_tiles2.alloc(need_tiles));
+            // no reference text at this seam: the extension structures are not built
+            int rc = build_front(ctx, st, d_entries.p, d_csr_ids.p, d_tiles2.p, d_scalars.p + 5, ExtBuildInputs{nullptr, nullptr, 0});
+            if (rc) return rc;
+        }
+        SHK_CUDA(ctx, cudaEventRecord(e1, st));
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        ix.entries = d_entries.release();
+        ix.csr_off = d_csr_off.release();
+        ix.csr_ids = d_csr_ids.release();
+        ix.info.n_genes = (uint32_t)(sb.last_idx + 1);
+        ix.info.n_records = ix.info.n_genes;
+        ix.info.tot_ids = tot_ids;
+        ix.info.n_windows = sb.n_pairs;
+        ix.info.bf_bits = ix.geom.bf_bits;
+        ix.info.device_bytes = ix.geom.n_sectors * 32 + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2 +
+                               ix.fgeom.n_entries * 16 * ix.fgeom.stride;
+        ix.info.build_ms = ms;
+        ix.built = true;
+        staged_free(ctx);
+        sb.mode = 2;
+        if (n_set_bits) *n_set_bits = n_set;
+        return SHK_OK;
+    }
+    return fail(ctx, SHK_E_STATE, "switch_mode(%d) in mode %d: only 0 -> 1 and 1 -> 2 exist (bloomfilter.h:112-184)", new_mode,
+                sb.mode);
 }
 
 }  // namespace shk

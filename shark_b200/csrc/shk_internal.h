@@ -125,8 +125,24 @@ struct Slot {
 
 }  // namespace shk
 
+namespace shk {
+// Staged build = the reference's BF protocol (bloomfilter.h:57-75,112-184): mode 0 set bits,
+// mode 1 attach gene ids, mode 2 query.  Mode 1 keeps (rank, gene) pairs on the device.
+struct StagedBuild {
+    int mode = 0;
+    bool hashed = false;          // a window was hashed with params.k: k is frozen
+    uint32_t n_set = 0;
+    int32_t last_idx = -1;        // largest input_idx seen by add_to_kmer
+    uint32_t *cnt = nullptr;      // occurrences per rank (n_set + 1)
+    uint32_t *pair_rank = nullptr;
+    uint16_t *pair_gene = nullptr;
+    uint64_t n_pairs = 0, cap = 0;
+};
+}  // namespace shk
+
 struct shk_ctx {
     shk_params params{};
+    shk::StagedBuild staged;
     int device = 0;
     int sm_count = 148;
     shk::DeviceIndex index;
@@ -163,6 +179,13 @@ int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *id
 int probe_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int64_t *rank, uint32_t *begin, uint32_t *len);
 int probe_bench_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, uint32_t reps, float *ms, uint64_t *hits);
 int random_sector_bench_device(shk_ctx *ctx, uint64_t n_loads, uint64_t span_bytes, uint64_t seed, float *ms);
+// staged build (the reference's functor protocol)
+int kmer_hashes_device(shk_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint64_t *hashes,
+                       uint64_t cap, uint64_t *n_hashes);
+int staged_add_at(shk_ctx *ctx, const uint64_t *positions, uint64_t n);
+int staged_switch_mode(shk_ctx *ctx, int new_mode, uint64_t *n_set_bits);
+int staged_add_to_kmer(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t input_idx);
+void staged_free(shk_ctx *ctx);
 
 // shk_reads.cu
 // Enqueues the classification kernels of one chunk on `st`; returns the number of launches.

@@ -73,6 +73,48 @@ class Shark:
         self.info = info
         return info
 
+    # -- staged build: the reference's functor protocol (KmerBuilder / BloomfilterFiller / class BF) --
+    def kmer_hashes(self, bases, rec_off):
+        """KmerBuilder::operator() (KmerBuilder.hpp:40-72) -> uint64 hashes of all canonical k-mers."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        out = np.zeros(max(len(bases), 1), np.uint64)
+        n = C.c_uint64()
+        self._check(self.lib.shk_kmer_hashes(self.ctx, capi.ptr(bases) if len(bases) else None, capi.ptr(rec_off),
+                                             len(rec_off) - 1, capi.ptr(out), len(bases), C.byref(n)))
+        return out[: n.value].copy()
+
+    def add_at(self, positions):
+        """BloomfilterFiller::operator() / BF::add_at (bloomfilter.h:57-59) for a batch."""
+        positions = np.ascontiguousarray(positions, dtype=np.uint64)
+        self._check(self.lib.shk_bf_add_at(self.ctx, capi.ptr(positions) if len(positions) else None, len(positions)))
+
+    def switch_mode(self, new_mode):
+        """BF::switch_mode (bloomfilter.h:112-184) -> number of set bits."""
+        n = C.c_uint64()
+        self._check(self.lib.shk_bf_switch_mode(self.ctx, new_mode, C.byref(n)))
+        if new_mode == 2:
+            info = capi.IndexInfo()
+            self._check(self.lib.shk_index_info_get(self.ctx, C.byref(info)))
+            self.info = info
+        return n.value
+
+    def add_to_kmer(self, kmers, input_idx):
+        """BF::add_to_kmer (bloomfilter.h:61-75)."""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        self._check(self.lib.shk_bf_add_to_kmer(self.ctx, capi.ptr(kmers) if len(kmers) else None, len(kmers), input_idx))
+
+    def mode(self):
+        return self.lib.shk_bf_mode(self.ctx)
+
+    def set_options(self, k=None, c=None, min_quality=None, single=None):
+        k = self.k if k is None else k
+        c = self.c if c is None else c
+        q = self.min_quality if min_quality is None else min_quality
+        s = self.single if single is None else bool(single)
+        self._check(self.lib.shk_set_options(self.ctx, k, c, q, int(s)))
+        self.k, self.c, self.min_quality, self.single = k, c, q, s
+
     def export_index(self):
         """-> (set_bit_pos uint64[n_set], offsets uint32[n_set+1], ids uint16[tot_ids])"""
         n, t = self.info.n_set_bits, self.info.tot_ids

@@ -33,7 +33,7 @@ def test_binding_matches_header(lib_path):
     from shark_b200 import capi
     assert sorted(capi.EXPORTED) == _declared()
     L = capi.load()
-    assert L.shk_abi_version() == 2
+    assert L.shk_abi_version() == 3
 
 
 def test_struct_sizes():
