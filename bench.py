@@ -103,6 +103,31 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def probe_kmers(bases, k, n, seed=7):
+    """n canonical k-mers for the stand-alone probe kernel (BF::get_index): half are windows of the
+    reference (hits), half are random (misses, up to the filter's false-positive rate)."""
+    rng = np.random.default_rng(seed)
+    code = np.full(256, 4, np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = code[ch | 0x20] = i
+    c = code[np.asarray(bases[: min(len(bases), 4_000_000)])].astype(np.uint64)
+    m = len(c) - k + 1
+    fwd = np.zeros(m, np.uint64)
+    rc = np.zeros(m, np.uint64)
+    bad = np.zeros(m, bool)
+    for j in range(k):
+        cj = c[j:j + m]
+        bad |= cj > 3
+        fwd = (fwd << np.uint64(2)) | (cj & np.uint64(3))
+        rc |= (np.uint64(3) - (cj & np.uint64(3))) << np.uint64(2 * j)
+    canon = np.minimum(fwd, rc)[~bad]
+    hits = canon[rng.integers(0, len(canon), n // 2)]
+    miss = rng.integers(0, 1 << 62, n - n // 2, dtype=np.uint64) & np.uint64((1 << (2 * k)) - 1)
+    out = np.concatenate([hits, miss])
+    rng.shuffle(out)
+    return out
+
+
 def make_workload(wl, rank, n_reads):
     """-> names, bases, rec_off, pinned chunk list [(seq, qual, off32, n)], keepalive buffers."""
     from shark_b200 import capi, synth
@@ -264,6 +289,17 @@ def main():
     rs_ms = sh.random_sector_bench(1 << 28)
     rs_gbs = (1 << 28) * 32 / rs_ms / 1e6
 
+    # stand-alone probe kernel (K5 = BF::get_index: filter word -> sector rank -> entry) on 2^25 canonical k-mers,
+    # half hits / half misses: the "BF probe GB/s vs the random-sector roofline" half of the metric
+    pk = probe_kmers(bases, wl["k"], 1 << 25)
+    pb_ms, pb_hits = sh.probe_bench(pk, reps=4)
+    pb_gbs = len(pk) * 32 / pb_ms / 1e6
+    probe = {"kernel": "probe_bench_kernel (hash -> filter word -> sector + rank -> entry)", "probes": len(pk),
+             "ms": pb_ms, "gprobes_per_s": len(pk) / pb_ms / 1e6, "achieved_gbs_32B_per_probe": pb_gbs,
+             "random_sector_ceiling_gbs": rs_gbs, "frac_of_random_sector_ceiling": pb_gbs / rs_gbs if rs_gbs else None,
+             "hit_fraction": pb_hits / len(pk)}
+    del pk
+
     # ---- device-resident: upload once, then time K passes of the kernels + result read-back
     for i, (s, q, o, n) in enumerate(chunks):
         sh.upload(i, s, q, o, n)
@@ -393,7 +429,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": n_reads * W * (2 if wl["q"] else 1)
                     + n_chunks * (CHUNK_READS + 1) * 4, "d2h_bytes_per_step": d2h[0] // max(args.steps, 1),
                     "ms_per_step": t_e2e_max / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall_max / args.steps * 1e3},
-            "gpu_launches": int(launches_res), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "gpu_launches": int(launches_res), "roofline": roofline, "probe": probe, "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
             "index": {"n_genes": info.n_genes, "n_set_bits": info.n_set_bits, "tot_ids": info.tot_ids,
                       "build_ms": info.build_ms, "broadcast_ms": bcast_ms, "device_bytes": info.device_bytes},
             "associations_per_step": sums.tolist()[2] / args.steps / world, "slow_reads_per_step": n_slow / args.steps,
