@@ -208,6 +208,9 @@ int shk_probe_bench(shk_ctx *ctx, const uint64_t *canonical_kmers, uint64_t n, u
 int shk_random_sector_bench(shk_ctx *ctx, uint64_t n_loads, uint64_t span_bytes, uint64_t seed, float *ms);
 
 /* ---- pinned staging memory ------------------------------------------------------------ */
+/* Page-locked host memory for chunk staging.  The pages are placed on the NUMA node of the calling
+ * thread's CURRENT CUDA device (the device of the last shk_create / cudaSetDevice on that thread), so
+ * that copies do not cross the socket interconnect; SHK_NUMA=0 turns the placement off. */
 int shk_alloc_pinned(void **ptr, size_t bytes);
 int shk_free_pinned(void *ptr);
 

@@ -5,6 +5,9 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <string>
+
+#include <sched.h>
 
 #include "shk_internal.h"
 
@@ -69,6 +72,89 @@ static void tmark(const char *what)
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 }
 
+
+// Pinned staging memory should live on the NUMA node the GPU hangs off: a host-to-device copy that
+// crosses the socket interconnect shares its bandwidth with every other GPU's copies (the 4-GPU
+// bench loses ~13 % of its end-to-end rate to that).  While a pinned allocation is made for the
+// CURRENT device, the calling thread is confined to that node's CPUs, so that the pages the driver
+// faults in and pins are local (first touch); the previous affinity is restored afterwards.  No
+// libnuma and no set_mempolicy (containers filter it); if sysfs does not describe the topology
+// this is a no-op.  SHK_NUMA=0 disables it.
+class NumaLocalScope {
+public:
+    NumaLocalScope()
+    {
+        static const bool enabled = !(getenv("SHK_NUMA") && atoi(getenv("SHK_NUMA")) == 0);
+        int dev = 0;
+        char bus[32] = {0};
+        if (!enabled || cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        for (char *c = bus; *c; ++c)
+            if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');  // sysfs spells bus ids in lower case
+        int node = -1;
+        if (!read_int((std::string("/sys/bus/pci/devices/") + bus + "/numa_node").c_str(), node) || node < 0) return;
+        cpu_set_t want;
+        CPU_ZERO(&want);
+        if (!read_cpulist(("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist").c_str(), want)) return;
+        if (sched_getaffinity(0, sizeof saved_, &saved_) != 0) return;
+        cpu_set_t both;
+        CPU_AND(&both, &want, &saved_);  // never leave the cpuset the process was given
+        if (CPU_COUNT(&both) == 0) return;
+        active_ = sched_setaffinity(0, sizeof both, &both) == 0;
+        node_ = node;
+    }
+    ~NumaLocalScope()
+    {
+        if (active_) sched_setaffinity(0, sizeof saved_, &saved_);
+    }
+    int node() const { return active_ ? node_ : -1; }
+
+private:
+    static bool read_int(const char *path, int &v)
+    {
+        FILE *f = fopen(path, "r");
+        if (!f) return false;
+        const bool ok = fscanf(f, "%d", &v) == 1;
+        fclose(f);
+        return ok;
+    }
+    static bool read_cpulist(const char *path, cpu_set_t &set)  // "0-31,64-95"
+    {
+        FILE *f = fopen(path, "r");
+        if (!f) return false;
+        char buf[4096];
+        const bool got = fgets(buf, sizeof buf, f) != nullptr;
+        fclose(f);
+        if (!got) return false;
+        int n = 0;
+        for (char *p = buf; *p && *p != '\n';) {
+            char *e;
+            long a = strtol(p, &e, 10), b = a;
+            if (e == p) break;
+            if (*e == '-') {
+                p = e + 1;
+                b = strtol(p, &e, 10);
+            }
+            for (long c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET((int)c, &set), ++n;
+            p = *e == ',' ? e + 1 : e;
+        }
+        return n > 0;
+    }
+    cpu_set_t saved_;
+    bool active_ = false;
+    int node_ = -1;
+};
+
+static cudaError_t pinned_alloc(void **ptr, size_t bytes)
+{
+    NumaLocalScope numa;
+    static const bool verbose = getenv("SHK_TIMING") != nullptr;
+    if (verbose) fprintf(stderr, "[libshark_b200/numa] pinned %zu bytes on node %d\n", bytes, numa.node());
+    return cudaMallocHost(ptr, bytes ? bytes : 1);
+}
+
 static int alloc_slot(shk_ctx *ctx, Slot &s)
 {
     const uint64_t R = ctx->max_reads, B = ctx->max_bytes;
@@ -93,10 +179,10 @@ static int alloc_slot(shk_ctx *ctx, Slot &s)
     s.assoc_cap = R + R / 4 + 1024;
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_assoc, s.assoc_cap * sizeof(shk_assoc)));
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_keep, R + 64));
-    SHK_CUDA(ctx, cudaMallocHost((void **)&s.h_counters, sizeof(ChunkCounters)));
+    SHK_CUDA(ctx, pinned_alloc((void **)&s.h_counters, sizeof(ChunkCounters)));
     s.h_assoc_cap = s.assoc_cap;
-    SHK_CUDA(ctx, cudaMallocHost((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
-    SHK_CUDA(ctx, cudaMallocHost((void **)&s.h_keep, R + 64));
+    SHK_CUDA(ctx, pinned_alloc((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
+    SHK_CUDA(ctx, pinned_alloc((void **)&s.h_keep, R + 64));
     return SHK_OK;
 }
 
@@ -522,7 +608,7 @@ int shk_random_sector_bench(shk_ctx *ctx, uint64_t n_loads, uint64_t span_bytes,
 int shk_alloc_pinned(void **ptr, size_t bytes)
 {
     if (!ptr) return SHK_E_ARG;
-    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    cudaError_t e = pinned_alloc(ptr, bytes);
     if (e != cudaSuccess) return fail(nullptr, SHK_E_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
     return SHK_OK;
 }
@@ -617,7 +703,7 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
         cudaFreeHost(s.h_assoc);
         s.h_assoc = nullptr;
         s.h_assoc_cap = c.n_assoc + c.n_assoc / 8 + 1024;
-        SHK_CUDA(ctx, cudaMallocHost((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
+        SHK_CUDA(ctx, pinned_alloc((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
     }
     if (c.n_assoc)
         SHK_CUDA(ctx, cudaMemcpyAsync(s.h_assoc, s.d_assoc, c.n_assoc * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
