@@ -205,6 +205,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extend", default="auto", choices=["auto", "on", "off"],
                     help="anchor-and-extend: automatic (on for DRAM-sized front tables), or forced (A/B runs)")
+    ap.add_argument("--index", default="broadcast", choices=["broadcast", "sharded", "both"],
+                    help="N > 1: build on rank 0 + NCCL broadcast (default), or every rank indexes one gene shard and the "
+                         "filters are OR-merged by the library's P2P kernel; 'both' times both and checks they are identical")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     n_reads = args.reads or wl["reads"]
@@ -275,13 +278,30 @@ def main():
                extend={"auto": None, "on": True, "off": False}[args.extend])
     # index: build on rank 0, replicate over NVLink
     bcast_ms = 0.0
-    if rank == 0:
-        info = sh.build_index(bases, rec_off)
-        log("[bench] index: %d genes, %d set bits, %d ids, %.2f ms on device" %
-            (info.n_genes, info.n_set_bits, info.tot_ids, info.build_ms))
-    if world > 1:
+    index_extra = {"mode": "single GPU" if world == 1 else args.index}
+    if world == 1 or args.index in ("broadcast", "both"):
+        if rank == 0:
+            info = sh.build_index(bases, rec_off)
+            log("[bench] index: %d genes, %d set bits, %d ids, %.2f ms on device (%.1f ms wall)" %
+                (info.n_genes, info.n_set_bits, info.tot_ids, info.build_ms, info.build_wall_ms))
+        if world > 1:
+            from shark_b200 import dist_index
+            bcast_ms = dist_index.broadcast_index(sh, src=0)
+    if world > 1 and args.index in ("sharded", "both"):
         from shark_b200 import dist_index
-        bcast_ms = dist_index.broadcast_index(sh, src=0)
+        before = sh.export_index() if args.index == "both" else None
+        b_info = sh.info
+        barrier()
+        s_info, s_secs = dist_index.build_index_sharded(sh, bases, rec_off)
+        index_extra.update({"sharded_wall_ms": s_secs * 1e3, "sharded_device_ms": s_info.build_ms, "n_shards": s_info.n_shards})
+        if before is not None:
+            after = sh.export_index()
+            same = all(np.array_equal(a, b) for a, b in zip(before, after)) and \
+                (b_info.n_genes, b_info.n_set_bits, b_info.tot_ids) == (s_info.n_genes, s_info.n_set_bits, s_info.tot_ids)
+            index_extra["sharded_equals_broadcast"] = bool(same)
+            if not same:
+                raise SystemExit("sharded index differs from the broadcast index on rank %d" % rank)
+        log("[bench] rank %d sharded index build: %.1f ms wall, %.2f ms on device" % (rank, s_secs * 1e3, s_info.build_ms))
     info = sh.info
     launches0 = sh.kernel_launches()
 
@@ -432,7 +452,8 @@ def main():
             "gpu_launches": int(launches_res), "roofline": roofline, "probe": probe, "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "index": {"n_genes": info.n_genes, "n_set_bits": info.n_set_bits, "tot_ids": info.tot_ids,
-                      "build_ms": info.build_ms, "broadcast_ms": bcast_ms, "device_bytes": info.device_bytes},
+                      "build_ms": info.build_ms, "build_wall_ms": info.build_wall_ms, "broadcast_ms": bcast_ms,
+                      "device_bytes": info.device_bytes, **index_extra},
             "associations_per_step": sums.tolist()[2] / args.steps / world, "slow_reads_per_step": n_slow / args.steps,
         }
         real_stdout.write(json.dumps(out) + "\n")

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SHK_ABI_VERSION 3
+#define SHK_ABI_VERSION 4
 
 typedef enum shk_status {
     SHK_OK = 0,
@@ -68,13 +68,17 @@ typedef struct shk_index_info {
     uint64_t n_windows;  /* k-mer occurrences hashed in each pass                                  */
     uint64_t bf_bits;
     uint64_t device_bytes; /* HBM held by the index                                               */
-    float build_ms;        /* device time of the whole build (CUDA events)                         */
+    float build_ms;        /* device time of the whole build: CUDA-event segments that exclude the
+                              host gaps between phases (allocations, read-backs of counts)         */
     uint32_t front_shift;  /* front table: log2(positions per bucket)                              */
     uint64_t front_entries; /* front table: entries (buckets + overflow records)                  */
     uint64_t ref_bases;    /* bases of the concatenated reference (extension structures)           */
     uint32_t extend;       /* 1 = the index carries the anchor-and-extend structures: front-table
                               entries are 32 bytes (slots + anchors), views 5-7 are present        */
     uint32_t coarse_shift; /* log2(filter positions per bit of the coarse miss filter)             */
+    float build_wall_ms;   /* host clock around the same build, allocations included               */
+    uint32_t n_shards;     /* 1 = built by shk_index_build; n = sharded build over n contexts;
+                              0 = staged protocol / adopted                                         */
 } shk_index_info;
 
 /* One association = one line of the reference's stdout (ReadOutput.hpp:43): read `read_idx`
@@ -153,6 +157,62 @@ int shk_index_finalize(shk_ctx *ctx);
 /* Same replication for two contexts of ONE process (the multi-GPU CLI): adopt + peer copies over
  * NVLink (cudaMemcpyPeerAsync) + finalize. */
 int shk_index_replicate(shk_ctx *src, shk_ctx *dst);
+
+/* ---- sharded index build (SURVEY.md 8e second mode, 8f.3) ------------------------------- */
+/* The north star's alternative to broadcasting a finished index: every context (= GPU) enumerates
+ * the k-mers of ONE shard of the reference records into its own filter (pass 1 of the reference,
+ * KmerBuilder.hpp:40-72 -> bloomfilter.h:57-59, over a subset of the genes); the filters are then
+ * OR-merged with a P2P kernel over NVLink (NCCL has no bitwise-OR reduction): phase 1 reduces
+ * slice i of every peer's filter into context i, phase 2 gathers the reduced slices.  Every
+ * context then builds the same rank directory (bloomfilter.h:121-124), converts its own windows to
+ * ranks, gathers the other shards' ranks and finishes pass 2 locally.  The result on every context
+ * is bit-identical to shk_index_build (tests/test_gpu_shard.py).
+ *
+ * Protocol, with a barrier across all contexts wherever a line says so (every call returns with
+ * its device work finished, so a host-side barrier is enough):
+ *     shk_shard_begin                       each context; fills its shk_shard_mem
+ *     (exchange the shk_shard_mem structs; other processes: shk_shard_open on each peer's)
+ *     -- barrier --  shk_shard_merge(1)  -- barrier --  shk_shard_merge(2)  shk_shard_rank
+ *     -- barrier --  shk_shard_finish    -- barrier --  shk_shard_close / shk_shard_end
+ * `all` is an array of n_shards structs indexed by shard whose dev_ptr are usable from the
+ * calling process (entry [own shard] is ignored). */
+typedef struct shk_shard_mem {
+    void *dev_ptr[3];           /* 0 filter sectors, 1 per-position window array, 2 per-record
+                                   window flags; valid in the process named by pid                 */
+    uint8_t ipc_handle[3][64];  /* cudaIpcMemHandle_t of each, for peers in other processes        */
+    int64_t pid;                /* owning process; negative after shk_shard_open mapped it         */
+    int32_t device;
+    uint32_t shard;
+    uint32_t ipc_ok;            /* 0: the handles could not be exported (same-process use only)    */
+    uint32_t reserved;
+} shk_shard_mem;
+/* How the reference is cut: cuts[n_shards+1] positions at record boundaries, balanced by bases
+ * (shard s enumerates the windows ending in [cuts[s], cuts[s+1])).  Pure host function. */
+int shk_shard_cuts(const uint64_t *rec_offsets, uint32_t n_records, uint32_t n_shards, uint64_t *cuts);
+int shk_shard_begin(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_offsets, uint32_t n_records,
+                    uint32_t shard, uint32_t n_shards, shk_shard_mem *mine);
+/* Makes a peer's buffers addressable from this context: peer access for a context of the same
+ * process, cudaIpcOpenMemHandle for another process.  `opened` receives the usable struct. */
+int shk_shard_open(shk_ctx *ctx, const shk_shard_mem *peer, shk_shard_mem *opened);
+int shk_shard_close(shk_ctx *ctx, shk_shard_mem *opened);
+int shk_shard_merge(shk_ctx *ctx, int phase, const shk_shard_mem *all);
+int shk_shard_rank(shk_ctx *ctx);
+int shk_shard_finish(shk_ctx *ctx, const shk_shard_mem *all, shk_index_info *info);
+int shk_shard_end(shk_ctx *ctx);
+/* The whole protocol for n contexts of ONE process (the multi-GPU CLI; also several contexts on one
+ * device), one host thread per context, barriers between the steps.  info (may be NULL) receives
+ * context 0's. */
+int shk_index_build_sharded(shk_ctx **ctxs, uint32_t n, const uint8_t *ref_bases, const uint64_t *rec_offsets,
+                            uint32_t n_records, shk_index_info *info);
+
+/* ---- index serialisation ------------------------------------------------- */
+/* The reference rebuilds its index on every run (main.cpp:128-193).  These two calls write the
+ * finished device index to a file and load it into a context created with the same k and bf_bits:
+ * header (magic, ABI version, k, shk_index_info, view sizes, FNV-1a checksum of the payload)
+ * followed by the raw views of shk_index_views_get.  A load that does not match (k, bf_bits, ABI
+ * version, checksum, truncated file) fails with SHK_E_ARG and leaves the context without an index. */
+int shk_index_save(shk_ctx *ctx, const char *path);
+int shk_index_load(shk_ctx *ctx, const char *path, shk_index_info *info);
 
 /* ---- staged index build: the reference's own functor protocol ------------------------- */
 /* The same index, built through the calls the reference's main.cpp makes (seam 2),

@@ -22,7 +22,8 @@ EXPORTED = [
     "shk_random_sector_bench", "shk_alloc_pinned", "shk_free_pinned", "shk_reads_submit", "shk_reads_collect",
     "shk_reads_upload", "shk_reads_analyze_resident", "shk_kernel_launches", "shk_device_timer_start",
     "shk_device_timer_stop", "shk_kmer_hashes", "shk_bf_add_at", "shk_bf_switch_mode", "shk_bf_add_to_kmer", "shk_bf_mode",
-    "shk_set_options",
+    "shk_set_options", "shk_shard_begin", "shk_shard_open", "shk_shard_close", "shk_shard_merge", "shk_shard_rank",
+    "shk_shard_finish", "shk_shard_end", "shk_shard_cuts", "shk_index_build_sharded", "shk_index_save", "shk_index_load",
 ]
 
 
@@ -46,7 +47,14 @@ class IndexInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint32), ("n_genes", C.c_uint32), ("n_set_bits", C.c_uint64), ("tot_ids", C.c_uint64),
                 ("n_windows", C.c_uint64), ("bf_bits", C.c_uint64), ("device_bytes", C.c_uint64), ("build_ms", C.c_float),
                 ("front_shift", C.c_uint32), ("front_entries", C.c_uint64), ("ref_bases", C.c_uint64),
-                ("extend", C.c_uint32), ("coarse_shift", C.c_uint32)]
+                ("extend", C.c_uint32), ("coarse_shift", C.c_uint32), ("build_wall_ms", C.c_float),
+                ("n_shards", C.c_uint32)]
+
+
+class ShardMem(C.Structure):
+    """shk_shard_mem: one context's buffers in the sharded index build."""
+    _fields_ = [("dev_ptr", C.c_void_p * 3), ("ipc_handle", (C.c_uint8 * 64) * 3), ("pid", C.c_int64),
+                ("device", C.c_int32), ("shard", C.c_uint32), ("ipc_ok", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class IndexViews(C.Structure):
@@ -107,6 +115,17 @@ def load():
     L.shk_bf_add_to_kmer.argtypes = [vp, vp, C.c_uint64, C.c_int32]
     L.shk_bf_mode.argtypes = [vp]
     L.shk_set_options.argtypes = [vp, C.c_uint32, C.c_double, C.c_int32, C.c_int32]
+    L.shk_shard_begin.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ShardMem)]
+    L.shk_shard_open.argtypes = [vp, C.POINTER(ShardMem), C.POINTER(ShardMem)]
+    L.shk_shard_close.argtypes = [vp, C.POINTER(ShardMem)]
+    L.shk_shard_merge.argtypes = [vp, C.c_int, C.POINTER(ShardMem)]
+    L.shk_shard_rank.argtypes = [vp]
+    L.shk_shard_finish.argtypes = [vp, C.POINTER(ShardMem), C.POINTER(IndexInfo)]
+    L.shk_shard_end.argtypes = [vp]
+    L.shk_shard_cuts.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
+    L.shk_index_build_sharded.argtypes = [C.POINTER(vp), C.c_uint32, vp, vp, C.c_uint32, C.POINTER(IndexInfo)]
+    L.shk_index_save.argtypes = [vp, C.c_char_p]
+    L.shk_index_load.argtypes = [vp, C.c_char_p, C.POINTER(IndexInfo)]
     L.shk_kernel_launches.restype = C.c_uint64
     for name in EXPORTED:
         f = getattr(L, name)

@@ -4,7 +4,10 @@
 // stamps.  The host does what the north star leaves on the host: FASTA/FASTQ parsing
 // (fastx.hpp), batching into pinned SoA chunks (FastaSplitter.hpp / FastqSplitter.hpp) and
 // output (ReadOutput.hpp); everything between goes through shk_index_build / shk_reads_submit /
-// shk_reads_collect.  Extensions (not in the reference): --gpus N, --chunk-reads N.
+// shk_reads_collect.  Extensions (not in the reference): --gpus N, --chunk-reads N, --sharded-build
+// (with --gpus N: every GPU indexes one gene shard, filters OR-merged over NVLink, instead of build +
+// replicate), --save-index FILE / --load-index FILE (the reference rebuilds its index on every run;
+// the gene names still come from -r).
 //
 // Pipeline (pipeline.hpp, ingest.hpp): one scanner thread per input file turns 8 MiB blocks into
 // record outcomes without copying; a batcher thread packs whole 50 000-read batches into pinned
@@ -69,6 +72,8 @@ struct Options {
     int n_threads = 1;
     int gpus = 1;                   // extension
     unsigned chunk_reads = 1000000; // extension; rounded to a multiple of the 50 000-read batch
+    bool sharded_build = false;     // extension
+    std::string save_index, load_index;  // extensions
 };
 
 // argument_parser.hpp:84-174, option by option (istringstream extraction included, so that e.g.
@@ -92,6 +97,9 @@ Options parse_arguments(int argc, char **argv)
                                              {"help", no_argument, nullptr, 'h'},
                                              {"gpus", required_argument, nullptr, 1000},
                                              {"chunk-reads", required_argument, nullptr, 1001},
+                                             {"sharded-build", no_argument, nullptr, 1002},
+                                             {"save-index", required_argument, nullptr, 1003},
+                                             {"load-index", required_argument, nullptr, 1004},
                                              {nullptr, 0, nullptr, 0}};
     for (int ch; (ch = getopt_long(argc, argv, shortopts, longopts, nullptr)) != -1;) {
         std::istringstream arg(optarg != nullptr ? optarg : "");
@@ -147,6 +155,9 @@ Options parse_arguments(int argc, char **argv)
         case 'h': std::cerr << USAGE_MESSAGE; exit(EXIT_SUCCESS);
         case 1000: arg >> opt.gpus; break;
         case 1001: arg >> opt.chunk_reads; break;
+        case 1002: opt.sharded_build = true; break;
+        case 1003: arg >> opt.save_index; break;
+        case 1004: arg >> opt.load_index; break;
         default:
             std::cerr << "shark : unknown argument" << std::endl;
             std::cerr << "\n" << USAGE_MESSAGE;
@@ -333,12 +344,29 @@ int main(int argc, char *argv[])
     }
     tstamp("contexts created");
     shk_index_info info;
-    SHK_TRY(ctxs[0], shk_index_build(ctxs[0], ref_bases.data(), rec_off.data(), (uint32_t)legend_ID.size(), &info));
+    bool replicated = false;
+    if (!opt.load_index.empty()) {
+        SHK_TRY(ctxs[0], shk_index_load(ctxs[0], opt.load_index.c_str(), &info));
+        if (info.n_records != legend_ID.size())
+            die("index " + opt.load_index + " was built from " + std::to_string(info.n_records) + " records, " +
+                opt.fasta_path + " has " + std::to_string(legend_ID.size()));
+    } else if (opt.sharded_build && opt.gpus > 1) {
+        SHK_TRY(ctxs[0], shk_index_build_sharded(ctxs.data(), (uint32_t)opt.gpus, ref_bases.data(), rec_off.data(),
+                                                 (uint32_t)legend_ID.size(), &info));
+        replicated = true;
+    } else {
+        SHK_TRY(ctxs[0], shk_index_build(ctxs[0], ref_bases.data(), rec_off.data(), (uint32_t)legend_ID.size(), &info));
+    }
     tstamp("index built");
+    if (!opt.save_index.empty()) {
+        SHK_TRY(ctxs[0], shk_index_save(ctxs[0], opt.save_index.c_str()));
+        tstamp("index saved");
+    }
     pelapsed("Transcript file processed");
     pelapsed("First switch performed");
     pelapsed("BF created from transcripts (" + std::to_string(info.n_genes) + " genes)");
-    for (int g = 1; g < opt.gpus; ++g) SHK_TRY(ctxs[g], shk_index_replicate(ctxs[0], ctxs[g]));
+    if (!replicated)
+        for (int g = 1; g < opt.gpus; ++g) SHK_TRY(ctxs[g], shk_index_replicate(ctxs[0], ctxs[g]));
     pelapsed("Second switch performed");
     std::vector<uint8_t>().swap(ref_bases);
 

@@ -5,7 +5,10 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <algorithm>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include <sched.h>
 
@@ -301,6 +304,8 @@ static int enqueue_upload(shk_ctx *ctx, Slot &s, const uint8_t *seq, const uint8
 
 using namespace shk;
 
+static_assert(sizeof(shk_index_info) == 88 && sizeof(shk_shard_mem) == 240, "layouts mirrored in shark_b200/capi.py");
+
 extern "C" {
 
 int shk_abi_version(void) { return SHK_ABI_VERSION; }
@@ -398,6 +403,7 @@ void shk_destroy(shk_ctx *ctx)
         delete[] ctx->slots;
     }
     staged_free(ctx);
+    shard_free(ctx);
     cudaFree(ctx->index.sectors);
     cudaFree(ctx->index.entries);
     cudaFree(ctx->index.csr_off);
@@ -580,6 +586,249 @@ int shk_index_replicate(shk_ctx *src, shk_ctx *dst)
     }
     SHK_CUDA(dst, cudaStreamSynchronize(dst->build_stream));
     return shk_index_finalize(dst);
+}
+
+// ---- sharded index build (shk_index.cu, "Sharded build") ---------------------------------------
+static int shard_guard(shk_ctx *ctx)
+{
+    if (!ctx) return SHK_E_ARG;
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return SHK_OK;
+}
+
+int shk_shard_cuts(const uint64_t *rec_offsets, uint32_t n_records, uint32_t n_shards, uint64_t *cuts)
+{
+    if (!rec_offsets || !cuts || n_shards == 0) return fail(nullptr, SHK_E_ARG, "bad argument");
+    shard_cuts_host(rec_offsets, n_records, n_shards, cuts);
+    return SHK_OK;
+}
+
+int shk_shard_begin(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_offsets, uint32_t n_records, uint32_t shard,
+                    uint32_t n_shards, shk_shard_mem *mine)
+{
+    if (!ctx || !rec_offsets || !mine) return fail(ctx, SHK_E_ARG, "NULL argument");
+    if (rec_offsets[n_records] && !ref_bases) return fail(ctx, SHK_E_ARG, "ref_bases is NULL");
+    int rc = shard_guard(ctx);
+    if (rc) return rc;
+    staged_free(ctx);
+    ctx->staged.mode = 0;
+    return shard_begin(ctx, ref_bases, rec_offsets, n_records, shard, n_shards, mine);
+}
+
+int shk_shard_open(shk_ctx *ctx, const shk_shard_mem *peer, shk_shard_mem *opened)
+{
+    if (!ctx || !peer || !opened) return fail(ctx, SHK_E_ARG, "NULL argument");
+    int rc = shard_guard(ctx);
+    return rc ? rc : shard_open(ctx, peer, opened);
+}
+
+int shk_shard_close(shk_ctx *ctx, shk_shard_mem *opened)
+{
+    if (!ctx || !opened) return fail(ctx, SHK_E_ARG, "NULL argument");
+    int rc = shard_guard(ctx);
+    return rc ? rc : shard_close(ctx, opened);
+}
+
+int shk_shard_merge(shk_ctx *ctx, int phase, const shk_shard_mem *all)
+{
+    if (!ctx || !all || (phase != 1 && phase != 2)) return fail(ctx, SHK_E_ARG, "bad argument");
+    int rc = shard_guard(ctx);
+    return rc ? rc : shard_merge(ctx, phase, all);
+}
+
+int shk_shard_rank(shk_ctx *ctx)
+{
+    int rc = shard_guard(ctx);
+    return rc ? rc : shard_rank(ctx);
+}
+
+int shk_shard_finish(shk_ctx *ctx, const shk_shard_mem *all, shk_index_info *info)
+{
+    if (!ctx || !all) return fail(ctx, SHK_E_ARG, "NULL argument");
+    int rc = shard_guard(ctx);
+    if (rc) return rc;
+    if ((rc = shard_finish(ctx, all)) != 0) return rc;
+    ctx->staged.mode = 2;
+    ctx->staged.hashed = true;
+    if ((rc = ensure_slow_table(ctx)) != 0) return rc;
+    if (info) *info = ctx->index.info;
+    return SHK_OK;
+}
+
+int shk_shard_end(shk_ctx *ctx)
+{
+    int rc = shard_guard(ctx);
+    if (rc) return rc;
+    shard_free(ctx);
+    return SHK_OK;
+}
+
+int shk_index_build_sharded(shk_ctx **ctxs, uint32_t n, const uint8_t *ref_bases, const uint64_t *rec_offsets,
+                            uint32_t n_records, shk_index_info *info)
+{
+    if (!ctxs || n == 0 || !ctxs[0]) return fail(nullptr, SHK_E_ARG, "no contexts");
+    for (uint32_t i = 0; i < n; ++i)
+        if (!ctxs[i]) return fail(ctxs[0], SHK_E_ARG, "context %u is NULL", i);
+    std::vector<shk_shard_mem> mem(n);
+    std::vector<std::vector<shk_shard_mem>> seen(n, std::vector<shk_shard_mem>(n));
+    std::vector<int> rcs(n, 0);
+    // one host thread per context per step; joining the threads is the barrier
+    auto step = [&](auto &&fn) {
+        std::vector<std::thread> th;
+        for (uint32_t i = 0; i < n; ++i)
+            th.emplace_back([&, i] {
+                if (rcs[i] == 0) rcs[i] = fn(i);
+            });
+        for (auto &t : th) t.join();
+        for (uint32_t i = 0; i < n; ++i)
+            if (rcs[i]) return rcs[i];
+        return 0;
+    };
+    int rc = step([&](uint32_t i) { return shk_shard_begin(ctxs[i], ref_bases, rec_offsets, n_records, i, n, &mem[i]); });
+    if (!rc)
+        rc = step([&](uint32_t i) {
+            for (uint32_t j = 0; j < n; ++j) {
+                int r = shk_shard_open(ctxs[i], &mem[j], &seen[i][j]);
+                if (r) return r;
+            }
+            return shk_shard_merge(ctxs[i], 1, seen[i].data());
+        });
+    if (!rc)
+        rc = step([&](uint32_t i) {
+            int r = shk_shard_merge(ctxs[i], 2, seen[i].data());
+            return r ? r : shk_shard_rank(ctxs[i]);
+        });
+    if (!rc) rc = step([&](uint32_t i) { return shk_shard_finish(ctxs[i], seen[i].data(), nullptr); });
+    for (uint32_t i = 0; i < n; ++i) shk_shard_end(ctxs[i]);
+    if (rc) {
+        for (uint32_t i = 0; i < n; ++i)
+            if (rcs[i] && i != 0) snprintf(ctxs[0]->err, sizeof ctxs[0]->err, "context %u: %.480s", i, ctxs[i]->err);
+        return rc;
+    }
+    if (info) *info = ctxs[0]->index.info;
+    return SHK_OK;
+}
+
+// ---- index serialisation -------------------------------------------------------------------------
+namespace {
+struct IndexFileHeader {
+    char magic[8];  // "SHKIDX\0\0"
+    uint32_t abi, k;
+    uint64_t bf_bits;
+    uint64_t view_bytes[SHK_INDEX_N_VIEWS];
+    uint64_t checksum;  // FNV-1a (64-bit words) over all view payloads in order
+    shk_index_info info;
+};
+constexpr size_t kIoPiece = 64u << 20;
+
+uint64_t fnv1a_words(uint64_t h, const uint8_t *p, size_t n)
+{
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0x100000001B3ull;
+    }
+    for (; i < n; ++i) h = (h ^ p[i]) * 0x100000001B3ull;
+    return h;
+}
+}  // namespace
+
+int shk_index_save(shk_ctx *ctx, const char *path)
+{
+    if (!ctx || !path) return fail(ctx, SHK_E_ARG, "NULL argument");
+    if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index to save");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    shk_index_views v;
+    int rc = shk_index_views_get(ctx, &v);
+    if (rc) return rc;
+    IndexFileHeader h{};
+    memcpy(h.magic, "SHKIDX\0\0", 8);
+    h.abi = SHK_ABI_VERSION;
+    h.k = ctx->params.k;
+    h.bf_bits = ctx->index.geom.bf_bits;
+    h.info = v.info;
+    for (int i = 0; i < SHK_INDEX_N_VIEWS; ++i) h.view_bytes[i] = v.bytes[i];
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(ctx, SHK_E_ARG, "cannot open %s for writing", path);
+    void *stage = nullptr;
+    if (cudaMallocHost(&stage, kIoPiece) != cudaSuccess) {
+        fclose(f);
+        return fail(ctx, SHK_E_NOMEM, "cannot allocate the staging buffer");
+    }
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    uint64_t sum = 0xCBF29CE484222325ull;
+    for (int i = 0; ok && i < SHK_INDEX_N_VIEWS; ++i)
+        for (uint64_t a = 0; ok && a < v.bytes[i]; a += kIoPiece) {
+            const size_t nb = (size_t)std::min<uint64_t>(kIoPiece, v.bytes[i] - a);
+            ok = cudaMemcpy(stage, (const uint8_t *)v.dev_ptr[i] + a, nb, cudaMemcpyDeviceToHost) == cudaSuccess;
+            if (ok) {
+                sum = fnv1a_words(sum, (const uint8_t *)stage, nb);
+                ok = fwrite(stage, 1, nb, f) == nb;
+            }
+        }
+    h.checksum = sum;
+    ok = ok && fseek(f, 0, SEEK_SET) == 0 && fwrite(&h, sizeof h, 1, f) == 1;
+    ok = (fclose(f) == 0) && ok;
+    cudaFreeHost(stage);
+    cudaGetLastError();
+    if (!ok) return fail(ctx, SHK_E_ARG, "writing %s failed", path);
+    return SHK_OK;
+}
+
+int shk_index_load(shk_ctx *ctx, const char *path, shk_index_info *info)
+{
+    if (!ctx || !path) return fail(ctx, SHK_E_ARG, "NULL argument");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(ctx, SHK_E_ARG, "cannot open %s", path);
+    IndexFileHeader h{};
+    auto bad = [&](const char *why) {
+        fclose(f);
+        ctx->index.built = false;
+        return fail(ctx, SHK_E_ARG, "%s: %s", path, why);
+    };
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SHKIDX\0\0", 8) != 0) return bad("not a shark-b200 index file");
+    if (h.abi != SHK_ABI_VERSION) return bad("written by another ABI version");
+    if (h.k != ctx->params.k) return bad("built with another k");
+    if (h.bf_bits != ctx->index.geom.bf_bits || h.info.bf_bits != h.bf_bits) return bad("built with another filter size");
+    staged_free(ctx);
+    int rc = shk_index_adopt(ctx, &h.info);
+    if (rc) {
+        fclose(f);
+        return rc;
+    }
+    shk_index_views v;
+    if ((rc = shk_index_views_get(ctx, &v)) != 0) {
+        fclose(f);
+        return rc;
+    }
+    for (int i = 0; i < SHK_INDEX_N_VIEWS; ++i)
+        if (v.bytes[i] != h.view_bytes[i]) return bad("view sizes do not match the header");
+    void *stage = nullptr;
+    if (cudaMallocHost(&stage, kIoPiece) != cudaSuccess) {
+        fclose(f);
+        return fail(ctx, SHK_E_NOMEM, "cannot allocate the staging buffer");
+    }
+    bool ok = true;
+    uint64_t sum = 0xCBF29CE484222325ull;
+    for (int i = 0; ok && i < SHK_INDEX_N_VIEWS; ++i)
+        for (uint64_t a = 0; ok && a < v.bytes[i]; a += kIoPiece) {
+            const size_t nb = (size_t)std::min<uint64_t>(kIoPiece, v.bytes[i] - a);
+            ok = fread(stage, 1, nb, f) == nb;
+            if (ok) {
+                sum = fnv1a_words(sum, (const uint8_t *)stage, nb);
+                ok = cudaMemcpy((uint8_t *)v.dev_ptr[i] + a, stage, nb, cudaMemcpyHostToDevice) == cudaSuccess;
+            }
+        }
+    cudaFreeHost(stage);
+    cudaGetLastError();
+    if (!ok) return bad("truncated file or copy failure");
+    if (sum != h.checksum) return bad("checksum mismatch");
+    fclose(f);
+    if ((rc = shk_index_finalize(ctx)) != 0) return rc;
+    if (info) *info = ctx->index.info;
+    return SHK_OK;
 }
 
 int shk_probe(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int64_t *rank, uint32_t *begin, uint32_t *len)

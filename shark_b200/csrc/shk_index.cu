@@ -3,6 +3,12 @@
 // the random-sector microbenchmark.  Citations are reference file:line.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <new>
+#include <unistd.h>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "shk_internal.h"
@@ -138,13 +144,14 @@ __device__ __forceinline__ uint32_t record_of(const uint64_t *rec_off, uint32_t 
 template <int MOD>
 __global__ void __launch_bounds__(256)
 enum_setbits_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ rec_off, uint32_t n_rec,
-                    uint64_t total, int k, FilterGeom g, uint32_t *sectors, uint64_t *win_pos,
+                    uint64_t lo, uint64_t hi, int k, FilterGeom g, uint32_t *sectors, uint64_t *win_pos,
                     uint32_t *rec_has_window, unsigned long long *n_windows)
 {
-    const uint64_t x0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kPosPerThread;
+    // windows ENDING in [lo, hi): the whole reference, or one shard of it (sharded build)
+    const uint64_t x0 = lo + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kPosPerThread;
     uint32_t my_windows = 0;
-    if (x0 < total) {
-        const uint64_t xend = min(x0 + (uint64_t)kPosPerThread, total);
+    if (x0 < hi) {
+        const uint64_t xend = min(x0 + (uint64_t)kPosPerThread, hi);
         uint64_t s = x0 >= (uint64_t)(k - 1) ? x0 - (k - 1) : 0;
         uint32_t r = record_of(rec_off, n_rec, s);
         uint64_t next_b = rec_off[r + 1];
@@ -597,6 +604,57 @@ struct DevBuf {
     }
 };
 
+// Device time of a build without the host gaps between its phases (cudaMalloc of GB-sized
+// buffers, result read-backs): a segment opens after the allocations of a phase and closes right
+// before the phase's stream synchronisation; build_ms is the sum of the segments.
+struct SegTimer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> segs;
+    bool open = false;
+    void start(cudaStream_t st)
+    {
+        if (open) return;
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        cudaEventRecord(a, st);
+        segs.emplace_back(a, b);
+        open = true;
+    }
+    void stop(cudaStream_t st)
+    {
+        if (!open) return;
+        cudaEventRecord(segs.back().second, st);
+        open = false;
+    }
+    // all segments must have completed (the caller has synchronised the stream)
+    float total()
+    {
+        float sum = 0;
+        for (auto &s : segs) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, s.first, s.second) == cudaSuccess) sum += t;
+        }
+        return sum;
+    }
+    void clear()
+    {
+        for (auto &s : segs) {
+            cudaEventDestroy(s.first);
+            cudaEventDestroy(s.second);
+        }
+        segs.clear();
+        open = false;
+    }
+    ~SegTimer() { clear(); }
+};
+static inline void seg_start(SegTimer *t, cudaStream_t st)
+{
+    if (t) t->start(st);
+}
+static inline void seg_stop(SegTimer *t, cudaStream_t st)
+{
+    if (t) t->stop(st);
+}
+
 static void free_index_arrays(DeviceIndex &ix)
 {
     if (ix.entries) cudaFree(ix.entries);
@@ -703,7 +761,7 @@ struct ExtBuildInputs {
 };
 
 static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries, const uint16_t *d_csr_ids,
-                       uint32_t *d_tiles, uint32_t *d_scalar, const ExtBuildInputs &xin)
+                       uint32_t *d_tiles, uint32_t *d_scalar, const ExtBuildInputs &xin, SegTimer *tm = nullptr)
 {
     DeviceIndex &ix = ctx->index;
     front_geometry(ix);
@@ -713,6 +771,7 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
     SHK_CUDA(ctx, d_cnt.alloc(nb));
     SHK_CUDA(ctx, d_cur.alloc(nb));
     SHK_CUDA(ctx, d_rec.alloc(nb + 1));
+    seg_start(tm, st);
     SHK_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, nb * 4, st));
     SHK_CUDA(ctx, cudaMemsetAsync(d_cur.p, 0, nb * 4, st));
     const unsigned blocks_s = (unsigned)((ix.geom.n_sectors + 255) / 256);
@@ -723,8 +782,10 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
         int rc = exclusive_scan(ctx, st, FrontRecordsIn{d_cnt.p}, U32Out{d_rec.p}, nb, d_tiles, d_scalar);
         if (rc) return rc;
         SHK_CUDA(ctx, cudaMemcpyAsync(&n_rec, d_scalar, 4, cudaMemcpyDeviceToHost, st));
+        seg_stop(tm, st);
         SHK_CUDA(ctx, cudaStreamSynchronize(st));
     }
+    seg_stop(tm, st);
     ix.fgeom.n_entries = nb + n_rec;
     if (ix.fgeom.n_entries >= 0x7FFFFFFFull) return fail(ctx, SHK_E_LIMIT, "front table too large");
     const bool ext = ix.info.n_set_bits > 0 && decide_extend(ctx, ix.fgeom.n_entries, xin.total);
@@ -741,6 +802,7 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
         if (rc) return rc;
         SHK_CUDA(ctx, d_anchor.alloc(ix.info.n_set_bits));
         SHK_CUDA(ctx, d_ebits.alloc((xin.total + 31) / 32 + 1));
+        seg_start(tm, st);
         SHK_CUDA(ctx, cudaMemsetAsync(d_anchor.p, 0xFF, ix.info.n_set_bits * 4, st));
         SHK_CUDA(ctx, cudaMemsetAsync(ix.estream, 0, ix.egeom.estream_words * 8, st));
         SHK_CUDA(ctx, cudaMemsetAsync(ix.ref2, 0, ix.egeom.ref2_words * 8, st));
@@ -756,7 +818,9 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
     if (ix.front) cudaFree(ix.front);
     ix.front = nullptr;
     const uint64_t front_bytes = ix.fgeom.n_entries * 16 * ix.fgeom.stride;
+    seg_stop(tm, st);  // cudaFree / cudaMalloc below wait for the device
     SHK_CUDA(ctx, cudaMalloc((void **)&ix.front, front_bytes));
+    seg_start(tm, st);
     SHK_CUDA(ctx, cudaMemsetAsync(ix.front, 0xFF, front_bytes, st));
     if (ix.info.n_set_bits > 0) {
         uint32_t *f32 = reinterpret_cast<uint32_t *>(ix.front);
@@ -766,6 +830,7 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
         ctx->launches += 2;
         SHK_CUDA(ctx, cudaGetLastError());
     }
+    seg_stop(tm, st);
     SHK_CUDA(ctx, cudaStreamSynchronize(st));  // the temporaries die with this scope
     ix.info.front_shift = ix.fgeom.shift;
     ix.info.front_entries = ix.fgeom.n_entries;
@@ -780,7 +845,7 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
 // d_len (n_set + 1 words) receives the final lengths, d_long / d_n_long queue the long lists.
 static int finish_lists(shk_ctx *ctx, cudaStream_t st, uint32_t n_set, const uint32_t *d_tmp_off, uint16_t *d_tmp_ids,
                         uint32_t *d_len, uint32_t *d_long, uint32_t *d_n_long, uint32_t *d_tiles, DevBuf<uint32_t> &d_csr_off,
-                        DevBuf<uint16_t> &d_csr_ids, DevBuf<uint64_t> &d_entries, uint64_t &tot_ids)
+                        DevBuf<uint16_t> &d_csr_ids, DevBuf<uint64_t> &d_entries, uint64_t &tot_ids, SegTimer *tm = nullptr)
 {
     const unsigned blocks_r = (unsigned)(((uint64_t)n_set + 255) / 256);
     SHK_CUDA(ctx, cudaMemsetAsync(d_n_long, 0, 4, st));
@@ -788,7 +853,9 @@ static int finish_lists(shk_ctx *ctx, cudaStream_t st, uint32_t n_set, const uin
     ctx->launches += 1;
     uint32_t h_long = 0;
     SHK_CUDA(ctx, cudaMemcpyAsync(&h_long, d_n_long, 4, cudaMemcpyDeviceToHost, st));
+    seg_stop(tm, st);
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    seg_start(tm, st);
     if (h_long > 0) {
         sort_unique_long_kernel<<<h_long, 256, 0, st>>>(d_tmp_off, d_long, d_tmp_ids, d_len);
         ctx->launches += 1;
@@ -797,11 +864,13 @@ static int finish_lists(shk_ctx *ctx, cudaStream_t st, uint32_t n_set, const uin
     if (rc) return rc;
     uint32_t h_tot = 0;
     SHK_CUDA(ctx, cudaMemcpyAsync(&h_tot, d_csr_off.p + n_set, 4, cudaMemcpyDeviceToHost, st));
+    seg_stop(tm, st);
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
     tot_ids = h_tot;
     if (tot_ids >= 0x7FFFFFFFull)
         return fail(ctx, SHK_E_LIMIT, "total id count overflows the reference's int (bloomfilter.h:130)");
     SHK_CUDA(ctx, d_csr_ids.alloc(tot_ids));
+    seg_start(tm, st);
     finalize_lists_kernel<<<blocks_r, 256, 0, st>>>(d_tmp_off, d_tmp_ids, d_csr_off.p, n_set, d_csr_ids.p, d_entries.p);
     ctx->launches += 1;
     SHK_CUDA(ctx, cudaGetLastError());
@@ -810,16 +879,41 @@ static int finish_lists(shk_ctx *ctx, cudaStream_t st, uint32_t n_set, const uin
 
 template <int MOD>
 static void launch_enum(shk_ctx *ctx, cudaStream_t st, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec,
-                        uint64_t total, uint64_t *win_pos, uint32_t *has_window, unsigned long long *n_windows)
+                        uint64_t lo, uint64_t hi, uint64_t *win_pos, uint32_t *has_window, unsigned long long *n_windows)
 {
-    uint64_t threads = (total + kPosPerThread - 1) / kPosPerThread;
+    uint64_t threads = (hi - lo + kPosPerThread - 1) / kPosPerThread;
     unsigned blocks = (unsigned)((threads + 255) / 256);
-    enum_setbits_kernel<MOD><<<blocks, 256, 0, st>>>(bases, rec_off, n_rec, total, (int)ctx->params.k, ctx->index.geom,
+    enum_setbits_kernel<MOD><<<blocks, 256, 0, st>>>(bases, rec_off, n_rec, lo, hi, (int)ctx->params.k, ctx->index.geom,
                                                       ctx->index.sectors, win_pos, has_window, n_windows);
     ctx->launches += 1;
 }
 
-int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_rec)
+// Device state of one build.  It lives on the stack of index_build_device for the one-call build
+// and in shk_ctx::shard between the calls of the sharded protocol.
+struct BuildState {
+    DevBuf<uint8_t> bases;
+    DevBuf<uint64_t> rec_off, win;  // win[e]: bit index (pass 1) / rank (pass 2) of the window ending at e
+    DevBuf<uint32_t> has, nidx, scalars, tiles;
+    DevBuf<unsigned long long> nwin;
+    uint64_t total = 0;
+    uint32_t n_rec = 0;
+    uint64_t lo = 0, hi = 0;  // window ends this context enumerates itself
+    uint32_t n_genes = 0, n_set = 0;
+    unsigned long long n_windows = 0;
+    SegTimer tm;
+    double t_wall0 = 0;
+};
+
+static double wall_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// Pass 1 over the window ends [lo, hi) of the reference (KmerBuilder + BloomfilterFiller + BF::add_at).
+static int build_pass1(shk_ctx *ctx, BuildState &bs, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_rec,
+                       uint64_t lo, uint64_t hi)
 {
     DeviceIndex &ix = ctx->index;
     cudaStream_t st = ctx->build_stream;
@@ -828,63 +922,104 @@ int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *r
     for (uint32_t i = 0; i < n_rec; ++i)
         if (rec_off[i + 1] < rec_off[i]) return fail(ctx, SHK_E_ARG, "rec_offsets must be non-decreasing");
     free_index_arrays(ix);
+    bs.t_wall0 = wall_ms();
+    bs.total = total, bs.n_rec = n_rec, bs.lo = lo, bs.hi = hi;
     const uint64_t sector_bytes = ix.geom.n_sectors * 32;
-
-    cudaEvent_t e0, e1;
-    SHK_CUDA(ctx, cudaEventCreate(&e0));
-    SHK_CUDA(ctx, cudaEventCreate(&e1));
-    SHK_CUDA(ctx, cudaEventRecord(e0, st));
-
-    DevBuf<uint8_t> d_bases;
-    DevBuf<uint64_t> d_rec_off, d_win;
-    DevBuf<uint32_t> d_has, d_nidx, d_scalars, d_tiles;
-    DevBuf<unsigned long long> d_nwin;
-    SHK_CUDA(ctx, d_bases.alloc(total));
-    SHK_CUDA(ctx, d_rec_off.alloc((uint64_t)n_rec + 1));
-    SHK_CUDA(ctx, d_win.alloc(total));
-    SHK_CUDA(ctx, d_has.alloc(n_rec));
-    SHK_CUDA(ctx, d_nidx.alloc(n_rec));
-    SHK_CUDA(ctx, d_scalars.alloc(8));  // 0 n_genes, 1 n_set, 2 n_occ, 3 tot_ids, 4 n_long
-    SHK_CUDA(ctx, d_nwin.alloc(1));
+    SHK_CUDA(ctx, bs.bases.alloc(total));
+    SHK_CUDA(ctx, bs.rec_off.alloc((uint64_t)n_rec + 1));
+    SHK_CUDA(ctx, bs.win.alloc(total));
+    SHK_CUDA(ctx, bs.has.alloc(n_rec));
+    SHK_CUDA(ctx, bs.nidx.alloc(n_rec));
+    SHK_CUDA(ctx, bs.scalars.alloc(8));  // 0 n_genes, 1 n_set, 2 n_occ, 3 tot_ids, 4 n_long
+    SHK_CUDA(ctx, bs.nwin.alloc(1));
     uint64_t max_scan_n = std::max<uint64_t>(ix.geom.n_sectors, total + 1);
-    SHK_CUDA(ctx, d_tiles.alloc(max_scan_n / kScanTile + 2));
-    SHK_CUDA(ctx, cudaMemcpyAsync(d_bases.p, ref_bases, total, cudaMemcpyHostToDevice, st));
-    SHK_CUDA(ctx, cudaMemcpyAsync(d_rec_off.p, rec_off, ((uint64_t)n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    SHK_CUDA(ctx, bs.tiles.alloc(max_scan_n / kScanTile + 2));
+    bs.tm.start(st);
+    SHK_CUDA(ctx, cudaMemcpyAsync(bs.bases.p, ref_bases, total, cudaMemcpyHostToDevice, st));
+    SHK_CUDA(ctx, cudaMemcpyAsync(bs.rec_off.p, rec_off, ((uint64_t)n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
     SHK_CUDA(ctx, cudaMemsetAsync(ix.sectors, 0, sector_bytes, st));
-    SHK_CUDA(ctx, cudaMemsetAsync(d_has.p, 0, std::max<uint64_t>(n_rec, 1) * 4, st));
-    SHK_CUDA(ctx, cudaMemsetAsync(d_scalars.p, 0, 8 * 4, st));
-    SHK_CUDA(ctx, cudaMemsetAsync(d_nwin.p, 0, 8, st));
-
-    // pass 1
-    if (total > 0) {
+    SHK_CUDA(ctx, cudaMemsetAsync(bs.has.p, 0, std::max<uint64_t>(n_rec, 1) * 4, st));
+    SHK_CUDA(ctx, cudaMemsetAsync(bs.scalars.p, 0, 8 * 4, st));
+    SHK_CUDA(ctx, cudaMemsetAsync(bs.nwin.p, 0, 8, st));
+    if (hi > lo) {
         switch (ix.geom.mod_kind) {
-        case MOD_POW2: launch_enum<MOD_POW2>(ctx, st, d_bases.p, d_rec_off.p, n_rec, total, d_win.p, d_has.p, d_nwin.p); break;
-        case MOD_B33: launch_enum<MOD_B33>(ctx, st, d_bases.p, d_rec_off.p, n_rec, total, d_win.p, d_has.p, d_nwin.p); break;
-        default: launch_enum<MOD_GENERIC>(ctx, st, d_bases.p, d_rec_off.p, n_rec, total, d_win.p, d_has.p, d_nwin.p); break;
+        case MOD_POW2: launch_enum<MOD_POW2>(ctx, st, bs.bases.p, bs.rec_off.p, n_rec, lo, hi, bs.win.p, bs.has.p, bs.nwin.p); break;
+        case MOD_B33: launch_enum<MOD_B33>(ctx, st, bs.bases.p, bs.rec_off.p, n_rec, lo, hi, bs.win.p, bs.has.p, bs.nwin.p); break;
+        default: launch_enum<MOD_GENERIC>(ctx, st, bs.bases.p, bs.rec_off.p, n_rec, lo, hi, bs.win.p, bs.has.p, bs.nwin.p); break;
         }
         SHK_CUDA(ctx, cudaGetLastError());
     }
-    assign_nidx_kernel<<<1, 1024, 0, st>>>(d_rec_off.p, d_has.p, n_rec, (int)ctx->params.k, d_nidx.p, d_scalars.p + 0);
+    return SHK_OK;
+}
+
+// `nidx` of every record (main.cpp:158-187) and BF::switch_mode(1): the rank directory and num_kmer
+// (bloomfilter.h:121-122).  Needs the complete filter and the complete window flags.
+static int build_rank(shk_ctx *ctx, BuildState &bs)
+{
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    bs.tm.start(st);
+    assign_nidx_kernel<<<1, 1024, 0, st>>>(bs.rec_off.p, bs.has.p, bs.n_rec, (int)ctx->params.k, bs.nidx.p, bs.scalars.p + 0);
     ctx->launches += 1;
-    // switch_mode(1): rank directory (bloomfilter.h:121-122)
-    int rc = exclusive_scan(ctx, st, SectorPopIn{ix.sectors}, SectorRankOut{ix.sectors}, ix.geom.n_sectors, d_tiles.p,
-                            d_scalars.p + 1);
+    int rc = exclusive_scan(ctx, st, SectorPopIn{ix.sectors}, SectorRankOut{ix.sectors}, ix.geom.n_sectors, bs.tiles.p,
+                            bs.scalars.p + 1);
     if (rc) return rc;
     uint32_t h_scalars[8];
-    unsigned long long h_nwin = 0;
-    SHK_CUDA(ctx, cudaMemcpyAsync(h_scalars, d_scalars.p, sizeof h_scalars, cudaMemcpyDeviceToHost, st));
-    SHK_CUDA(ctx, cudaMemcpyAsync(&h_nwin, d_nwin.p, 8, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaMemcpyAsync(h_scalars, bs.scalars.p, sizeof h_scalars, cudaMemcpyDeviceToHost, st));
+    SHK_CUDA(ctx, cudaMemcpyAsync(&bs.n_windows, bs.nwin.p, 8, cudaMemcpyDeviceToHost, st));
+    bs.tm.stop(st);
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint32_t n_genes = h_scalars[0];
-    const uint32_t n_set = h_scalars[1];
-    if (n_genes > 65536)
+    bs.n_genes = h_scalars[0];
+    bs.n_set = h_scalars[1];
+    if (bs.n_genes > 65536)
         return fail(ctx, SHK_E_LIMIT,
                     "%u gene indices: the reference stores gene ids in 16 bits (small_vector.hpp:46), "
                     "more than 65536 is not supported",
-                    n_genes);
-    if (n_set >= 0x7FFFFFFFu || h_nwin >= 0xFFFFFFFFull) return fail(ctx, SHK_E_LIMIT, "too many set bits / windows");
+                    bs.n_genes);
+    if (bs.n_set >= 0x7FFFFFFFu || bs.n_windows >= 0xFFFFFFFFull)
+        return fail(ctx, SHK_E_LIMIT, "too many set bits / windows");
+    return SHK_OK;
+}
 
-    // pass 2
+// Sharded build: bit index -> rank for this context's own window ends only (no counting yet).
+__global__ void __launch_bounds__(256)
+rank_convert_kernel(uint64_t *win_pos, uint64_t lo, uint64_t hi, const uint32_t *__restrict__ sectors)
+{
+    uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= hi) return;
+    uint64_t p = win_pos[x];
+    if (p == kInvalidPos) return;
+    uint64_t q = p >> 5;
+    uint64_t sec = q / kWordsPerSector;
+    uint32_t slot = (uint32_t)(q - sec * kWordsPerSector);
+    const uint4 *sp = reinterpret_cast<const uint4 *>(sectors + sec * 8);
+    uint4 a = sp[0], b = sp[1];
+    Sector s;
+    s.w[0] = a.x, s.w[1] = a.y, s.w[2] = a.z, s.w[3] = a.w, s.w[4] = b.x, s.w[5] = b.y, s.w[6] = b.z, s.w[7] = b.w;
+    win_pos[x] = sector_rank(s, slot, (uint32_t)(p & 31));
+}
+
+// Sharded build: occurrences per rank over the gathered window array (+ the number of windows).
+__global__ void __launch_bounds__(256)
+count_ranks_kernel(const uint64_t *__restrict__ win, uint64_t total, uint32_t *cnt, unsigned long long *n_windows)
+{
+    uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t v = x < total ? win[x] : kInvalidPos;
+    const bool valid = v != kInvalidPos;
+    if (valid) atomicAdd(&cnt[(uint32_t)v], 1u);
+    uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(n_windows, (unsigned long long)n);
+}
+
+// Pass 2 (main.cpp:154-189 -> BF::add_to_kmer), BF::switch_mode(2), front table, info.
+// win_is_rank: the window array already holds ranks (sharded build, gathered from all shards).
+static int build_lists(shk_ctx *ctx, BuildState &bs, bool win_is_rank)
+{
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    const uint64_t total = bs.total;
+    const uint32_t n_set = bs.n_set;
+    int rc;
     DevBuf<uint32_t> d_cnt, d_fill, d_tmp_off, d_long;
     DevBuf<uint16_t> d_tmp_ids;
     DevBuf<uint32_t> d_csr_off;
@@ -894,59 +1029,340 @@ int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *r
     SHK_CUDA(ctx, d_fill.alloc((uint64_t)n_set + 1));
     SHK_CUDA(ctx, d_tmp_off.alloc((uint64_t)n_set + 1));
     SHK_CUDA(ctx, d_long.alloc((uint64_t)n_set + 1));
-    SHK_CUDA(ctx, d_tmp_ids.alloc(h_nwin + 1));
+    // the sharded build learns the total number of windows only while counting: one id per position bounds it
+    SHK_CUDA(ctx, d_tmp_ids.alloc((win_is_rank ? total : bs.n_windows) + 1));
     SHK_CUDA(ctx, d_csr_off.alloc((uint64_t)n_set + 1));
     SHK_CUDA(ctx, d_entries.alloc((uint64_t)n_set + 1));
+    bs.tm.start(st);
     SHK_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, ((uint64_t)n_set + 1) * 4, st));
     SHK_CUDA(ctx, cudaMemsetAsync(d_fill.p, 0, ((uint64_t)n_set + 1) * 4, st));
     uint64_t tot_ids = 0;
     if (n_set > 0) {
         unsigned blocks_x = (unsigned)((total + 255) / 256);
-        rank_count_kernel<<<blocks_x, 256, 0, st>>>(d_win.p, total, ix.sectors, d_cnt.p);
+        if (win_is_rank) {
+            SHK_CUDA(ctx, cudaMemsetAsync(bs.nwin.p, 0, 8, st));
+            count_ranks_kernel<<<blocks_x, 256, 0, st>>>(bs.win.p, total, d_cnt.p, bs.nwin.p);
+            SHK_CUDA(ctx, cudaMemcpyAsync(&bs.n_windows, bs.nwin.p, 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            rank_count_kernel<<<blocks_x, 256, 0, st>>>(bs.win.p, total, ix.sectors, d_cnt.p);
+        }
         ctx->launches += 1;
-        rc = exclusive_scan(ctx, st, U32In{d_cnt.p}, U32Out{d_tmp_off.p}, (uint64_t)n_set, d_tiles.p, d_tmp_off.p + n_set);
+        rc = exclusive_scan(ctx, st, U32In{d_cnt.p}, U32Out{d_tmp_off.p}, (uint64_t)n_set, bs.tiles.p, d_tmp_off.p + n_set);
         if (rc) return rc;
-        fill_kernel<<<blocks_x, 256, 0, st>>>(d_win.p, total, d_rec_off.p, n_rec, d_nidx.p, d_tmp_off.p, d_fill.p,
+        fill_kernel<<<blocks_x, 256, 0, st>>>(bs.win.p, total, bs.rec_off.p, bs.n_rec, bs.nidx.p, d_tmp_off.p, d_fill.p,
                                               d_tmp_ids.p);
         ctx->launches += 1;
-        rc = finish_lists(ctx, st, n_set, d_tmp_off.p, d_tmp_ids.p, d_fill.p, d_long.p, d_scalars.p + 4, d_tiles.p, d_csr_off,
-                          d_csr_ids, d_entries, tot_ids);
+        rc = finish_lists(ctx, st, n_set, d_tmp_off.p, d_tmp_ids.p, d_fill.p, d_long.p, bs.scalars.p + 4, bs.tiles.p, d_csr_off,
+                          d_csr_ids, d_entries, tot_ids, &bs.tm);
         if (rc) return rc;
     } else {
         SHK_CUDA(ctx, cudaMemsetAsync(d_csr_off.p, 0, 4, st));
+        bs.tm.stop(st);
         SHK_CUDA(ctx, d_csr_ids.alloc(1));
     }
+    bs.tm.stop(st);
     // front table over the finished entries
     ix.info.n_set_bits = n_set;
     {
         uint64_t need_tiles = (((ix.geom.bf_bits + 31) >> 5) + kScanTile - 1) / kScanTile + 2;
         DevBuf<uint32_t> d_tiles2;
         SHK_CUDA(ctx, d_tiles2.alloc(need_tiles));
-        rc = build_front(ctx, st, d_entries.p, d_csr_ids.p, d_tiles2.p, d_scalars.p + 5,
-                         ExtBuildInputs{d_bases.p, d_win.p, total});
+        rc = build_front(ctx, st, d_entries.p, d_csr_ids.p, d_tiles2.p, bs.scalars.p + 5,
+                         ExtBuildInputs{bs.bases.p, bs.win.p, total}, &bs.tm);
         if (rc) return rc;
     }
-    SHK_CUDA(ctx, cudaEventRecord(e1, st));
+    bs.tm.stop(st);
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    if (bs.n_windows >= 0xFFFFFFFFull) return fail(ctx, SHK_E_LIMIT, "too many windows");
 
     ix.entries = d_entries.release();
     ix.csr_off = d_csr_off.release();
     ix.csr_ids = d_csr_ids.release();
-    ix.info.n_records = n_rec;
-    ix.info.n_genes = n_genes;
+    ix.info.n_records = bs.n_rec;
+    ix.info.n_genes = bs.n_genes;
     ix.info.n_set_bits = n_set;
     ix.info.tot_ids = tot_ids;
-    ix.info.n_windows = h_nwin;
+    ix.info.n_windows = bs.n_windows;
     ix.info.bf_bits = ix.geom.bf_bits;
-    ix.info.device_bytes = sector_bytes + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2 +
+    ix.info.device_bytes = ix.geom.n_sectors * 32 + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2 +
                            ix.fgeom.n_entries * 16 * ix.fgeom.stride +
                            (ix.egeom.enabled ? ix.egeom.estream_words * 8 + ix.egeom.ref2_words * 8 + ix.egeom.coarse_words * 4 : 0);
-    ix.info.build_ms = ms;
+    ix.info.build_ms = bs.tm.total();
+    ix.info.build_wall_ms = (float)(wall_ms() - bs.t_wall0);
     ix.built = true;
+    return SHK_OK;
+}
+
+int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_rec)
+{
+    BuildState bs;
+    int rc = build_pass1(ctx, bs, ref_bases, rec_off, n_rec, 0, rec_off[n_rec]);
+    if (rc) return rc;
+    if ((rc = build_rank(ctx, bs)) != 0) return rc;
+    if ((rc = build_lists(ctx, bs, false)) != 0) return rc;
+    ctx->index.info.n_shards = 1;
+    return SHK_OK;
+}
+
+// =============================================================================================
+// Sharded build (second mode): every context enumerates the windows of one shard of
+// the reference records into its own filter; the filters are OR-merged with a P2P kernel (slice
+// reduce, then slice gather: each context reads 2 (n-1)/n of a filter over NVLink instead of n-1
+// filters); every context then builds the same rank directory, converts its own windows to ranks,
+// gathers the other shards' ranks (disjoint position ranges) and finishes pass 2 locally.  The
+// result is the index of the one-call build, on every context.  The caller provides the barriers
+// between the steps (every call returns with its device work finished).
+// =============================================================================================
+struct ShardBuild {
+    BuildState bs;
+    uint32_t shard = 0, n_shards = 0;
+    std::vector<uint64_t> cut;  // n_shards + 1 position cuts (record boundaries)
+    int step = 0;               // 1 begun, 2 merged (phase 1), 3 merged (phase 2), 4 ranked
+};
+
+constexpr int kMaxShards = 16;
+struct PeerVecs {
+    const uint4 *p[kMaxShards];
+    int n;
+};
+
+// local[i] |= peer[i] for every peer, i in [v0, v1) (128-bit words).  Peers do not write this
+// slice while it runs (they reduce their own slices).
+__global__ void __launch_bounds__(256)
+or_merge_kernel(uint4 *__restrict__ local, PeerVecs peers, uint64_t v0, uint64_t v1)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += stride) {
+        uint4 v = local[i];
+        for (int j = 0; j < peers.n; ++j) {
+            const uint4 t = peers.p[j][i];
+            v.x |= t.x, v.y |= t.y, v.z |= t.z, v.w |= t.w;
+        }
+        local[i] = v;
+    }
+}
+
+// dst[i] = src[i] over NVLink (or within the device), i in [v0, v1)
+__global__ void __launch_bounds__(256)
+p2p_gather_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint64_t v0, uint64_t v1)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += stride) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256)
+p2p_gather_u64_kernel(uint64_t *__restrict__ dst, const uint64_t *__restrict__ src, uint64_t lo, uint64_t hi)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) dst[i] = src[i];
+}
+
+struct PeerFlags {
+    const uint32_t *p[kMaxShards];
+    int n;
+};
+__global__ void __launch_bounds__(256) or_flags_kernel(uint32_t *local, PeerFlags peers, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = local[i];
+    for (int j = 0; j < peers.n; ++j) v |= peers.p[j][i];
+    local[i] = v;
+}
+
+void shard_free(shk_ctx *ctx)
+{
+    delete ctx->shard;
+    ctx->shard = nullptr;
+}
+
+// Position cuts at record boundaries, balanced by bases: cut[s] = the record boundary nearest to
+// s * total / n.  A pure function of the offsets: identical on every rank.
+static void shard_cuts(const uint64_t *rec_off, uint32_t n_rec, uint32_t n_shards, std::vector<uint64_t> &cut)
+{
+    const uint64_t total = rec_off[n_rec];
+    cut.assign(n_shards + 1, total);
+    cut[0] = 0;
+    for (uint32_t s = 1; s < n_shards; ++s) {
+        const uint64_t want = (uint64_t)((unsigned __int128)total * s / n_shards);
+        const uint64_t *it = std::lower_bound(rec_off, rec_off + n_rec + 1, want);  // *it >= want
+        uint64_t c = *it;
+        if (it != rec_off && want - it[-1] < c - want) c = it[-1];  // the nearer boundary
+        cut[s] = std::max(c, cut[s - 1]);
+    }
+}
+
+void shard_cuts_host(const uint64_t *rec_off, uint32_t n_rec, uint32_t n_shards, uint64_t *cuts)
+{
+    std::vector<uint64_t> c;
+    shard_cuts(rec_off, n_rec, n_shards, c);
+    std::copy(c.begin(), c.end(), cuts);
+}
+
+static void enable_peer(int from_dev, int to_dev)
+{
+    if (from_dev == to_dev) return;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, from_dev, to_dev) == cudaSuccess && can) cudaDeviceEnablePeerAccess(to_dev, 0);
+    cudaGetLastError();  // "already enabled" is fine
+}
+
+int shard_begin(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_rec, uint32_t shard,
+                uint32_t n_shards, shk_shard_mem *mine)
+{
+    if (n_shards == 0 || n_shards > (uint32_t)kMaxShards || shard >= n_shards)
+        return fail(ctx, SHK_E_ARG, "shard %u of %u: at most %d shards", shard, n_shards, kMaxShards);
+    shard_free(ctx);
+    ctx->shard = new (std::nothrow) ShardBuild;
+    if (!ctx->shard) return fail(ctx, SHK_E_NOMEM, "out of host memory");
+    ShardBuild &sb = *ctx->shard;
+    sb.shard = shard, sb.n_shards = n_shards;
+    shard_cuts(rec_off, n_rec, n_shards, sb.cut);
+    int rc = build_pass1(ctx, sb.bs, ref_bases, rec_off, n_rec, sb.cut[shard], sb.cut[shard + 1]);
+    if (rc) return rc;
+    cudaStream_t st = ctx->build_stream;
+    sb.bs.tm.stop(st);
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    memset(mine, 0, sizeof *mine);
+    mine->dev_ptr[0] = ctx->index.sectors;
+    mine->dev_ptr[1] = sb.bs.win.p;
+    mine->dev_ptr[2] = sb.bs.has.p;
+    mine->device = ctx->device;
+    mine->shard = shard;
+    mine->pid = (int64_t)getpid();
+    mine->ipc_ok = 1;
+    for (int i = 0; i < 3; ++i) {
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, mine->dev_ptr[i]) != cudaSuccess) {
+            cudaGetLastError();
+            mine->ipc_ok = 0;  // same-process peers still work through dev_ptr
+            break;
+        }
+        static_assert(sizeof h == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(mine->ipc_handle[i], &h, 64);
+    }
+    sb.step = 1;
+    return SHK_OK;
+}
+
+int shard_open(shk_ctx *ctx, const shk_shard_mem *peer, shk_shard_mem *opened)
+{
+    *opened = *peer;
+    if (peer->pid == (int64_t)getpid()) {  // same process: the pointers are usable as they are
+        enable_peer(ctx->device, peer->device);
+        return SHK_OK;
+    }
+    if (!peer->ipc_ok) return fail(ctx, SHK_E_CUDA, "shard %u exported no CUDA IPC handles", peer->shard);
+    for (int i = 0; i < 3; ++i) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, peer->ipc_handle[i], 64);
+        void *p = nullptr;
+        SHK_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        opened->dev_ptr[i] = p;
+    }
+    opened->pid = -(int64_t)getpid();  // marks pointers that shk_shard_close must release
+    return SHK_OK;
+}
+
+int shard_close(shk_ctx *ctx, shk_shard_mem *opened)
+{
+    if (opened->pid != -(int64_t)getpid()) return SHK_OK;
+    for (int i = 0; i < 3; ++i)
+        if (opened->dev_ptr[i]) {
+            cudaIpcCloseMemHandle(opened->dev_ptr[i]);
+            opened->dev_ptr[i] = nullptr;
+        }
+    cudaGetLastError();
+    opened->pid = 0;
+    return SHK_OK;
+}
+
+int shard_merge(shk_ctx *ctx, int phase, const shk_shard_mem *all)
+{
+    ShardBuild *sbp = ctx->shard;
+    if (!sbp || sbp->step != phase) return fail(ctx, SHK_E_STATE, "shk_shard_merge(%d) out of order", phase);
+    ShardBuild &sb = *sbp;
+    DeviceIndex &ix = ctx->index;
+    cudaStream_t st = ctx->build_stream;
+    const uint32_t n = sb.n_shards, me = sb.shard;
+    const uint64_t n_vec = ix.geom.n_sectors * 2;  // 128-bit words of the filter
+    auto slice = [&](uint32_t s) { return (uint64_t)((unsigned __int128)n_vec * s / n); };
+    const unsigned blocks = (unsigned)ctx->sm_count * 8;
+    uint4 *local = reinterpret_cast<uint4 *>(ix.sectors);
+    sb.bs.tm.start(st);
+    if (phase == 1) {
+        PeerVecs pv{};
+        PeerFlags pf{};
+        for (uint32_t s = 0; s < n; ++s) {
+            if (s == me) continue;
+            pv.p[pv.n++] = reinterpret_cast<const uint4 *>(all[s].dev_ptr[0]);
+            pf.p[pf.n++] = reinterpret_cast<const uint32_t *>(all[s].dev_ptr[2]);
+        }
+        if (pv.n && slice(me + 1) > slice(me)) {
+            or_merge_kernel<<<blocks, 256, 0, st>>>(local, pv, slice(me), slice(me + 1));
+            ctx->launches += 1;
+        }
+        // window flags: records belong to exactly one shard, the OR over all shards is the full array
+        if (pf.n && sb.bs.n_rec) {
+            or_flags_kernel<<<(sb.bs.n_rec + 255) / 256, 256, 0, st>>>(sb.bs.has.p, pf, sb.bs.n_rec);
+            ctx->launches += 1;
+        }
+    } else {
+        for (uint32_t s = 0; s < n; ++s) {
+            if (s == me || slice(s + 1) <= slice(s)) continue;
+            p2p_gather_kernel<<<blocks, 256, 0, st>>>(local, reinterpret_cast<const uint4 *>(all[s].dev_ptr[0]), slice(s),
+                                                      slice(s + 1));
+            ctx->launches += 1;
+        }
+    }
+    SHK_CUDA(ctx, cudaGetLastError());
+    sb.bs.tm.stop(st);
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    sb.step = phase + 1;
+    return SHK_OK;
+}
+
+int shard_rank(shk_ctx *ctx)
+{
+    ShardBuild *sbp = ctx->shard;
+    if (!sbp || sbp->step != 3) return fail(ctx, SHK_E_STATE, "shk_shard_rank out of order");
+    ShardBuild &sb = *sbp;
+    int rc = build_rank(ctx, sb.bs);
+    if (rc) return rc;
+    cudaStream_t st = ctx->build_stream;
+    if (sb.bs.hi > sb.bs.lo && sb.bs.n_set > 0) {
+        sb.bs.tm.start(st);
+        rank_convert_kernel<<<(unsigned)((sb.bs.hi - sb.bs.lo + 255) / 256), 256, 0, st>>>(sb.bs.win.p, sb.bs.lo, sb.bs.hi,
+                                                                                          ctx->index.sectors);
+        ctx->launches += 1;
+        SHK_CUDA(ctx, cudaGetLastError());
+        sb.bs.tm.stop(st);
+        SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    sb.step = 4;
+    return SHK_OK;
+}
+
+int shard_finish(shk_ctx *ctx, const shk_shard_mem *all)
+{
+    ShardBuild *sbp = ctx->shard;
+    if (!sbp || sbp->step != 4) return fail(ctx, SHK_E_STATE, "shk_shard_finish out of order");
+    ShardBuild &sb = *sbp;
+    cudaStream_t st = ctx->build_stream;
+    const unsigned blocks = (unsigned)ctx->sm_count * 8;
+    sb.bs.tm.start(st);
+    for (uint32_t s = 0; s < sb.n_shards; ++s) {
+        if (s == sb.shard || sb.cut[s + 1] <= sb.cut[s]) continue;
+        p2p_gather_u64_kernel<<<blocks, 256, 0, st>>>(sb.bs.win.p, reinterpret_cast<const uint64_t *>(all[s].dev_ptr[1]),
+                                                      sb.cut[s], sb.cut[s + 1]);
+        ctx->launches += 1;
+    }
+    SHK_CUDA(ctx, cudaGetLastError());
+    sb.bs.tm.stop(st);  // build_lists allocates first; the gathers run meanwhile
+    int rc = build_lists(ctx, sb.bs, true);
+    if (rc) return rc;
+    ctx->index.info.n_shards = sb.n_shards;
+    sb.step = 5;
     return SHK_OK;
 }
 

@@ -140,9 +140,14 @@ struct StagedBuild {
 };
 }  // namespace shk
 
+namespace shk {
+struct ShardBuild;  // sharded build state (shk_index.cu)
+}
+
 struct shk_ctx {
     shk_params params{};
     shk::StagedBuild staged;
+    shk::ShardBuild *shard = nullptr;
     int device = 0;
     int sm_count = 148;
     shk::DeviceIndex index;
@@ -186,6 +191,16 @@ int staged_add_at(shk_ctx *ctx, const uint64_t *positions, uint64_t n);
 int staged_switch_mode(shk_ctx *ctx, int new_mode, uint64_t *n_set_bits);
 int staged_add_to_kmer(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t input_idx);
 void staged_free(shk_ctx *ctx);
+// sharded build (SURVEY.md 8e second mode)
+int shard_begin(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_rec, uint32_t shard,
+                uint32_t n_shards, shk_shard_mem *mine);
+int shard_open(shk_ctx *ctx, const shk_shard_mem *peer, shk_shard_mem *opened);
+int shard_close(shk_ctx *ctx, shk_shard_mem *opened);
+int shard_merge(shk_ctx *ctx, int phase, const shk_shard_mem *all);
+int shard_rank(shk_ctx *ctx);
+int shard_finish(shk_ctx *ctx, const shk_shard_mem *all);
+void shard_free(shk_ctx *ctx);
+void shard_cuts_host(const uint64_t *rec_off, uint32_t n_rec, uint32_t n_shards, uint64_t *cuts);
 
 // shk_reads.cu
 // Enqueues the classification kernels of one chunk on `st`; returns the number of launches.

@@ -74,3 +74,48 @@ def broadcast_index(sh, src=0):
     if rank != src:
         sh.finalize_index()
     return e0.elapsed_time(e1)
+
+
+def shard_cuts(rec_off, n_shards):
+    """Position cuts of the sharded build (shk_shard_cuts): shard s owns window ends [cuts[s], cuts[s+1])."""
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+    cuts = np.zeros(n_shards + 1, np.uint64)
+    rc = capi.load().shk_shard_cuts(capi.ptr(rec_off), len(rec_off) - 1, n_shards, capi.ptr(cuts))
+    if rc:
+        raise capi.SharkError(rc, capi.load().shk_last_error(None).decode())
+    return cuts
+
+
+def build_index_sharded(sh, bases, rec_off, barrier=None, all_gather=None):
+    """Sharded index build, one process per GPU (SURVEY.md 8e second mode): rank r enumerates the
+    k-mers of record shard r into its own filter, the filters are OR-merged by the library's P2P
+    kernel over NVLink (peer buffers mapped through CUDA IPC handles that travel as bytes over
+    torch.distributed), then every rank finishes the same index locally.  torch.distributed only
+    carries the 256-byte handle structs and the barriers.  Returns (info, wall seconds)."""
+    import time
+    barrier = barrier or dist.barrier
+    rank, world = dist.get_rank(), dist.get_world_size()
+    t0 = time.perf_counter()
+    mine = sh.shard_begin(bases, rec_off, rank, world)
+    blobs = [None] * world
+    (all_gather or dist.all_gather_object)(blobs, bytes(mine))
+    arr = (capi.ShardMem * world)()
+    for s in range(world):
+        peer = capi.ShardMem.from_buffer_copy(blobs[s])
+        if peer.shard != s:
+            raise capi.SharkError(-3, "shard structs arrived out of order")
+        arr[s] = mine if s == rank else sh.shard_open(peer)
+    barrier()
+    sh.shard_merge(1, arr)
+    barrier()
+    sh.shard_merge(2, arr)
+    sh.shard_rank()
+    barrier()
+    info = sh.shard_finish(arr)
+    barrier()
+    for s in range(world):
+        if s != rank:
+            sh.shard_close(arr[s])
+    barrier()  # nobody frees a buffer that a peer still has mapped
+    sh.shard_end()
+    return info, time.perf_counter() - t0

@@ -73,6 +73,65 @@ class Shark:
         self.info = info
         return info
 
+    # -- sharded build (SURVEY.md 8e second mode): per-GPU gene shards + P2P OR-merge ---------
+    def shard_begin(self, bases, rec_off, shard, n_shards):
+        """Pass 1 over this context's shard of the records -> capi.ShardMem (exchange it with the peers)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        mem = capi.ShardMem()
+        self._check(self.lib.shk_shard_begin(self.ctx, capi.ptr(bases) if len(bases) else None, capi.ptr(rec_off),
+                                             len(rec_off) - 1, shard, n_shards, C.byref(mem)))
+        return mem
+
+    def shard_open(self, peer):
+        opened = capi.ShardMem()
+        self._check(self.lib.shk_shard_open(self.ctx, C.byref(peer), C.byref(opened)))
+        return opened
+
+    def shard_close(self, opened):
+        self._check(self.lib.shk_shard_close(self.ctx, C.byref(opened)))
+
+    def shard_merge(self, phase, all_mem):
+        self._check(self.lib.shk_shard_merge(self.ctx, phase, all_mem))
+
+    def shard_rank(self):
+        self._check(self.lib.shk_shard_rank(self.ctx))
+
+    def shard_finish(self, all_mem):
+        info = capi.IndexInfo()
+        self._check(self.lib.shk_shard_finish(self.ctx, all_mem, C.byref(info)))
+        self.info = info
+        return info
+
+    def shard_end(self):
+        self._check(self.lib.shk_shard_end(self.ctx))
+
+    @staticmethod
+    def build_index_sharded(sharks, bases, rec_off):
+        """The whole sharded protocol for several contexts of this process (shk_index_build_sharded)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        arr = (C.c_void_p * len(sharks))(*[s.ctx for s in sharks])
+        info = capi.IndexInfo()
+        rc = sharks[0].lib.shk_index_build_sharded(arr, len(sharks), capi.ptr(bases) if len(bases) else None,
+                                                   capi.ptr(rec_off), len(rec_off) - 1, C.byref(info))
+        sharks[0]._check(rc)
+        for s in sharks:
+            i = capi.IndexInfo()
+            s._check(s.lib.shk_index_info_get(s.ctx, C.byref(i)))
+            s.info = i
+        return info
+
+    # -- index serialisation ------------------------------------------------------------------
+    def save_index(self, path):
+        self._check(self.lib.shk_index_save(self.ctx, str(path).encode()))
+
+    def load_index(self, path):
+        info = capi.IndexInfo()
+        self._check(self.lib.shk_index_load(self.ctx, str(path).encode(), C.byref(info)))
+        self.info = info
+        return info
+
     # -- staged build: the reference's functor protocol (KmerBuilder / BloomfilterFiller / class BF) --
     def kmer_hashes(self, bases, rec_off):
         """KmerBuilder::operator() (KmerBuilder.hpp:40-72) -> uint64 hashes of all canonical k-mers."""

@@ -33,17 +33,18 @@ def test_binding_matches_header(lib_path):
     from shark_b200 import capi
     assert sorted(capi.EXPORTED) == _declared()
     L = capi.load()
-    assert L.shk_abi_version() == 3
+    assert L.shk_abi_version() == 4
 
 
 def test_struct_sizes():
     from shark_b200 import capi
     # must match the C layouts in include/shark_b200.h (x86-64 SysV)
     assert ctypes.sizeof(capi.Params) == 88
-    assert ctypes.sizeof(capi.IndexInfo) == 80
+    assert ctypes.sizeof(capi.IndexInfo) == 88
     assert ctypes.sizeof(capi.Assoc) == 8
     assert ctypes.sizeof(capi.ChunkResult) == 80
-    assert ctypes.sizeof(capi.IndexViews) == 64 + 64 + 80
+    assert ctypes.sizeof(capi.IndexViews) == 64 + 64 + 88
+    assert ctypes.sizeof(capi.ShardMem) == 24 + 192 + 8 + 16
 
 
 def test_no_cpu_fallback(lib_path):

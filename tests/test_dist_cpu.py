@@ -66,6 +66,108 @@ def _worker(rank, world, port, tmp):
     open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
 
 
+class _FakeShark:
+    """Records the sharded-build protocol calls; checks the cross-rank ordering through files:
+    a step may only start when every rank has finished the previous one."""
+
+    def __init__(self, rank, world, tmp):
+        self.rank, self.world, self.tmp = rank, world, tmp
+        self.log = []
+
+    def _done(self, step):
+        open(os.path.join(self.tmp, "%s.%d" % (step, self.rank)), "w").write("x")
+
+    def _need(self, step):
+        for r in range(self.world):
+            assert os.path.exists(os.path.join(self.tmp, "%s.%d" % (step, r))), (step, r, self.rank)
+
+    def shard_begin(self, bases, rec_off, shard, n_shards):
+        from shark_b200 import capi
+        assert (shard, n_shards) == (self.rank, self.world)
+        m = capi.ShardMem(pid=1000 + self.rank, device=self.rank, shard=shard, ipc_ok=1)
+        m.dev_ptr[0] = 0x1000 * (self.rank + 1)
+        self.log.append("begin")
+        self._done("begin")
+        return m
+
+    def shard_open(self, peer):
+        from shark_b200 import capi
+        assert peer.shard != self.rank and peer.pid == 1000 + peer.shard
+        o = capi.ShardMem.from_buffer_copy(bytes(peer))
+        o.pid = -1
+        self.log.append("open%d" % peer.shard)
+        return o
+
+    def shard_merge(self, phase, arr):
+        self._need("begin" if phase == 1 else "merge1")
+        assert [arr[s].shard for s in range(self.world)] == list(range(self.world))
+        assert arr[self.rank].pid == 1000 + self.rank and all(arr[s].pid == -1 for s in range(self.world) if s != self.rank)
+        assert all(arr[s].dev_ptr[0] == 0x1000 * (s + 1) for s in range(self.world))
+        self.log.append("merge%d" % phase)
+        self._done("merge%d" % phase)
+
+    def shard_rank(self):
+        self.log.append("rank")
+        self._done("rank")
+
+    def shard_finish(self, arr):
+        from shark_b200 import capi
+        self._need("rank")
+        self.log.append("finish")
+        self._done("finish")
+        return capi.IndexInfo(n_shards=self.world)
+
+    def shard_close(self, opened):
+        self._need("finish")
+        self.log.append("close%d" % opened.shard)
+        self._done("close")
+
+    def shard_end(self):
+        self._need("close")
+        self.log.append("end")
+
+
+def _shard_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from shark_b200 import dist_index
+    sh = _FakeShark(rank, world, tmp)
+    info, secs = dist_index.build_index_sharded(sh, np.zeros(4, np.uint8), np.array([0, 4], np.uint64))
+    assert info.n_shards == world and secs >= 0
+    other = 1 - rank
+    assert sh.log == ["begin", "open%d" % other, "merge1", "merge2", "rank", "finish", "close%d" % other, "end"], sh.log
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
+
+
+def test_sharded_build_protocol_gloo_world2(tmp_path):
+    """Host side of the one-process-per-GPU sharded index build: the handle structs travel as bytes,
+    arrive in shard order, and the barriers separate the steps on every rank."""
+    world = 2
+    mp.spawn(_shard_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def test_shard_cuts_properties():
+    """shk_shard_cuts (pure host): monotone cuts at record boundaries covering [0, total), balanced."""
+    from shark_b200 import dist_index
+    rng = np.random.default_rng(11)
+    for n_rec in (0, 1, 7, 1000):
+        lens = rng.integers(0, 5000, n_rec)
+        rec_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        total = int(rec_off[-1])
+        for n in (1, 2, 3, 8, 16):
+            cuts = dist_index.shard_cuts(rec_off, n)
+            assert len(cuts) == n + 1 and cuts[0] == 0 and cuts[-1] == total
+            assert np.all(np.diff(cuts.astype(np.int64)) >= 0)
+            assert np.all(np.isin(cuts, rec_off))
+            if n_rec == 1000:
+                ideal = total / n
+                assert np.max(np.abs(np.diff(cuts.astype(np.int64)) - ideal)) <= 5000
+
+
 def test_gloo_world2(tmp_path):
     world = 2
     port = _free_port()
