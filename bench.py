@@ -7,13 +7,18 @@ A step = one pass of the hot path over this rank's whole batch of synthetic read
 default: SYN(1000 genes), 10 M single-end 100 bp reads, k=17, 1 GiB Bloom filter).
   value   reads/s with the reads already resident in HBM when the timed region starts
   e2e     reads/s through the public API (Shark.analyze_chunks -> shk_reads_submit/collect) from
-          pinned HOST buffers, H2D and D2H inside the timed region
+          pinned HOST buffers of read TEXT, H2D and D2H inside the timed region.  --upload split (default):
+          shk_reads_submit sends part of every chunk as text and packs the rest to 3 bits per base on the
+          host cores while that copy runs (SHK_F_HOST_PACK; the packing is inside the timed region and the
+          time is max(device stopwatch, host clock)); --upload plain: text only.  The mode not chosen is
+          measured too (e2e_other).
   roofline  analyze_reads_kernel: 32 B x (k-mer windows probed) / its CUDA-event time, against the
           measured HBM copy rate in MEASURED_PEAKS.json (and the measured random-sector ceiling)
   cpu_baseline  the unmodified reference (oracle/_ref/shark -t <cores>) on a bounded prefix of the
           same reads, on this box's host cores
 N > 1: one process per GPU (torchrun); reads are sharded (weak scaling: every rank gets its own
-batch of the same size), the index is built on rank 0 and replicated with an NCCL broadcast.
+batch of the same size), the index is built on rank 0 and replicated with an NCCL broadcast
+(--index sharded|both: every rank indexes one gene shard, filters OR-merged by the library's P2P kernel).
 """
 import argparse
 import json
@@ -191,6 +196,11 @@ def reference_arm_run(wl, sample_reads, workdir, threads):
     return max(t_full - t_tiny, 1e-6), t_full, os.path.join(workdir, "full.ssv")
 
 
+def capi_pack_info():
+    from shark_b200 import capi
+    return capi.host_pack_info()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,6 +215,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extend", default="auto", choices=["auto", "on", "off"],
                     help="anchor-and-extend: automatic (on for DRAM-sized front tables), or forced (A/B runs)")
+    ap.add_argument("--upload", default="split",
+                    help="how e2e moves the reads: 'plain' (text over PCIe), 'split' (part of every chunk packed to 3 bits "
+                         "per base by the host cores while the rest is in flight, auto-balanced) or a fixed packed share "
+                         "in (0, 1]; the other mode is measured too and reported as e2e_other")
     ap.add_argument("--index", default="broadcast", choices=["broadcast", "sharded", "both"],
                     help="N > 1: build on rank 0 + NCCL broadcast (default), or every rank indexes one gene shard and the "
                          "filters are OR-merged by the library's P2P kernel; 'both' times both and checks they are identical")
@@ -222,6 +236,10 @@ def main():
     config = {"workload": wl["desc"], "reads_per_gpu": n_reads, "read_len": wl["L"], "paired": wl["paired"], "k": wl["k"],
               "bf_gib": wl["b"], "min_quality": wl["q"], "single": wl["single"], "chunk_reads": CHUNK_READS,
               "sharding": "reads sharded by rank, index replicated (NCCL broadcast)" if world > 1 else "single GPU",
+              "upload": ("e2e: plain text over PCIe" if args.upload == "plain" else
+                         "e2e: split upload through shk_reads_submit (SHK_F_HOST_PACK): text in pinned host memory, part of "
+                         "every chunk packed to 3 bits/base by the host cores inside the timed region, share = %s"
+                         % ("auto-balanced" if args.upload == "split" else args.upload)),
               "l2": "inputs larger than L2: every step streams %d MB of reads and probes a %.1f GB filter at random"
                     % (n_reads * (2 * wl["L"] + 1 if wl["paired"] else wl["L"]) // 1_000_000, wl["b"] * 8 / 7 * 1.0737)}
 
@@ -271,6 +289,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the split upload packs with host threads: share the box's cores between the ranks of this node
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("SHK_PACK_THREADS", str(max(2, min(32, cores // max(local_world, 1)))))
     names, bases, rec_off, chunks, keep_alive, W = make_workload(wl, rank, n_reads)
     n_chunks = len(chunks)
     sh = Shark(k=wl["k"], c=wl["c"], bf_bits=wl["b"] << 33, min_quality=wl["q"], single=wl["single"], device=local_rank,
@@ -293,7 +314,8 @@ def main():
         b_info = sh.info
         barrier()
         s_info, s_secs = dist_index.build_index_sharded(sh, bases, rec_off)
-        index_extra.update({"sharded_wall_ms": s_secs * 1e3, "sharded_device_ms": s_info.build_ms, "n_shards": s_info.n_shards})
+        index_extra.update({"sharded_wall_ms": s_secs * 1e3, "sharded_device_ms": s_info.build_ms, "n_shards": s_info.n_shards,
+                            "sharded_steps_wall_ms": getattr(dist_index.build_index_sharded, "last_steps_ms", None)})
         if before is not None:
             after = sh.export_index()
             same = all(np.array_equal(a, b) for a, b in zip(before, after)) and \
@@ -367,25 +389,46 @@ def main():
     def on_result(r):
         d2h[0] += r["n_assoc"] * 8 + r["n_reads"] + 48
 
-    for _ in range(args.warmup):
-        sh2.analyze_chunks(chunks, copy=False, on_result=lambda r: None)
-    barrier()
-    t0 = time.perf_counter()
-    sh2.timer_start()
-    for _ in range(args.steps):
-        sh2.analyze_chunks(chunks, copy=False, on_result=on_result)
-    t_e2e = sh2.timer_stop() * 1e-3
-    barrier()
-    t_e2e_wall = time.perf_counter() - t0
+    def upload_mode(name):
+        return False if name == "plain" else (True if name == "split" else float(name))
+
+    leg_stats = {}
+
+    def e2e_leg(mode):
+        sh2.set_upload_mode(upload_mode(mode))
+        d2h[0] = 0
+        for _ in range(args.warmup):
+            sh2.analyze_chunks(chunks, copy=False, on_result=lambda r: None)
+        barrier()
+        h0 = sh2.h2d_bytes()
+        t0 = time.perf_counter()
+        sh2.timer_start()
+        for _ in range(args.steps):
+            sh2.analyze_chunks(chunks, copy=False, on_result=on_result)
+        t_dev = sh2.timer_stop() * 1e-3
+        # the split upload packs on the host BEFORE a chunk's first device operation: the device stopwatch would
+        # miss the packing of the first chunk of a step, the host clock around the same region does not
+        barrier()
+        t_wall = time.perf_counter() - t0
+        leg_stats[mode] = sh2.upload_stats()
+        return t_dev, t_wall, (sh2.h2d_bytes() - h0) // max(args.steps, 1), d2h[0] // max(args.steps, 1)
+
+    other_mode = "split" if args.upload == "plain" else "plain"
+    o_dev, o_wall, o_h2d, _ = e2e_leg(other_mode)
+    t_e2e, t_e2e_wall, h2d_step, d2h_step = e2e_leg(args.upload)
+    if args.upload != "plain":
+        t_e2e = max(t_e2e, t_e2e_wall)
+    if other_mode != "plain":
+        o_dev = max(o_dev, o_wall)
     clocks = sampler.stop()
 
     # max over ranks (device times; the wall-clock figures ride along as a cross-check)
-    times = torch.tensor([t_res, t_e2e, probe_ms, t_res_wall, t_e2e_wall], dtype=torch.float64, device="cuda")
+    times = torch.tensor([t_res, t_e2e, probe_ms, t_res_wall, t_e2e_wall, o_dev], dtype=torch.float64, device="cuda")
     sums = torch.tensor([float(n_probes), float(n_hits), float(n_assoc)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    t_res_max, t_e2e_max, probe_ms_max, t_res_wall_max, t_e2e_wall_max = times.tolist()
+    t_res_max, t_e2e_max, probe_ms_max, t_res_wall_max, t_e2e_wall_max, o_dev_max = times.tolist()
     total_reads = n_reads * world * args.steps
     value = total_reads / t_res_max
     e2e_value = total_reads / t_e2e_max
@@ -446,9 +489,14 @@ def main():
             "timing": "CUDA events over all slot streams (shk_device_timer_*), max over ranks",
             "wall_ms_per_step": t_res_wall_max / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": n_reads * W * (2 if wl["q"] else 1)
-                    + n_chunks * (CHUNK_READS + 1) * 4, "d2h_bytes_per_step": d2h[0] // max(args.steps, 1),
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_step),
+                    "d2h_bytes_per_step": int(d2h_step), "upload": args.upload,
+                    "packed_share": leg_stats[args.upload][0], "pack_gbases_per_s": leg_stats[args.upload][1],
                     "ms_per_step": t_e2e_max / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall_max / args.steps * 1e3},
+            "e2e_other": {"upload": other_mode, "value": total_reads / o_dev_max, "unit": "reads/s",
+                          "h2d_bytes_per_step": int(o_h2d), "ms_per_step": o_dev_max / args.steps * 1e3,
+                          "pack": "%s, %d threads" % capi_pack_info(),
+                          "packed_share": leg_stats[other_mode][0], "pack_gbases_per_s": leg_stats[other_mode][1]},
             "gpu_launches": int(launches_res), "roofline": roofline, "probe": probe, "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "index": {"n_genes": info.n_genes, "n_set_bits": info.n_set_bits, "tot_ids": info.tot_ids,

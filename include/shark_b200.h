@@ -52,13 +52,23 @@ typedef struct shk_params {
     uint32_t max_reads_per_chunk; /* slot capacity in reads   (0 -> 1<<20)                         */
     uint64_t max_bytes_per_chunk; /* slot capacity in sequence bytes (0 -> 320 * max_reads)        */
     uint32_t flags;               /* SHK_F_*; 0 = defaults                                         */
-    uint32_t reserved[7];         /* must be zero                                                  */
+    uint32_t host_pack_permille;  /* with SHK_F_HOST_PACK: share of each chunk the host packs, in
+                                     1/1000; 0 = balanced automatically against the link           */
+    uint32_t reserved[6];         /* must be zero                                                  */
 } shk_params;
 
 /* shk_params.flags.  Anchor-and-extend: results are identical either way; by default
  * it is switched on when the front table is too large to stay in L2. */
 #define SHK_F_EXTEND_ON 1u  /* always build and use the extension structures                       */
 #define SHK_F_EXTEND_OFF 2u /* never                                                               */
+/* Split upload: the plain path is PCIe-bound at 3-5 x below the kernels' rate, with the host cores idle.
+ * With this flag shk_reads_submit sends the first part of a chunk as it is and, WHILE that copy runs,
+ * reduces the rest to what the kernels use of a text byte - one validity bit (after the -q masking rule,
+ * FastqSplitter.hpp:104-109) and a 2-bit code - on the host cores (AVX2, all pack threads, blocking); that
+ * part crosses the link at 0.375 bytes per base instead of 1 (2 with qualities) and a kernel expands it
+ * back to text in HBM.  The split point balances host and link (measured packing rate; host_pack_permille
+ * fixes it).  Results are identical (the parity suite runs both ways). */
+#define SHK_F_HOST_PACK 4u
 
 typedef struct shk_index_info {
     uint32_t n_records;  /* FASTA records given (= legend_ID.size(), FastaSplitter.hpp:48)         */
@@ -303,6 +313,26 @@ int shk_reads_analyze_resident(shk_ctx *ctx, uint32_t slot);
  * with this pair. */
 int shk_device_timer_start(shk_ctx *ctx);
 int shk_device_timer_stop(shk_ctx *ctx, float *ms);
+
+/* The packing step of SHK_F_HOST_PACK as a pure host function (tests, tools): per text byte i, after
+ * the masking rule when min_quality != 0 (`seq[i] -= 64` where `qual[i] < q+33`), valid bit i % 32 of
+ * valid[i / 32] = byte is one of ACGTacgt, code at bits 2 (i % 32) of codes[i / 32] = (byte >> 1) & 3
+ * (A 0, C 1, T 2, G 3; 0 when invalid).  Both arrays have ceil(n / 32) words.  parallel != 0 uses the
+ * process-wide pack threads.  Needs no GPU. */
+int shk_host_pack(const uint8_t *seq, const uint8_t *qual, int32_t min_quality, uint64_t n, uint64_t *codes,
+                  uint32_t *valid, int32_t parallel);
+/* "avx2" or "scalar"; n_threads (may be NULL) receives the size of the pack pool. */
+const char *shk_host_pack_info(int32_t *n_threads);
+
+/* Switches the split upload (SHK_F_HOST_PACK, host_pack_permille) on or off while no chunk is in flight. */
+int shk_set_upload_mode(shk_ctx *ctx, uint32_t host_pack, uint32_t permille);
+
+/* Split upload diagnostics: the share of a chunk currently packed by the host (0 when off) and the last
+ * measured packing rate in 10^9 bases per second.  Either pointer may be NULL. */
+int shk_upload_stats(const shk_ctx *ctx, double *packed_share, double *pack_gbases_per_s);
+
+/* Bytes that shk_reads_submit / shk_reads_upload copied host -> device on this context so far. */
+uint64_t shk_h2d_bytes(const shk_ctx *ctx);
 
 /* Kernel launches issued by this context so far (for bench accounting). */
 uint64_t shk_kernel_launches(const shk_ctx *ctx);

@@ -14,6 +14,7 @@ CLI = os.path.join(HERE, "shark-b200")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU_SOURCES = ["shk_capi.cu", "shk_index.cu", "shk_reads.cu"]
+CPP_SOURCES = ["shk_hostpack.cpp"]  # host code of the library (g++): read packing for the H2D link
 HOST_SOURCES = ["host/shark_main.cpp"]
 
 
@@ -31,6 +32,15 @@ def _deps():
     return out
 
 
+def _host_objects():
+    objs = []
+    for src in CPP_SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cpp", ".o"))
+        subprocess.check_call(["g++", "-O3", "-std=c++17", "-Wall", "-fPIC", "-pthread", "-c", os.path.join(CSRC, src), "-o", obj])
+        objs.append(obj)
+    return objs
+
+
 def build_variant(name, flags):
     """Tuning only: libshark_b200_<name>.so built with extra nvcc flags (picked up via SHK_LIB)."""
     out = os.path.join(HERE, "libshark_b200_%s.so" % name)
@@ -40,7 +50,8 @@ def build_variant(name, flags):
         subprocess.check_call([NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *flags, "-c",
                                os.path.join(CSRC, src), "-o", obj])
         objs.append(obj)
-    subprocess.check_call([NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart"])
+    objs += _host_objects()
+    subprocess.check_call([NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart", "-lpthread"])
     return out
 
 
@@ -54,7 +65,8 @@ def build(force=False, verbose=False):
                    *os.environ.get("SHK_NVCC_FLAGS", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
             subprocess.check_call(cmd)
             objs.append(obj)
-        subprocess.check_call([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"])
+        objs += _host_objects()
+        subprocess.check_call([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lpthread"])
     host = [os.path.join(CSRC, s) for s in HOST_SOURCES]
     if all(os.path.exists(h) for h in host) and (force or _newer(CLI, deps + [LIB])):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", *host, "-o", CLI, "-L", HERE,

@@ -24,6 +24,7 @@ EXPORTED = [
     "shk_device_timer_stop", "shk_kmer_hashes", "shk_bf_add_at", "shk_bf_switch_mode", "shk_bf_add_to_kmer", "shk_bf_mode",
     "shk_set_options", "shk_shard_begin", "shk_shard_open", "shk_shard_close", "shk_shard_merge", "shk_shard_rank",
     "shk_shard_finish", "shk_shard_end", "shk_shard_cuts", "shk_index_build_sharded", "shk_index_save", "shk_index_load",
+    "shk_host_pack", "shk_host_pack_info", "shk_h2d_bytes", "shk_set_upload_mode", "shk_upload_stats",
 ]
 
 
@@ -37,10 +38,10 @@ class Params(C.Structure):
     _fields_ = [("k", C.c_uint32), ("c", C.c_double), ("bf_bits", C.c_uint64), ("min_quality", C.c_int32),
                 ("single", C.c_int32), ("device", C.c_int32), ("n_slots", C.c_uint32),
                 ("max_reads_per_chunk", C.c_uint32), ("max_bytes_per_chunk", C.c_uint64), ("flags", C.c_uint32),
-                ("reserved", C.c_uint32 * 7)]
+                ("host_pack_permille", C.c_uint32), ("reserved", C.c_uint32 * 6)]
 
 
-F_EXTEND_ON, F_EXTEND_OFF = 1, 2
+F_EXTEND_ON, F_EXTEND_OFF, F_HOST_PACK = 1, 2, 4
 
 
 class IndexInfo(C.Structure):
@@ -126,9 +127,18 @@ def load():
     L.shk_index_build_sharded.argtypes = [C.POINTER(vp), C.c_uint32, vp, vp, C.c_uint32, C.POINTER(IndexInfo)]
     L.shk_index_save.argtypes = [vp, C.c_char_p]
     L.shk_index_load.argtypes = [vp, C.c_char_p, C.POINTER(IndexInfo)]
+    L.shk_host_pack.argtypes = [vp, vp, C.c_int32, C.c_uint64, vp, vp, C.c_int32]
+    L.shk_host_pack_info.argtypes = [C.POINTER(C.c_int32)]
+    L.shk_host_pack_info.restype = C.c_char_p
+    L.shk_set_upload_mode.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.shk_upload_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.shk_h2d_bytes.argtypes = [vp]
+    L.shk_h2d_bytes.restype = C.c_uint64
     L.shk_kernel_launches.restype = C.c_uint64
     for name in EXPORTED:
         f = getattr(L, name)
+        if name in ("shk_host_pack_info", "shk_h2d_bytes", "shk_kernel_launches", "shk_last_error", "shk_destroy"):
+            continue
         if f.restype is C.c_int or name in ("shk_create",):
             f.restype = C.c_int
     _lib = L
@@ -165,3 +175,25 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+def host_pack(seq, qual=None, min_quality=0, parallel=False):
+    """shk_host_pack: (codes uint64[ceil(n/32)], valid uint32[ceil(n/32)]) of a text buffer.  Pure host code."""
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    n = len(seq)
+    g = (n + 31) // 32
+    codes = np.zeros(max(g, 1), np.uint64)
+    valid = np.zeros(max(g, 1), np.uint32)
+    if qual is not None:
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+    rc = load().shk_host_pack(ptr(seq) if n else None, ptr(qual) if qual is not None and n else None, min_quality, n,
+                              ptr(codes), ptr(valid), int(parallel))
+    if rc:
+        raise SharkError(rc, load().shk_last_error(None).decode())
+    return codes[:g], valid[:g]
+
+
+def host_pack_info():
+    n = C.c_int32()
+    isa = load().shk_host_pack_info(C.byref(n)).decode()
+    return isa, n.value

@@ -12,6 +12,7 @@
 
 #include <sched.h>
 
+#include "shk_hostpack.h"
 #include "shk_internal.h"
 
 namespace shk {
@@ -56,6 +57,8 @@ static void free_slot(Slot &s)
     cudaFreeHost(s.h_counters);
     cudaFreeHost(s.h_assoc);
     cudaFreeHost(s.h_keep);
+    cudaFreeHost(s.h_pack);
+    cudaFree(s.d_pack);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_ka) cudaEventDestroy(s.ev_ka);
@@ -186,6 +189,11 @@ static int alloc_slot(shk_ctx *ctx, Slot &s)
     s.h_assoc_cap = s.assoc_cap;
     SHK_CUDA(ctx, pinned_alloc((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
     SHK_CUDA(ctx, pinned_alloc((void **)&s.h_keep, R + 64));
+    if (ctx->host_pack) {
+        s.pack_groups_cap = (B + 63) / 32;
+        SHK_CUDA(ctx, cudaMalloc((void **)&s.d_pack, s.pack_groups_cap * 12));
+        SHK_CUDA(ctx, pinned_alloc((void **)&s.h_pack, s.pack_groups_cap * 12));
+    }
     return SHK_OK;
 }
 
@@ -282,15 +290,85 @@ static int check_chunk(shk_ctx *ctx, uint32_t slot, const uint32_t *off, uint32_
     return SHK_OK;
 }
 
+// Split upload (SHK_F_HOST_PACK): share x of a chunk's bytes that the host packs.  Packing more relieves the
+// link (0.375 bytes per base instead of 1, or 2 with qualities) and loads the host cores; the best x is where
+// the submitting thread just keeps up with the device side.  A feedback loop finds it: per chunk, the time the
+// host spent BLOCKED in shk_reads_collect waiting for the device is compared with the cycle time - blocked
+// more than 12 % of it: the device side (link) is the bottleneck, pack more; less than 4 %: the host is, pack
+// less.  Starts from the analytic balance of a measured packing rate P against an assumed link rate B
+// (x/P = ((1-x) b + 0.375 x)/B); shk_params.host_pack_permille fixes x instead.
+static double now_secs()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static double pack_fraction(shk_ctx *ctx, bool has_qual)
+{
+    if (ctx->params.host_pack_permille) return std::min(1.0, ctx->params.host_pack_permille / 1000.0);
+    PackControl &pc = ctx->pack;
+    const double t = now_secs();
+    if (pc.x <= 0) {  // first chunk: a guess from the pool size
+        const double B = 52e9, b = has_qual ? 2.0 : 1.0, P = 2.5e9 * host_pack_threads() / b;
+        pc.x = std::min(1.0, std::max(0.05, 0.8 * P * b / (B + P * (b - 0.375))));
+    } else if (pc.last_submit > 0) {
+        const double cycle = t - pc.last_submit;
+        if (cycle > 0 && cycle < 1.0) {  // (a long pause is not a pipeline cycle)
+            const double blocked = pc.blocked_secs / cycle;
+            if (blocked > 0.12) pc.x = std::min(1.0, pc.x + 0.03);
+            else if (blocked < 0.04) pc.x = std::max(0.05, pc.x - 0.03);
+        }
+    }
+    pc.last_submit = t;
+    pc.blocked_secs = 0;
+    return pc.x;
+}
+
 static int enqueue_upload(shk_ctx *ctx, Slot &s, const uint8_t *seq, const uint8_t *qual, const uint32_t *off,
-                          uint32_t n_reads)
+                          uint32_t n_reads, bool allow_pack)
 {
     s.n_reads = n_reads;
     s.n_bytes = n_reads ? off[n_reads] : 0;
     s.has_qual = (ctx->params.min_quality & 0xFF) != 0;
     s.launches = 0;
+    if (allow_pack && ctx->host_pack && s.n_bytes) {
+        // Split upload: the first S bytes of the chunk cross the link as they are (asynchronous copy from the
+        // caller's buffer), the rest is packed to 3 bits per base by the host cores WHILE that copy runs, then
+        // copied and expanded to text in HBM.  S balances the two resources (see pack_fraction()).
+        const uint64_t n = s.n_bytes;
+        const double x = pack_fraction(ctx, s.has_qual);
+        uint64_t S = (uint64_t)((1.0 - x) * (double)n) & ~31ull;
+        if (S > n) S = n & ~31ull;
+        const uint64_t groups = (n - S + 31) / 32;
+        const int mq = (int)(signed char)(unsigned char)((ctx->params.min_quality & 0xFF) + 33);
+        SHK_CUDA(ctx, cudaEventRecord(s.ev_start, s.stream));
+        SHK_CUDA(ctx, cudaMemcpyAsync(s.d_off, off, ((uint64_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+        if (S) {
+            SHK_CUDA(ctx, cudaMemcpyAsync(s.d_seq, seq, S, cudaMemcpyHostToDevice, s.stream));
+            if (s.has_qual) {
+                SHK_CUDA(ctx, cudaMemcpyAsync(s.d_qual, qual, S, cudaMemcpyHostToDevice, s.stream));
+                // the packed part carries its masking in the validity bits: qualities that mask nothing
+                if (n > S) SHK_CUDA(ctx, cudaMemsetAsync(s.d_qual + S, 0x7F, n - S, s.stream));
+            }
+        } else {
+            s.has_qual = false;
+        }
+        ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 4 + S * (s.has_qual ? 2 : 1) + groups * 12;
+        if (groups) {
+            uint32_t *h_valid = reinterpret_cast<uint32_t *>(s.h_pack + groups);
+            const double t0 = now_secs();
+            host_pack_parallel(seq + S, qual && (ctx->params.min_quality & 0xFF) ? qual + S : nullptr, mq, n - S, s.h_pack, h_valid);
+            const double secs = now_secs() - t0;
+            if (secs > 0) ctx->pack.rate = (double)(n - S) / secs;
+            SHK_CUDA(ctx, cudaMemcpyAsync(s.d_pack, s.h_pack, groups * 12, cudaMemcpyHostToDevice, s.stream));
+            s.launches += (uint32_t)launch_unpack(ctx, s.d_pack, reinterpret_cast<const uint32_t *>(s.d_pack + groups), n - S,
+                                                  s.d_seq + S, s.stream);
+            SHK_CUDA(ctx, cudaGetLastError());
+        }
+        return SHK_OK;
+    }
     SHK_CUDA(ctx, cudaEventRecord(s.ev_start, s.stream));
     if (n_reads) {
+        ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 4 + s.n_bytes * (s.has_qual ? 2 : 1);
         SHK_CUDA(ctx, cudaMemcpyAsync(s.d_off, off, ((uint64_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s.stream));
         if (s.n_bytes) {
             SHK_CUDA(ctx, cudaMemcpyAsync(s.d_seq, seq, s.n_bytes, cudaMemcpyHostToDevice, s.stream));
@@ -321,7 +399,7 @@ int shk_create(const shk_params *p, shk_ctx **out)
     if (p->bf_bits < 64) return fail(nullptr, SHK_E_ARG, "bf_bits must be >= 64");
     if ((p->flags & SHK_F_EXTEND_ON) && (p->flags & SHK_F_EXTEND_OFF))
         return fail(nullptr, SHK_E_ARG, "SHK_F_EXTEND_ON and SHK_F_EXTEND_OFF are exclusive");
-    if (p->flags & ~(SHK_F_EXTEND_ON | SHK_F_EXTEND_OFF)) return fail(nullptr, SHK_E_ARG, "unknown flag bits");
+    if (p->flags & ~(SHK_F_EXTEND_ON | SHK_F_EXTEND_OFF | SHK_F_HOST_PACK)) return fail(nullptr, SHK_E_ARG, "unknown flag bits");
     const uint64_t n_words = (p->bf_bits + 31) / 32;
     const uint64_t n_sectors = (n_words + kWordsPerSector - 1) / kWordsPerSector;
     if (n_sectors * 8 > 0xFFFFFFFFull)
@@ -339,6 +417,8 @@ int shk_create(const shk_params *p, shk_ctx **out)
     if (!ctx) return fail(nullptr, SHK_E_NOMEM, "out of host memory");
     ctx->params = *p;
     ctx->device = p->device;
+    ctx->host_pack = (p->flags & SHK_F_HOST_PACK) != 0;
+    if (const char *ev = getenv("SHK_HOST_PACK")) ctx->host_pack = atoi(ev) != 0;  // tuning override
     int rc = SHK_OK;
     auto bail = [&](int code) {
         shk_destroy(ctx);
@@ -875,7 +955,7 @@ int shk_reads_submit(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint
     if (rc) return rc;
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[slot];
-    rc = enqueue_upload(ctx, s, seq, qual, off, n_reads);
+    rc = enqueue_upload(ctx, s, seq, qual, off, n_reads, true);
     if (rc) return rc;
     rc = enqueue_chunk_kernels(ctx, s);
     if (rc) return rc;
@@ -890,7 +970,7 @@ int shk_reads_upload(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint
     if (rc) return rc;
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[slot];
-    rc = enqueue_upload(ctx, s, seq, qual, off, n_reads);
+    rc = enqueue_upload(ctx, s, seq, qual, off, n_reads, false);  // kernel-only timing: always the plain text
     if (rc) return rc;
     SHK_CUDA(ctx, cudaStreamSynchronize(s.stream));
     s.pending = false;
@@ -918,7 +998,9 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
     Slot &s = ctx->slots[slot];
     if (!s.pending) return fail(ctx, SHK_E_STATE, "slot %u has no submitted chunk", slot);
     for (int attempt = 0;; ++attempt) {
+        const double t_block = ctx->host_pack ? now_secs() : 0;
         SHK_CUDA(ctx, cudaEventSynchronize(s.ev_done));
+        if (ctx->host_pack) ctx->pack.blocked_secs += now_secs() - t_block;  // feeds pack_fraction()
         const ChunkCounters &c = *s.h_counters;
         if (c.pool_overflow) {
             // more tied winners than the pool holds: grow it and run the chunk again (exact)
@@ -1020,6 +1102,56 @@ int shk_device_timer_stop(shk_ctx *ctx, float *ms)
     SHK_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
     SHK_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
     return SHK_OK;
+}
+
+uint64_t shk_h2d_bytes(const shk_ctx *ctx) { return ctx ? ctx->h2d_bytes.load() : 0; }
+
+int shk_upload_stats(const shk_ctx *ctx, double *packed_share, double *pack_gbases_per_s)
+{
+    if (!ctx) return SHK_E_ARG;
+    if (packed_share)
+        *packed_share = !ctx->host_pack ? 0.0
+                        : ctx->params.host_pack_permille ? ctx->params.host_pack_permille / 1000.0 : ctx->pack.x;
+    if (pack_gbases_per_s) *pack_gbases_per_s = ctx->pack.rate * 1e-9;
+    return SHK_OK;
+}
+
+int shk_set_upload_mode(shk_ctx *ctx, uint32_t host_pack, uint32_t permille)
+{
+    if (!ctx || permille > 1000) return fail(ctx, SHK_E_ARG, "bad argument");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < ctx->n_slots; ++i)
+        if (ctx->slots[i].pending) return fail(ctx, SHK_E_STATE, "slot %u has a chunk in flight", i);
+    if (host_pack)
+        for (uint32_t i = 0; i < ctx->n_slots; ++i) {
+            Slot &s = ctx->slots[i];
+            if (s.d_pack) continue;
+            s.pack_groups_cap = (ctx->max_bytes + 63) / 32;
+            SHK_CUDA(ctx, cudaMalloc((void **)&s.d_pack, s.pack_groups_cap * 12));
+            SHK_CUDA(ctx, pinned_alloc((void **)&s.h_pack, s.pack_groups_cap * 12));
+        }
+    ctx->host_pack = host_pack != 0;
+    ctx->params.host_pack_permille = permille;
+    ctx->pack = PackControl{};
+    return SHK_OK;
+}
+
+int shk_host_pack(const uint8_t *seq, const uint8_t *qual, int32_t min_quality, uint64_t n, uint64_t *codes, uint32_t *valid,
+                  int32_t parallel)
+{
+    if ((n && !seq) || !codes || !valid) return fail(nullptr, SHK_E_ARG, "NULL argument");
+    const int mq = (int)(signed char)(unsigned char)((min_quality & 0xFF) + 33);
+    const uint8_t *q = (min_quality & 0xFF) != 0 ? qual : nullptr;
+    if ((min_quality & 0xFF) != 0 && !qual && n) return fail(nullptr, SHK_E_ARG, "min_quality != 0 needs the quality bytes");
+    if (parallel) host_pack_parallel(seq, q, mq, n, codes, valid);
+    else host_pack(seq, q, mq, n, codes, valid);
+    return SHK_OK;
+}
+
+const char *shk_host_pack_info(int32_t *n_threads)
+{
+    if (n_threads) *n_threads = host_pack_threads();
+    return host_pack_isa();
 }
 
 uint64_t shk_kernel_launches(const shk_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }

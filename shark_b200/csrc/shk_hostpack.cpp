@@ -1,0 +1,220 @@
+// Host-side packing of read text (see shk_hostpack.h).  Plain C++ (g++), no CUDA.
+#include "shk_hostpack.h"
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+#if defined(__linux__)
+#include <sched.h>
+#endif
+
+namespace shk {
+
+namespace {
+
+inline bool valid_base(uint32_t ch)
+{
+    const uint32_t u = (ch | 0x20u) - 0x61u;  // 'a' -> 0
+    return u < 32u && ((0x00080045u >> u) & 1u);  // a, c, g, t
+}
+
+// groups [g0, g1) of 32 bytes; the last group of the text may be partial (n)
+void pack_scalar(const uint8_t *seq, const uint8_t *qual, int mq, uint64_t n, uint64_t g0, uint64_t g1, uint64_t *codes,
+                 uint32_t *valid)
+{
+    for (uint64_t g = g0; g < g1; ++g) {
+        uint64_t c = 0;
+        uint32_t v = 0;
+        const uint64_t i0 = g * 32, i1 = i0 + 32 < n ? i0 + 32 : n;
+        for (uint64_t i = i0; i < i1; ++i) {
+            uint32_t ch = seq[i];
+            if (qual && (int)(signed char)qual[i] < mq) ch = (ch - 64u) & 0xFFu;  // seq[i] = seq[i] - 64
+            if (valid_base(ch)) {
+                v |= 1u << (i - i0);
+                c |= (uint64_t)((ch >> 1) & 3u) << (2 * (i - i0));
+            }
+        }
+        codes[g] = c;
+        valid[g] = v;
+    }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void pack_avx2(const uint8_t *seq, const uint8_t *qual, int mq, uint64_t n, uint64_t g0,
+                                               uint64_t g1, uint64_t *codes, uint32_t *valid)
+{
+    const uint64_t full = n / 32;  // groups that are complete
+    const uint64_t ge = g1 < full ? g1 : full;
+    const __m256i k20 = _mm256_set1_epi8(0x20), k40 = _mm256_set1_epi8(0x40), k3 = _mm256_set1_epi8(3);
+    const __m256i ca = _mm256_set1_epi8('a'), cc = _mm256_set1_epi8('c'), cg = _mm256_set1_epi8('g'), ct = _mm256_set1_epi8('t');
+    const __m256i vmq = _mm256_set1_epi8((char)mq);
+    const __m256i m14 = _mm256_set1_epi16(0x0401);       // bytes (1, 4): c0 + 4 c1
+    const __m256i m116 = _mm256_set1_epi32(0x00100001);  // words (1, 16): t0 + 16 t1
+    const __m256i pick = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                          0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    // mq outside the signed-char range: the comparison is constant (mq is (signed char) in practice)
+    const bool all_masked = mq > 127, none_masked = mq < -128;
+    for (uint64_t g = g0; g < ge; ++g) {
+        __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(seq + g * 32));
+        if (qual && !none_masked) {
+            const __m256i q = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(qual + g * 32));
+            const __m256i lt = all_masked ? _mm256_set1_epi8(-1) : _mm256_cmpgt_epi8(vmq, q);  // q < mq, signed
+            v = _mm256_sub_epi8(v, _mm256_and_si256(lt, k40));
+        }
+        const __m256i lo = _mm256_or_si256(v, k20);
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(lo, ca), _mm256_cmpeq_epi8(lo, cc)),
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(lo, cg), _mm256_cmpeq_epi8(lo, ct)));
+        valid[g] = (uint32_t)_mm256_movemask_epi8(ok);
+        __m256i x = _mm256_and_si256(_mm256_and_si256(_mm256_srli_epi16(v, 1), k3), ok);
+        x = _mm256_maddubs_epi16(x, m14);
+        x = _mm256_madd_epi16(x, m116);
+        x = _mm256_shuffle_epi8(x, pick);
+        const uint64_t lo32 = (uint32_t)_mm256_extract_epi32(x, 0), hi32 = (uint32_t)_mm256_extract_epi32(x, 4);
+        codes[g] = lo32 | (hi32 << 32);
+    }
+    if (ge < g1) pack_scalar(seq, qual, mq, n, ge > g0 ? ge : g0, g1, codes, valid);
+}
+#endif
+
+bool have_avx2()
+{
+#if defined(__x86_64__)
+    static const bool ok = __builtin_cpu_supports("avx2") && !getenv("SHK_PACK_SCALAR");
+    return ok;
+#else
+    return false;
+#endif
+}
+
+void pack_groups(const uint8_t *seq, const uint8_t *qual, int mq, uint64_t n, uint64_t g0, uint64_t g1, uint64_t *codes,
+                 uint32_t *valid)
+{
+#if defined(__x86_64__)
+    if (have_avx2()) {
+        pack_avx2(seq, qual, mq, n, g0, g1, codes, valid);
+        return;
+    }
+#endif
+    pack_scalar(seq, qual, mq, n, g0, g1, codes, valid);
+}
+
+// Persistent worker pool: run(fn) executes fn on every worker and on the caller, returns when all are done.
+class Pool {
+  public:
+    explicit Pool(int n_workers)
+    {
+        for (int i = 0; i < n_workers; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~Pool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size() + 1; }
+    void run(const std::function<void()> &fn)
+    {
+        std::lock_guard<std::mutex> serial(run_mu_);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = &fn;
+            pending_ = (int)workers_.size();
+            ++gen_;
+        }
+        cv_work_.notify_all();
+        fn();
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+  private:
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void()> *job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                job = job_;
+            }
+            (*job)();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) cv_done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void()> *job_ = nullptr;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+Pool &pool()
+{
+    static Pool *p = [] {
+        int n = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+        cpu_set_t set;  // the cores this process may run on (cgroup / taskset), not the machine's
+        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) n = CPU_COUNT(&set);
+#endif
+        if (n < 1) n = 1;
+        if (n > 32) n = 32;
+        if (const char *ev = getenv("SHK_PACK_THREADS")) {
+            const int v = atoi(ev);
+            if (v >= 1 && v <= 256) n = v;
+        }
+        return new Pool(n - 1);  // lives for the process: no destruction-order trouble at exit
+    }();
+    return *p;
+}
+
+}  // namespace
+
+void host_pack(const uint8_t *seq, const uint8_t *qual, int mq, uint64_t n, uint64_t *codes, uint32_t *valid)
+{
+    pack_groups(seq, qual, mq, n, 0, (n + 31) / 32, codes, valid);
+}
+
+void host_pack_parallel(const uint8_t *seq, const uint8_t *qual, int mq, uint64_t n, uint64_t *codes, uint32_t *valid)
+{
+    const uint64_t groups = (n + 31) / 32;
+    constexpr uint64_t kBlock = 4096;  // groups per grab = 128 KiB of text
+    if (groups <= kBlock) {
+        pack_groups(seq, qual, mq, n, 0, groups, codes, valid);
+        return;
+    }
+    std::atomic<uint64_t> next{0};
+    pool().run([&] {
+        for (;;) {
+            const uint64_t g0 = next.fetch_add(kBlock, std::memory_order_relaxed);
+            if (g0 >= groups) break;
+            pack_groups(seq, qual, mq, n, g0, g0 + kBlock < groups ? g0 + kBlock : groups, codes, valid);
+        }
+    });
+}
+
+int host_pack_threads() { return pool().size(); }
+
+const char *host_pack_isa() { return have_avx2() ? "avx2" : "scalar"; }
+
+}  // namespace shk

@@ -115,6 +115,9 @@ struct Slot {
     shk_assoc *h_assoc = nullptr;
     uint64_t h_assoc_cap = 0;
     uint8_t *h_keep = nullptr;
+    // host-packed upload (SHK_F_HOST_PACK): codes (8 bytes per 32 bases) then validity words (4 bytes)
+    uint64_t *h_pack = nullptr, *d_pack = nullptr;
+    uint64_t pack_groups_cap = 0;
     // state
     uint32_t n_reads = 0;
     uint64_t n_bytes = 0;
@@ -142,6 +145,14 @@ struct StagedBuild {
 
 namespace shk {
 struct ShardBuild;  // sharded build state (shk_index.cu)
+// Split upload (SHK_F_HOST_PACK): the share of a chunk that the host packs, steered by how long the submitting
+// thread is blocked waiting for the device (pack_fraction() in shk_capi.cu).  One submitting thread per context.
+struct PackControl {
+    double x = 0;             // current share, 0 = not initialised
+    double last_submit = 0;   // host clock of the previous packed submit
+    double blocked_secs = 0;  // time blocked in shk_reads_collect since then
+    double rate = 0;          // last measured packing rate, bases/s (diagnostics)
+};
 }
 
 struct shk_ctx {
@@ -161,6 +172,9 @@ struct shk_ctx {
     cudaStream_t timer_stream = nullptr;  // shk_device_timer_*: joins every slot stream
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_join = nullptr;
     uint64_t pol_first = 0, pol_last = 0;  // createpolicy evict_first / evict_last descriptors
+    bool host_pack = false;                // shk_reads_submit packs the text on the host cores first
+    std::atomic<uint64_t> h2d_bytes{0};    // bytes shk_reads_submit / upload copied to the device
+    shk::PackControl pack;                 // split upload: feedback state of the packed share
     char err[512] = {0};
 };
 
@@ -208,5 +222,8 @@ int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_ca
                         cudaEvent_t ev_ka, cudaEvent_t ev_k1);
 int launch_scatter(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st);
 int fetch_cache_policies(shk_ctx *ctx);
+// host-packed reads (shk_hostpack.h) -> text in d_seq; returns the number of launches
+int launch_unpack(shk_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_bytes, uint8_t *d_seq,
+                  cudaStream_t st);
 
 }  // namespace shk

@@ -888,6 +888,46 @@ __global__ void fetch_policies_kernel(uint64_t *out)
     out[1] = make_policy_evict_last();
 }
 
+// Expands host-packed reads (shk_hostpack.h: 2-bit code + validity bit per base) back to text in HBM:
+// valid -> 'A','C','T','G' by code, invalid -> 'N'.  The classification kernels only look at a byte's
+// validity and code (to_int, kmer_utils.hpp:29-41), and the quality masking is already folded into the
+// validity bits, so they run on this text without qualities and produce the same results.
+// One thread = one group of 32 bases = 32 output bytes (two 16-byte stores).
+__global__ void __launch_bounds__(256)
+unpack_reads_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ valid, uint64_t groups, uint4 *text)
+{
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    const uint64_t c = codes[g];
+    const uint32_t v = valid[g];
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = j * 4 + b;
+            const uint32_t code = (uint32_t)(c >> (2 * i)) & 3u;
+            const uint32_t ch = ((v >> i) & 1u) ? ((0x47544341u >> (8 * code)) & 0xFFu) : (uint32_t)'N';  // A C T G
+            word |= ch << (8 * b);
+        }
+        w[j] = word;
+    }
+    text[2 * g] = make_uint4(w[0], w[1], w[2], w[3]);
+    text[2 * g + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+int launch_unpack(shk_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_bytes, uint8_t *d_seq,
+                  cudaStream_t st)
+{
+    const uint64_t groups = (n_bytes + 31) / 32;
+    if (!groups) return 0;
+    unpack_reads_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(d_codes, d_valid, groups,
+                                                                          reinterpret_cast<uint4 *>(d_seq));
+    ctx->launches += 1;
+    return 1;
+}
+
 int fetch_cache_policies(shk_ctx *ctx)
 {
     uint64_t *d = nullptr, h[2] = {0, 0};

@@ -91,31 +91,48 @@ def build_index_sharded(sh, bases, rec_off, barrier=None, all_gather=None):
     k-mers of record shard r into its own filter, the filters are OR-merged by the library's P2P
     kernel over NVLink (peer buffers mapped through CUDA IPC handles that travel as bytes over
     torch.distributed), then every rank finishes the same index locally.  torch.distributed only
-    carries the 256-byte handle structs and the barriers.  Returns (info, wall seconds)."""
+    carries the 240-byte handle structs and the barriers.  Returns (info, wall seconds); the host time
+    of each step is left in build_index_sharded.last_steps_ms."""
     import time
     barrier = barrier or dist.barrier
     rank, world = dist.get_rank(), dist.get_world_size()
-    t0 = time.perf_counter()
+    steps = {}
+    t0 = last = time.perf_counter()
+
+    def mark(name):
+        nonlocal last
+        now = time.perf_counter()
+        steps[name] = (now - last) * 1e3
+        last = now
+
     mine = sh.shard_begin(bases, rec_off, rank, world)
+    mark("begin")
     blobs = [None] * world
     (all_gather or dist.all_gather_object)(blobs, bytes(mine))
+    mark("exchange")
     arr = (capi.ShardMem * world)()
     for s in range(world):
         peer = capi.ShardMem.from_buffer_copy(blobs[s])
         if peer.shard != s:
             raise capi.SharkError(-3, "shard structs arrived out of order")
         arr[s] = mine if s == rank else sh.shard_open(peer)
+    mark("open")
     barrier()
     sh.shard_merge(1, arr)
     barrier()
     sh.shard_merge(2, arr)
+    mark("merge")
     sh.shard_rank()
     barrier()
+    mark("rank")
     info = sh.shard_finish(arr)
     barrier()
+    mark("finish")
     for s in range(world):
         if s != rank:
             sh.shard_close(arr[s])
     barrier()  # nobody frees a buffer that a peer still has mapped
     sh.shard_end()
+    mark("close")
+    build_index_sharded.last_steps_ms = steps
     return info, time.perf_counter() - t0

@@ -15,14 +15,20 @@ from . import capi
 
 class Shark:
     def __init__(self, k=17, c=0.6, bf_bits=1 << 33, min_quality=0, single=False, device=0, n_slots=2,
-                 max_reads_per_chunk=1 << 20, max_bytes_per_chunk=0, extend=None):
+                 max_reads_per_chunk=1 << 20, max_bytes_per_chunk=0, extend=None, host_pack=False):
         """extend: None = automatic (anchor-and-extend when the front table is DRAM-sized), True /
         False = force it on / off (results are identical; tests run both)."""
         self.lib = capi.load()
         flags = 0 if extend is None else (capi.F_EXTEND_ON if extend else capi.F_EXTEND_OFF)
+        permille = 0
+        if host_pack:  # split upload: part of every chunk is packed to 3 bits per base by the host cores
+            flags |= capi.F_HOST_PACK
+            if host_pack is not True:  # a number in (0, 1]: fixed share instead of the automatic balance
+                permille = max(1, min(1000, int(round(float(host_pack) * 1000))))
         self.params = capi.Params(k=k, c=c, bf_bits=bf_bits, min_quality=min_quality, single=int(bool(single)),
                                   device=device, n_slots=n_slots, max_reads_per_chunk=max_reads_per_chunk,
-                                  max_bytes_per_chunk=max_bytes_per_chunk, flags=flags)
+                                  max_bytes_per_chunk=max_bytes_per_chunk, flags=flags,
+                                  host_pack_permille=permille)
         self.ctx = C.c_void_p()
         rc = self.lib.shk_create(C.byref(self.params), C.byref(self.ctx))
         if rc:
@@ -256,6 +262,20 @@ class Shark:
         ms = C.c_float()
         self._check(self.lib.shk_device_timer_stop(self.ctx, C.byref(ms)))
         return ms.value
+
+    def set_upload_mode(self, host_pack):
+        """False = plain text upload; True = split upload, balanced automatically; a number in (0, 1] = fixed share."""
+        permille = 0 if host_pack in (True, False, None) else max(1, min(1000, int(round(float(host_pack) * 1000))))
+        self._check(self.lib.shk_set_upload_mode(self.ctx, int(bool(host_pack)), permille))
+
+    def upload_stats(self):
+        """-> (share of a chunk the host packs, last packing rate in Gbases/s)"""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.shk_upload_stats(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def h2d_bytes(self):
+        return int(self.lib.shk_h2d_bytes(self.ctx))
 
     def kernel_launches(self):
         return int(self.lib.shk_kernel_launches(self.ctx))

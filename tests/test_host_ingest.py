@@ -8,6 +8,8 @@ import subprocess
 
 import pytest
 
+from helpers import ROOT
+
 HOST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shark_b200", "csrc", "host")
 
 
@@ -109,3 +111,51 @@ def test_empty_and_missing_files(tool, tmp_path):
     assert _check(tool, p, 100) == 3
     r = subprocess.run([tool, "scan-check", str(tmp_path / "nope.fq")], capture_output=True, text=True)
     assert r.returncode == 0 and "OPEN_FAILED" in r.stdout
+
+
+def test_host_pack_matches_numpy_restatement():
+    """shk_host_pack (pure host code of the split upload): validity after the masking rule
+    (FastqSplitter.hpp:104-109: `seq[i] -= 64` where `(char)qual[i] < (char)(q+33)`; to_int kmer_utils.hpp:29-41)
+    and 2-bit codes, against a numpy restatement - AVX2 and scalar paths, single and parallel, ragged sizes,
+    every byte value, `char` wrap-around of q."""
+    import subprocess
+    import sys
+    import numpy as np
+    from shark_b200 import capi
+
+    def ref_pack(seq, qual, q):
+        ch = seq.astype(np.int64)
+        if qual is not None and (q & 0xFF) != 0:
+            mq = np.int64(np.int8(np.uint8(((q & 0xFF) + 33) & 0xFF)))
+            ch = np.where(qual.astype(np.int8).astype(np.int64) < mq, (ch - 64) & 0xFF, ch)
+        ok = np.isin(ch | 0x20, [0x61, 0x63, 0x67, 0x74])
+        code = np.where(ok, (ch >> 1) & 3, 0).astype(np.uint64)
+        g = (len(seq) + 31) // 32
+        pad = g * 32 - len(seq)
+        ok = np.concatenate([ok, np.zeros(pad, bool)]).reshape(g, 32).astype(np.uint64)
+        code = np.concatenate([code, np.zeros(pad, np.uint64)]).reshape(g, 32)
+        sh = np.arange(32, dtype=np.uint64)
+        return (code << (2 * sh)).sum(1).astype(np.uint64), (ok << sh).sum(1).astype(np.uint32)
+
+    isa, threads = capi.host_pack_info()
+    assert isa in ("avx2", "scalar") and threads >= 1
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 31, 32, 33, 1000, (1 << 19) + 77):
+        seq = rng.integers(0, 256, n, dtype=np.uint8)
+        m = rng.random(n) < 0.7
+        seq[m] = np.frombuffer(b"ACGTacgtNn", np.uint8)[rng.integers(0, 10, int(m.sum()))]
+        qual = rng.integers(0, 256, n, dtype=np.uint8)
+        for q in (0, 20, 94, 95, 200, 223):
+            c0, v0 = ref_pack(seq, qual, q)
+            for par in (False, True):
+                c, v = capi.host_pack(seq, qual, q, par)
+                assert np.array_equal(c, c0) and np.array_equal(v, v0), (n, q, par)
+    # the scalar fallback, in a fresh process (the ISA choice is made once)
+    code = ("import numpy as np; from shark_b200 import capi; assert capi.host_pack_info()[0] == 'scalar';"
+            "s = np.frombuffer(b'ACGTNacgtn\\x81' * 13, np.uint8); q = np.arange(len(s), dtype=np.uint8) * 3;"
+            "c, v = capi.host_pack(s, q, 20); print(c.tolist(), v.tolist())")
+    env = dict(os.environ, SHK_PACK_SCALAR="1", PYTHONPATH=ROOT)
+    scalar = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, check=True).stdout
+    s = np.frombuffer(b"ACGTNacgtn\x81" * 13, np.uint8)
+    c, v = capi.host_pack(s, np.arange(len(s), dtype=np.uint8) * 3, 20)
+    assert scalar.decode().strip() == "%s %s" % (c.tolist(), v.tolist())
