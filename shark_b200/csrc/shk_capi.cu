@@ -290,36 +290,41 @@ static int check_chunk(shk_ctx *ctx, uint32_t slot, const uint32_t *off, uint32_
     return SHK_OK;
 }
 
-// Split upload (SHK_F_HOST_PACK): share x of a chunk's bytes that the host packs.  Packing more relieves the
-// link (0.375 bytes per base instead of 1, or 2 with qualities) and loads the host cores; the best x is where
-// the submitting thread just keeps up with the device side.  A feedback loop finds it: per chunk, the time the
-// host spent BLOCKED in shk_reads_collect waiting for the device is compared with the cycle time - blocked
-// more than 12 % of it: the device side (link) is the bottleneck, pack more; less than 4 %: the host is, pack
-// less.  Starts from the analytic balance of a measured packing rate P against an assumed link rate B
-// (x/P = ((1-x) b + 0.375 x)/B); shk_params.host_pack_permille fixes x instead.
+// Split upload (SHK_F_HOST_PACK): share x of a chunk's n bases that the host packs.  Packing more relieves the
+// link (0.375 bytes per base instead of b = 1, or 2 with qualities) and loads the submitting thread.  x balances
+// the two per chunk:   host  x n / P + h0   =   link  ((1 - x) b + 0.375 x) n / B
+// with P the packing rate (measured, smoothed), h0 the submitting thread's other work per chunk (measured:
+// cycle time minus packing minus the time blocked on the device in shk_reads_collect), B the link rate
+// (SHK_PCIE_GBS, default 53: what the plain path measures on a B200 host).  Measured (profiles/
+// hostpack_r1_v13.md): the balance point is within a few percent of the best fixed share on C2, C3 and C4.
+// shk_params.host_pack_permille fixes x instead.
 static double now_secs()
 {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static double pack_fraction(shk_ctx *ctx, bool has_qual)
+static double pack_fraction(shk_ctx *ctx, bool has_qual, uint64_t n)
 {
     if (ctx->params.host_pack_permille) return std::min(1.0, ctx->params.host_pack_permille / 1000.0);
+    static const double B = [] {
+        const char *ev = getenv("SHK_PCIE_GBS");
+        const double v = ev ? atof(ev) : 0;
+        return (v > 1 ? v : 53.0) * 1e9;
+    }();
     PackControl &pc = ctx->pack;
     const double t = now_secs();
-    if (pc.x <= 0) {  // first chunk: a guess from the pool size
-        const double B = 52e9, b = has_qual ? 2.0 : 1.0, P = 2.5e9 * host_pack_threads() / b;
-        pc.x = std::min(1.0, std::max(0.05, 0.8 * P * b / (B + P * (b - 0.375))));
-    } else if (pc.last_submit > 0) {
+    if (pc.last_submit > 0) {
         const double cycle = t - pc.last_submit;
-        if (cycle > 0 && cycle < 1.0) {  // (a long pause is not a pipeline cycle)
-            const double blocked = pc.blocked_secs / cycle;
-            if (blocked > 0.12) pc.x = std::min(1.0, pc.x + 0.03);
-            else if (blocked < 0.04) pc.x = std::max(0.05, pc.x - 0.03);
-        }
+        const double h = cycle - pc.last_pack_secs - pc.blocked_secs;
+        if (cycle < 1.0 && h >= 0) pc.h0 = 0.7 * pc.h0 + 0.3 * std::min(h, 5e-3);  // (a long pause is not a cycle)
     }
     pc.last_submit = t;
     pc.blocked_secs = 0;
+    pc.last_pack_secs = 0;
+    const double b = has_qual ? 2.0 : 1.0;
+    const double P = pc.rate > 0 ? pc.rate : 3e9 * host_pack_threads() / b;  // first chunk: a guess
+    const double nn = (double)n;
+    pc.x = std::min(1.0, std::max(0.05, (b * nn / B - pc.h0) / (nn / P + (b - 0.375) * nn / B)));
     return pc.x;
 }
 
@@ -335,7 +340,7 @@ static int enqueue_upload(shk_ctx *ctx, Slot &s, const uint8_t *seq, const uint8
         // caller's buffer), the rest is packed to 3 bits per base by the host cores WHILE that copy runs, then
         // copied and expanded to text in HBM.  S balances the two resources (see pack_fraction()).
         const uint64_t n = s.n_bytes;
-        const double x = pack_fraction(ctx, s.has_qual);
+        const double x = pack_fraction(ctx, s.has_qual, n);
         uint64_t S = (uint64_t)((1.0 - x) * (double)n) & ~31ull;
         if (S > n) S = n & ~31ull;
         const uint64_t groups = (n - S + 31) / 32;
@@ -358,7 +363,9 @@ static int enqueue_upload(shk_ctx *ctx, Slot &s, const uint8_t *seq, const uint8
             const double t0 = now_secs();
             host_pack_parallel(seq + S, qual && (ctx->params.min_quality & 0xFF) ? qual + S : nullptr, mq, n - S, s.h_pack, h_valid);
             const double secs = now_secs() - t0;
-            if (secs > 0) ctx->pack.rate = (double)(n - S) / secs;
+            ctx->pack.last_pack_secs = secs;
+            if (secs > 0 && n - S >= (1u << 20))
+                ctx->pack.rate = ctx->pack.rate > 0 ? 0.7 * ctx->pack.rate + 0.3 * (double)(n - S) / secs : (double)(n - S) / secs;
             SHK_CUDA(ctx, cudaMemcpyAsync(s.d_pack, s.h_pack, groups * 12, cudaMemcpyHostToDevice, s.stream));
             s.launches += (uint32_t)launch_unpack(ctx, s.d_pack, reinterpret_cast<const uint32_t *>(s.d_pack + groups), n - S,
                                                   s.d_seq + S, s.stream);

@@ -145,13 +145,15 @@ struct StagedBuild {
 
 namespace shk {
 struct ShardBuild;  // sharded build state (shk_index.cu)
-// Split upload (SHK_F_HOST_PACK): the share of a chunk that the host packs, steered by how long the submitting
-// thread is blocked waiting for the device (pack_fraction() in shk_capi.cu).  One submitting thread per context.
+// Split upload (SHK_F_HOST_PACK): measurements behind the share of a chunk that the host packs
+// (pack_fraction() in shk_capi.cu).  One submitting thread per context.
 struct PackControl {
-    double x = 0;             // current share, 0 = not initialised
-    double last_submit = 0;   // host clock of the previous packed submit
-    double blocked_secs = 0;  // time blocked in shk_reads_collect since then
-    double rate = 0;          // last measured packing rate, bases/s (diagnostics)
+    double x = 0;               // current share
+    double rate = 0;            // packing rate, bases/s (smoothed)
+    double h0 = 3e-4;           // submitting thread's other work per chunk, seconds (smoothed)
+    double last_submit = 0;     // host clock of the previous packed submit
+    double last_pack_secs = 0;  // packing time of that submit
+    double blocked_secs = 0;    // time blocked on the device in shk_reads_collect since then
 };
 }
 

@@ -265,7 +265,8 @@ class Shark:
 
     def set_upload_mode(self, host_pack):
         """False = plain text upload; True = split upload, balanced automatically; a number in (0, 1] = fixed share."""
-        permille = 0 if host_pack in (True, False, None) else max(1, min(1000, int(round(float(host_pack) * 1000))))
+        auto = host_pack is None or isinstance(host_pack, bool)   # (1.0 == True in Python: test the type)
+        permille = 0 if auto else max(1, min(1000, int(round(float(host_pack) * 1000))))
         self._check(self.lib.shk_set_upload_mode(self.ctx, int(bool(host_pack)), permille))
 
     def upload_stats(self):
