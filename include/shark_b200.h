@@ -321,7 +321,7 @@ int shk_device_timer_stop(shk_ctx *ctx, float *ms);
  * process-wide pack threads.  Needs no GPU. */
 int shk_host_pack(const uint8_t *seq, const uint8_t *qual, int32_t min_quality, uint64_t n, uint64_t *codes,
                   uint32_t *valid, int32_t parallel);
-/* "avx2" or "scalar"; n_threads (may be NULL) receives the size of the pack pool. */
+/* "avx512", "avx2" or "scalar"; n_threads (may be NULL) receives the size of the pack pool. */
 const char *shk_host_pack_info(int32_t *n_threads);
 
 /* Switches the split upload (SHK_F_HOST_PACK, host_pack_permille) on or off while no chunk is in flight. */

@@ -83,6 +83,45 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *seq, const uint8_t
     }
     if (ge < g1) pack_scalar(seq, qual, mq, n, ge > g0 ? ge : g0, g1, codes, valid);
 }
+
+// 64 bases per iteration (two groups): byte compares straight into mask registers, vpmovdb compacts the codes.
+__attribute__((target("avx512f,avx512bw,avx512vl"))) void pack_avx512(const uint8_t *seq, const uint8_t *qual, int mq,
+                                                                      uint64_t n, uint64_t g0, uint64_t g1, uint64_t *codes,
+                                                                      uint32_t *valid)
+{
+    const uint64_t full = n / 32;
+    const uint64_t ge = g1 < full ? g1 : full;
+    uint64_t g = g0;
+    const __m512i k20 = _mm512_set1_epi8(0x20), k40 = _mm512_set1_epi8(0x40), k3 = _mm512_set1_epi8(3);
+    const __m512i ca = _mm512_set1_epi8('a'), cc = _mm512_set1_epi8('c'), cg = _mm512_set1_epi8('g'), ct = _mm512_set1_epi8('t');
+    const __m512i vmq = _mm512_set1_epi8((char)mq);
+    const __m512i m14 = _mm512_set1_epi16(0x0401), m116 = _mm512_set1_epi32(0x00100001);
+    const bool all_masked = mq > 127, none_masked = mq < -128;
+    for (; g + 2 <= ge; g += 2) {
+        __m512i v = _mm512_loadu_si512(seq + g * 32);
+        if (qual && !none_masked) {
+            const __m512i q = _mm512_loadu_si512(qual + g * 32);
+            const __mmask64 lt = all_masked ? ~0ull : _mm512_cmplt_epi8_mask(q, vmq);  // q < mq, signed
+            v = _mm512_mask_sub_epi8(v, lt, v, k40);
+        }
+        const __m512i lo = _mm512_or_si512(v, k20);
+        const __mmask64 ok = _mm512_cmpeq_epi8_mask(lo, ca) | _mm512_cmpeq_epi8_mask(lo, cc) | _mm512_cmpeq_epi8_mask(lo, cg) |
+                             _mm512_cmpeq_epi8_mask(lo, ct);
+        __m512i x = _mm512_maskz_mov_epi8(ok, _mm512_and_si512(_mm512_srli_epi16(v, 1), k3));
+        x = _mm512_madd_epi16(_mm512_maddubs_epi16(x, m14), m116);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(codes + g), _mm512_cvtepi32_epi8(x));
+        valid[g] = (uint32_t)ok;
+        valid[g + 1] = (uint32_t)(ok >> 32);
+    }
+    if (g < g1) pack_avx2(seq, qual, mq, n, g, g1, codes, valid);
+}
+
+bool have_avx512()
+{
+    static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                           __builtin_cpu_supports("avx512vl") && !getenv("SHK_PACK_SCALAR") && !getenv("SHK_PACK_AVX2");
+    return ok;
+}
 #endif
 
 bool have_avx2()
@@ -99,6 +138,10 @@ void pack_groups(const uint8_t *seq, const uint8_t *qual, int mq, uint64_t n, ui
                  uint32_t *valid)
 {
 #if defined(__x86_64__)
+    if (have_avx512()) {
+        pack_avx512(seq, qual, mq, n, g0, g1, codes, valid);
+        return;
+    }
     if (have_avx2()) {
         pack_avx2(seq, qual, mq, n, g0, g1, codes, valid);
         return;
@@ -215,6 +258,12 @@ void host_pack_parallel(const uint8_t *seq, const uint8_t *qual, int mq, uint64_
 
 int host_pack_threads() { return pool().size(); }
 
-const char *host_pack_isa() { return have_avx2() ? "avx2" : "scalar"; }
+const char *host_pack_isa()
+{
+#if defined(__x86_64__)
+    if (have_avx512()) return "avx512";
+#endif
+    return have_avx2() ? "avx2" : "scalar";
+}
 
 }  // namespace shk

@@ -5,7 +5,7 @@
 // -q (FastqSplitter.hpp:47-93) - and the kernels are 3-5 x faster than the link.  Everything the
 // kernels need from a text byte is 3 bits: is it a valid base AFTER the quality masking
 // (`seq[i] -= 64` where `qual[i] < q+33`, FastqSplitter.hpp:104-109; to_int, kmer_utils.hpp:29-41),
-// and which of the four.  These functions compute exactly those bits on the host cores (AVX2, a
+// and which of the four.  These functions compute exactly those bits on the host cores (AVX-512 or AVX2, a
 // scalar fallback elsewhere), so that 0.375 bytes per base cross the link instead of 1 (2 under -q);
 // a small kernel expands them back to text in HBM and the classification kernels run unchanged.
 #pragma once
@@ -23,6 +23,6 @@ void host_pack(const uint8_t *seq, const uint8_t *qual, int mq, uint64_t n, uint
 // SHK_PACK_THREADS overrides its size = min(hardware threads, 32)).  Calls are serialised.
 void host_pack_parallel(const uint8_t *seq, const uint8_t *qual, int mq, uint64_t n, uint64_t *codes, uint32_t *valid);
 int host_pack_threads();
-const char *host_pack_isa();  // "avx2" or "scalar"
+const char *host_pack_isa();  // "avx512", "avx2" or "scalar"
 
 }  // namespace shk

@@ -138,7 +138,7 @@ def test_host_pack_matches_numpy_restatement():
         return (code << (2 * sh)).sum(1).astype(np.uint64), (ok << sh).sum(1).astype(np.uint32)
 
     isa, threads = capi.host_pack_info()
-    assert isa in ("avx2", "scalar") and threads >= 1
+    assert isa in ("avx512", "avx2", "scalar") and threads >= 1
     rng = np.random.default_rng(1)
     for n in (0, 1, 31, 32, 33, 1000, (1 << 19) + 77):
         seq = rng.integers(0, 256, n, dtype=np.uint8)
@@ -150,12 +150,21 @@ def test_host_pack_matches_numpy_restatement():
             for par in (False, True):
                 c, v = capi.host_pack(seq, qual, q, par)
                 assert np.array_equal(c, c0) and np.array_equal(v, v0), (n, q, par)
-    # the scalar fallback, in a fresh process (the ISA choice is made once)
-    code = ("import numpy as np; from shark_b200 import capi; assert capi.host_pack_info()[0] == 'scalar';"
-            "s = np.frombuffer(b'ACGTNacgtn\\x81' * 13, np.uint8); q = np.arange(len(s), dtype=np.uint8) * 3;"
-            "c, v = capi.host_pack(s, q, 20); print(c.tolist(), v.tolist())")
-    env = dict(os.environ, SHK_PACK_SCALAR="1", PYTHONPATH=ROOT)
-    scalar = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, check=True).stdout
-    s = np.frombuffer(b"ACGTNacgtn\x81" * 13, np.uint8)
-    c, v = capi.host_pack(s, np.arange(len(s), dtype=np.uint8) * 3, 20)
-    assert scalar.decode().strip() == "%s %s" % (c.tolist(), v.tolist())
+    # the other instruction sets, each in a fresh process (the choice is made once): byte-identical output
+    code = ("import numpy as np; from shark_b200 import capi; print(capi.host_pack_info()[0]);"
+            "rng = np.random.default_rng(3); s = rng.integers(0, 256, 100003, dtype=np.uint8);"
+            "m = rng.random(len(s)) < 0.7; s[m] = np.frombuffer(b'ACGTacgtNn', np.uint8)[rng.integers(0, 10, int(m.sum()))];"
+            "q = rng.integers(0, 256, len(s), dtype=np.uint8);"
+            "import hashlib; h = hashlib.md5();"
+            "[h.update(a.tobytes()) for mq in (0, 20, 95) for a in capi.host_pack(s, q, mq)]; print(h.hexdigest())")
+    outs = {}
+    for name, extra in (("default", {}), ("avx2", {"SHK_PACK_AVX2": "1"}), ("scalar", {"SHK_PACK_SCALAR": "1"})):
+        env = dict(os.environ, PYTHONPATH=ROOT, **extra)
+        isa_used, digest = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                          check=True).stdout.decode().split()
+        outs[name] = digest
+        if name == "scalar":
+            assert isa_used == "scalar"
+        if name == "avx2":
+            assert isa_used in ("avx2", "scalar")
+    assert outs["default"] == outs["avx2"] == outs["scalar"], outs
