@@ -400,7 +400,7 @@ def main():
         for _ in range(args.warmup):
             sh2.analyze_chunks(chunks, copy=False, on_result=lambda r: None)
         barrier()
-        h0 = sh2.h2d_bytes()
+        h0, dd0 = sh2.h2d_bytes(), sh2.d2h_bytes()
         t0 = time.perf_counter()
         sh2.timer_start()
         for _ in range(args.steps):
@@ -411,7 +411,7 @@ def main():
         barrier()
         t_wall = time.perf_counter() - t0
         leg_stats[mode] = sh2.upload_stats()
-        return t_dev, t_wall, (sh2.h2d_bytes() - h0) // max(args.steps, 1), d2h[0] // max(args.steps, 1)
+        return t_dev, t_wall, (sh2.h2d_bytes() - h0) // max(args.steps, 1), (sh2.d2h_bytes() - dd0) // max(args.steps, 1)
 
     other_mode = "split" if args.upload == "plain" else "plain"
     o_dev, o_wall, o_h2d, _ = e2e_leg(other_mode)

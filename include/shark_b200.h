@@ -333,6 +333,10 @@ int shk_upload_stats(const shk_ctx *ctx, double *packed_share, double *pack_gbas
 
 /* Bytes that shk_reads_submit / shk_reads_upload copied host -> device on this context so far. */
 uint64_t shk_h2d_bytes(const shk_ctx *ctx);
+/* Result bytes (associations, keep flags, counters) copied device -> host on this context so far.  The
+ * read-back of a chunk is enqueued with its kernels, sized by the previous chunks' associations per read;
+ * shk_reads_collect fetches what that did not cover. */
+uint64_t shk_d2h_bytes(const shk_ctx *ctx);
 
 /* Kernel launches issued by this context so far (for bench accounting). */
 uint64_t shk_kernel_launches(const shk_ctx *ctx);

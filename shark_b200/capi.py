@@ -24,7 +24,7 @@ EXPORTED = [
     "shk_device_timer_stop", "shk_kmer_hashes", "shk_bf_add_at", "shk_bf_switch_mode", "shk_bf_add_to_kmer", "shk_bf_mode",
     "shk_set_options", "shk_shard_begin", "shk_shard_open", "shk_shard_close", "shk_shard_merge", "shk_shard_rank",
     "shk_shard_finish", "shk_shard_end", "shk_shard_cuts", "shk_index_build_sharded", "shk_index_save", "shk_index_load",
-    "shk_host_pack", "shk_host_pack_info", "shk_h2d_bytes", "shk_set_upload_mode", "shk_upload_stats",
+    "shk_host_pack", "shk_host_pack_info", "shk_h2d_bytes", "shk_d2h_bytes", "shk_set_upload_mode", "shk_upload_stats",
 ]
 
 
@@ -134,10 +134,12 @@ def load():
     L.shk_upload_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.shk_h2d_bytes.argtypes = [vp]
     L.shk_h2d_bytes.restype = C.c_uint64
+    L.shk_d2h_bytes.argtypes = [vp]
+    L.shk_d2h_bytes.restype = C.c_uint64
     L.shk_kernel_launches.restype = C.c_uint64
     for name in EXPORTED:
         f = getattr(L, name)
-        if name in ("shk_host_pack_info", "shk_h2d_bytes", "shk_kernel_launches", "shk_last_error", "shk_destroy"):
+        if name in ("shk_host_pack_info", "shk_h2d_bytes", "shk_d2h_bytes", "shk_kernel_launches", "shk_last_error", "shk_destroy"):
             continue
         if f.restype is C.c_int or name in ("shk_create",):
             f.restype = C.c_int

@@ -270,6 +270,17 @@ static int enqueue_chunk_kernels(shk_ctx *ctx, Slot &s)
     s.launches += (uint32_t)launch_read_kernels(ctx, a, s.assoc_cap, s.stream, s.ev_k0, s.ev_ka, s.ev_k1);
     SHK_CUDA(ctx, cudaGetLastError());
     SHK_CUDA(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(ChunkCounters), cudaMemcpyDeviceToHost, s.stream));
+    // Results follow on the stream, before the host knows their size: as many associations as the previous chunks
+    // produced per read (+5 %), the rest - if any - is fetched by shk_reads_collect.  This keeps the read-back
+    // off the collecting thread's critical path and lets it overlap the other slots' kernels.
+    const double per_read = ctx->assoc_per_read.load();
+    uint64_t pre = per_read < 0 ? s.n_reads : (uint64_t)(per_read * 1.05 * s.n_reads) + 4096;
+    pre = std::min(pre, std::min(s.assoc_cap, s.h_assoc_cap));
+    if (!s.n_reads) pre = 0;
+    if (pre) SHK_CUDA(ctx, cudaMemcpyAsync(s.h_assoc, s.d_assoc, pre * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
+    if (s.n_reads) SHK_CUDA(ctx, cudaMemcpyAsync(s.h_keep, s.d_keep, s.n_reads, cudaMemcpyDeviceToHost, s.stream));
+    s.pre_assoc = pre;
+    ctx->d2h_bytes += pre * sizeof(shk_assoc) + s.n_reads + sizeof(ChunkCounters);
     SHK_CUDA(ctx, cudaEventRecord(s.ev_done, s.stream));
     return SHK_OK;
 }
@@ -341,8 +352,9 @@ static int enqueue_upload(shk_ctx *ctx, Slot &s, const uint8_t *seq, const uint8
         // copied and expanded to text in HBM.  S balances the two resources (see pack_fraction()).
         const uint64_t n = s.n_bytes;
         const double x = pack_fraction(ctx, s.has_qual, n);
-        uint64_t S = (uint64_t)((1.0 - x) * (double)n) & ~31ull;
-        if (S > n) S = n & ~31ull;
+        // multiple of 64: whole groups for the unpack kernel, and the packer's 64-byte loads never split a cache line
+        uint64_t S = (uint64_t)((1.0 - x) * (double)n) & ~63ull;
+        if (S > n) S = n & ~63ull;
         const uint64_t groups = (n - S + 31) / 32;
         const int mq = (int)(signed char)(unsigned char)((ctx->params.min_quality & 0xFF) + 33);
         SHK_CUDA(ctx, cudaEventRecord(s.ev_start, s.stream));
@@ -1032,6 +1044,7 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
             s.launches += (uint32_t)launch_scatter(ctx, a, s.assoc_cap, s.stream);
             SHK_CUDA(ctx, cudaGetLastError());
             SHK_CUDA(ctx, cudaEventRecord(s.ev_done, s.stream));
+            s.pre_assoc = 0;  // the list was rebuilt in a new buffer: fetch all of it below
             continue;
         }
         break;
@@ -1042,11 +1055,15 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
         s.h_assoc = nullptr;
         s.h_assoc_cap = c.n_assoc + c.n_assoc / 8 + 1024;
         SHK_CUDA(ctx, pinned_alloc((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
+        s.pre_assoc = 0;
     }
-    if (c.n_assoc)
-        SHK_CUDA(ctx, cudaMemcpyAsync(s.h_assoc, s.d_assoc, c.n_assoc * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
-    if (s.n_reads) SHK_CUDA(ctx, cudaMemcpyAsync(s.h_keep, s.d_keep, s.n_reads, cudaMemcpyDeviceToHost, s.stream));
-    SHK_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    if (c.n_assoc > s.pre_assoc) {  // what the read-back enqueued with the kernels did not cover
+        SHK_CUDA(ctx, cudaMemcpyAsync(s.h_assoc + s.pre_assoc, s.d_assoc + s.pre_assoc,
+                                      (c.n_assoc - s.pre_assoc) * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
+        ctx->d2h_bytes += (c.n_assoc - s.pre_assoc) * sizeof(shk_assoc);
+        SHK_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    }
+    if (s.n_reads) ctx->assoc_per_read.store((double)c.n_assoc / (double)s.n_reads);
     float k_ms = 0, t_ms = 0, p_ms = 0;
     cudaEventElapsedTime(&k_ms, s.ev_k0, s.ev_k1);
     cudaEventElapsedTime(&p_ms, s.ev_k0, s.ev_ka);
@@ -1112,6 +1129,7 @@ int shk_device_timer_stop(shk_ctx *ctx, float *ms)
 }
 
 uint64_t shk_h2d_bytes(const shk_ctx *ctx) { return ctx ? ctx->h2d_bytes.load() : 0; }
+uint64_t shk_d2h_bytes(const shk_ctx *ctx) { return ctx ? ctx->d2h_bytes.load() : 0; }
 
 int shk_upload_stats(const shk_ctx *ctx, double *packed_share, double *pack_gbases_per_s)
 {

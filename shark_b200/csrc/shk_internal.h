@@ -114,6 +114,7 @@ struct Slot {
     ChunkCounters *h_counters = nullptr;
     shk_assoc *h_assoc = nullptr;
     uint64_t h_assoc_cap = 0;
+    uint64_t pre_assoc = 0;  // associations whose read-back was enqueued with the kernels
     uint8_t *h_keep = nullptr;
     // host-packed upload (SHK_F_HOST_PACK): codes (8 bytes per 32 bases) then validity words (4 bytes)
     uint64_t *h_pack = nullptr, *d_pack = nullptr;
@@ -176,6 +177,8 @@ struct shk_ctx {
     uint64_t pol_first = 0, pol_last = 0;  // createpolicy evict_first / evict_last descriptors
     bool host_pack = false;                // shk_reads_submit packs the text on the host cores first
     std::atomic<uint64_t> h2d_bytes{0};    // bytes shk_reads_submit / upload copied to the device
+    std::atomic<uint64_t> d2h_bytes{0};    // result bytes copied back
+    std::atomic<double> assoc_per_read{-1.0};  // last chunk's associations per read: sizes the early read-back
     shk::PackControl pack;                 // split upload: feedback state of the packed share
     char err[512] = {0};
 };

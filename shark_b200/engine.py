@@ -278,6 +278,9 @@ class Shark:
     def h2d_bytes(self):
         return int(self.lib.shk_h2d_bytes(self.ctx))
 
+    def d2h_bytes(self):
+        return int(self.lib.shk_d2h_bytes(self.ctx))
+
     def kernel_launches(self):
         return int(self.lib.shk_kernel_launches(self.ctx))
 
