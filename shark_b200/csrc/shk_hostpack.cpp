@@ -118,8 +118,12 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) void pack_avx512(const uint
 
 bool have_avx512()
 {
+    // opt-in (SHK_PACK_AVX512=1): on the B200 host (16 threads, memory-bound) it measured no faster than AVX2 at
+    // the packer (50-53 vs 50-51 Gbases/s with qualities, 70-75 vs 69-85 without) and a few percent slower end to
+    // end on C2 (643-665 vs 665-691 M reads/s), profiles/hostpack_r1_v13.md
     static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
-                           __builtin_cpu_supports("avx512vl") && !getenv("SHK_PACK_SCALAR") && !getenv("SHK_PACK_AVX2");
+                           __builtin_cpu_supports("avx512vl") && !getenv("SHK_PACK_SCALAR") && !getenv("SHK_PACK_AVX2") &&
+                           getenv("SHK_PACK_AVX512") && atoi(getenv("SHK_PACK_AVX512")) != 0;
     return ok;
 }
 #endif

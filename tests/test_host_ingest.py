@@ -158,7 +158,8 @@ def test_host_pack_matches_numpy_restatement():
             "import hashlib; h = hashlib.md5();"
             "[h.update(a.tobytes()) for mq in (0, 20, 95) for a in capi.host_pack(s, q, mq)]; print(h.hexdigest())")
     outs = {}
-    for name, extra in (("default", {}), ("avx2", {"SHK_PACK_AVX2": "1"}), ("scalar", {"SHK_PACK_SCALAR": "1"})):
+    for name, extra in (("default", {}), ("avx512", {"SHK_PACK_AVX512": "1"}), ("avx2", {"SHK_PACK_AVX2": "1"}),
+                        ("scalar", {"SHK_PACK_SCALAR": "1"})):
         env = dict(os.environ, PYTHONPATH=ROOT, **extra)
         isa_used, digest = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
                                           check=True).stdout.decode().split()
@@ -167,4 +168,4 @@ def test_host_pack_matches_numpy_restatement():
             assert isa_used == "scalar"
         if name == "avx2":
             assert isa_used in ("avx2", "scalar")
-    assert outs["default"] == outs["avx2"] == outs["scalar"], outs
+    assert outs["default"] == outs["avx512"] == outs["avx2"] == outs["scalar"], outs
