@@ -219,6 +219,8 @@ def main():
                     help="how e2e moves the reads: 'plain' (text over PCIe), 'split' (part of every chunk packed to 3 bits "
                          "per base by the host cores while the rest is in flight, auto-balanced) or a fixed packed share "
                          "in (0, 1]; the other mode is measured too and reported as e2e_other")
+    ap.add_argument("--e2e-slots", type=int, default=3,
+                    help="chunks in flight in the e2e leg (slots reused round-robin by Shark.analyze_chunks)")
     ap.add_argument("--index", default="broadcast", choices=["broadcast", "sharded", "both"],
                     help="N > 1: build on rank 0 + NCCL broadcast (default), or every rank indexes one gene shard and the "
                          "filters are OR-merged by the library's P2P kernel; 'both' times both and checks they are identical")
@@ -383,7 +385,7 @@ def main():
 
     # ---- end to end through the public API: pinned host chunks -> H2D -> kernels -> D2H
     sh2 = sh  # same context; slots 0/1 are reused round-robin by analyze_chunks
-    sh2.n_slots = 2
+    sh2.n_slots = max(2, min(args.e2e_slots, n_chunks))
     d2h = [0]
 
     def on_result(r):
@@ -490,7 +492,7 @@ def main():
             "wall_ms_per_step": t_res_wall_max / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_step),
-                    "d2h_bytes_per_step": int(d2h_step), "upload": args.upload,
+                    "d2h_bytes_per_step": int(d2h_step), "upload": args.upload, "slots": sh2.n_slots,
                     "packed_share": leg_stats[args.upload][0], "pack_gbases_per_s": leg_stats[args.upload][1],
                     "ms_per_step": t_e2e_max / args.steps * 1e3, "wall_ms_per_step": t_e2e_wall_max / args.steps * 1e3},
             "e2e_other": {"upload": other_mode, "value": total_reads / o_dev_max, "unit": "reads/s",

@@ -63,6 +63,7 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *seq, const uint8_t
                                           0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
     // mq outside the signed-char range: the comparison is constant (mq is (signed char) in practice)
     const bool all_masked = mq > 127, none_masked = mq < -128;
+    static const bool nt = !getenv("SHK_PACK_NO_NT");
     for (uint64_t g = g0; g < ge; ++g) {
         __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(seq + g * 32));
         if (qual && !none_masked) {
@@ -73,14 +74,21 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *seq, const uint8_t
         const __m256i lo = _mm256_or_si256(v, k20);
         const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(lo, ca), _mm256_cmpeq_epi8(lo, cc)),
                                            _mm256_or_si256(_mm256_cmpeq_epi8(lo, cg), _mm256_cmpeq_epi8(lo, ct)));
-        valid[g] = (uint32_t)_mm256_movemask_epi8(ok);
+        const uint32_t vmask = (uint32_t)_mm256_movemask_epi8(ok);
         __m256i x = _mm256_and_si256(_mm256_and_si256(_mm256_srli_epi16(v, 1), k3), ok);
         x = _mm256_maddubs_epi16(x, m14);
         x = _mm256_madd_epi16(x, m116);
         x = _mm256_shuffle_epi8(x, pick);
         const uint64_t lo32 = (uint32_t)_mm256_extract_epi32(x, 0), hi32 = (uint32_t)_mm256_extract_epi32(x, 4);
-        codes[g] = lo32 | (hi32 << 32);
+        if (nt) {  // streaming stores: the output is read next by the DMA engine, not by this core
+            _mm_stream_si64(reinterpret_cast<long long *>(codes + g), (long long)(lo32 | (hi32 << 32)));
+            _mm_stream_si32(reinterpret_cast<int *>(valid + g), (int)vmask);
+        } else {
+            codes[g] = lo32 | (hi32 << 32);
+            valid[g] = vmask;
+        }
     }
+    if (nt) _mm_sfence();
     if (ge < g1) pack_scalar(seq, qual, mq, n, ge > g0 ? ge : g0, g1, codes, valid);
 }
 
