@@ -774,10 +774,16 @@ int shk_index_build_sharded(shk_ctx **ctxs, uint32_t n, const uint8_t *ref_bases
     // one host thread per context per step; joining the threads is the barrier
     auto step = [&](auto &&fn) {
         std::vector<std::thread> th;
-        for (uint32_t i = 0; i < n; ++i)
-            th.emplace_back([&, i] {
+        for (uint32_t i = 0; i < n; ++i) {
+            auto body = [&, i] {
                 if (rcs[i] == 0) rcs[i] = fn(i);
-            });
+            };
+            try {
+                th.emplace_back(body);
+            } catch (...) {  // no thread to be had: run this context's step on the calling thread
+                body();
+            }
+        }
         for (auto &t : th) t.join();
         for (uint32_t i = 0; i < n; ++i)
             if (rcs[i]) return rcs[i];

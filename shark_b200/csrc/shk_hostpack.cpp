@@ -167,7 +167,13 @@ class Pool {
   public:
     explicit Pool(int n_workers)
     {
-        for (int i = 0; i < n_workers; ++i) workers_.emplace_back([this] { loop(); });
+        for (int i = 0; i < n_workers; ++i) {
+            try {
+                workers_.emplace_back([this] { loop(); });
+            } catch (...) {  // thread limit reached: work with the threads we have
+                break;
+            }
+        }
     }
     ~Pool()
     {
