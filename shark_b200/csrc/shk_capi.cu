@@ -161,6 +161,14 @@ static cudaError_t pinned_alloc(void **ptr, size_t bytes)
     return cudaMallocHost(ptr, bytes ? bytes : 1);
 }
 
+// The pack threads are created on first use and inherit the creating thread's affinity for good: create them
+// while confined to the GPU's NUMA node, next to the pinned staging buffers they read and write.
+static void start_pack_pool_numa_local()
+{
+    NumaLocalScope numa;
+    (void)host_pack_threads();
+}
+
 static int alloc_slot(shk_ctx *ctx, Slot &s)
 {
     const uint64_t R = ctx->max_reads, B = ctx->max_bytes;
@@ -190,6 +198,7 @@ static int alloc_slot(shk_ctx *ctx, Slot &s)
     SHK_CUDA(ctx, pinned_alloc((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
     SHK_CUDA(ctx, pinned_alloc((void **)&s.h_keep, R + 64));
     if (ctx->host_pack) {
+        start_pack_pool_numa_local();
         s.pack_groups_cap = (B + 63) / 32;
         SHK_CUDA(ctx, cudaMalloc((void **)&s.d_pack, s.pack_groups_cap * 12));
         SHK_CUDA(ctx, pinned_alloc((void **)&s.h_pack, s.pack_groups_cap * 12));
@@ -1153,6 +1162,7 @@ int shk_set_upload_mode(shk_ctx *ctx, uint32_t host_pack, uint32_t permille)
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
     for (uint32_t i = 0; i < ctx->n_slots; ++i)
         if (ctx->slots[i].pending) return fail(ctx, SHK_E_STATE, "slot %u has a chunk in flight", i);
+    if (host_pack) start_pack_pool_numa_local();
     if (host_pack)
         for (uint32_t i = 0; i < ctx->n_slots; ++i) {
             Slot &s = ctx->slots[i];
