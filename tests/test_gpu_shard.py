@@ -8,7 +8,6 @@
 
 The yardstick is the oracle (bit-exact), as in test_gpu_parity.py.
 """
-import ctypes as C
 import os
 
 import numpy as np
