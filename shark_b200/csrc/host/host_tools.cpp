@@ -1,6 +1,7 @@
 // Host-side test and measurement tool (no device code, no CUDA): used by tests/test_host_ingest.py
 // and for tuning the ingest/output stages on a machine without a GPU.
 //   host_tools scan-check FILE [BLOCK_BYTES]   FastqScanner vs FastxReader, outcome by outcome
+//   host_tools scan-dump FILE [BLOCK_BYTES [N]]  count / end status of the records the scanner yields, hash of the first N
 //   host_tools ingest-bench FQ1 [FQ2] [--qual]  scanner -> batcher -> writer with every read kept
 //                                               (results faked: this measures the host stages only)
 #include <chrono>
@@ -62,6 +63,37 @@ static int scan_check(const char *path, size_t block_bytes)
     return 0;
 }
 
+// Records up to the first non-record outcome: count, that outcome's status, FNV-1a over name \0 seq \0 qual \0 of
+// the first `hash_first` records.
+static int scan_dump(const char *path, size_t block_bytes, uint64_t hash_first)
+{
+    FastqScanner sc(path, block_bytes);
+    if (!sc.ok()) {
+        printf("OPEN_FAILED\n");
+        return 0;
+    }
+    uint64_t h = 0xCBF29CE484222325ull, count = 0;
+    auto eat = [&](const char *p, uint32_t n) {
+        for (uint32_t i = 0; i < n; ++i) h = (h ^ (unsigned char)p[i]) * 0x100000001B3ull;
+        h = (h ^ 0) * 0x100000001B3ull;
+    };
+    for (;;) {
+        std::unique_ptr<Block> b = sc.next(1000);
+        for (const Rec &r : b->recs) {
+            if (r.status < 0) {
+                printf("DUMP count=%llu last=%d hash=%016llx\n", (unsigned long long)count, r.status, (unsigned long long)h);
+                return 0;
+            }
+            if (count < hash_first) {
+                eat(r.name, r.name_len);
+                eat(r.seq, r.seq_len);
+                eat(r.qual, r.qual_len);
+            }
+            ++count;
+        }
+    }
+}
+
 static int scan_bench(const char *path)
 {
     const double t0 = now();
@@ -118,6 +150,7 @@ static int ingest_bench(const char *f1, const char *f2, bool with_qual)
 int main(int argc, char **argv)
 {
     if (argc >= 3 && std::string(argv[1]) == "scan-check") return scan_check(argv[2], argc > 3 ? (size_t)atol(argv[3]) : (8u << 20));
+    if (argc >= 3 && std::string(argv[1]) == "scan-dump") return scan_dump(argv[2], argc > 3 ? (size_t)atol(argv[3]) : (8u << 20), argc > 4 ? strtoull(argv[4], nullptr, 10) : ~0ull);
     if (argc >= 3 && std::string(argv[1]) == "scan-bench") return scan_bench(argv[2]);
     if (argc >= 3 && std::string(argv[1]) == "ingest-bench") {
         const char *f2 = nullptr;

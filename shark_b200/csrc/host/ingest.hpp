@@ -27,6 +27,8 @@
 #include <thread>
 #include <vector>
 
+#include "bgzf.hpp"
+
 namespace shkhost {
 
 // One kseq_read() outcome.  Pointers are not NUL-terminated and stay valid while the Block lives.
@@ -109,9 +111,10 @@ public:
         unsigned char magic[2] = {0, 0};
         const ssize_t m = pread(fd_, magic, 2, 0);
         if (m == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-            f_ = gzdopen(fd_, "r");
-            if (f_) gzbuffer(f_, 1u << 20);
-            else {
+            // blocked gzip (bgzip): members located up front and inflated in parallel (bgzf.hpp); anything
+            // else, and whatever follows the first member that is not such a block, goes through zlib
+            if (bgzf_.open(fd_)) use_bgzf_ = true;
+            else if (!open_zlib(0)) {
                 close(fd_);
                 fd_ = -1;
             }
@@ -119,6 +122,7 @@ public:
     }
     ~FastqScanner()
     {
+        bgzf_.shutdown();     // its read-ahead thread uses fd_
         if (f_) gzclose(f_);  // closes fd_ too
         else if (fd_ >= 0) close(fd_);
     }
@@ -154,6 +158,14 @@ public:
 private:
     enum { kOk = 0, kNeedMore = 1, kFormat = 2 };
 
+    bool open_zlib(uint64_t at)
+    {
+        if (lseek(fd_, (off_t)at, SEEK_SET) < 0) return false;
+        f_ = gzdopen(fd_, "r");
+        if (f_) gzbuffer(f_, 1u << 20);
+        return f_ != nullptr;
+    }
+
     // ---- buffer management ---------------------------------------------------------------
     void attach_buffer()
     {
@@ -175,7 +187,25 @@ private:
         size_t got = 0;
         while (got < block_bytes_) {  // gzread returns short counts at member boundaries
             long n;
-            if (f_) {
+            if (use_bgzf_) {
+                n = bgzf_.read(nb.get() + tail + got, block_bytes_ - got);
+                if (n == BgzfSource::kHandover) {
+                    // the member at this offset is zlib's: a gzip member continues the stream exactly as under
+                    // gzread; anything else after gzip data is trailing garbage, which gzread ignores (gz_look)
+                    use_bgzf_ = false;
+                    const uint64_t at = bgzf_.handover_offset();
+                    unsigned char mg[2] = {0, 0};
+                    if (pread(fd_, mg, 2, (off_t)at) == 2 && mg[0] == 0x1f && mg[1] == 0x8b) {
+                        if (!open_zlib(at)) n = -1;
+                        else continue;
+                    } else {
+                        n = 0;
+                        garbage_tail_ = true;
+                    }
+                }
+            } else if (garbage_tail_) {
+                n = 0;
+            } else if (f_) {
                 n = gzread(f_, nb.get() + tail + got, (unsigned)(block_bytes_ - got));
             } else {
                 do n = (long)read(fd_, nb.get() + tail + got, block_bytes_ - got);
@@ -348,7 +378,9 @@ private:
     }
 
     int fd_ = -1;
-    gzFile f_ = nullptr;  // set when the input is gzip
+    gzFile f_ = nullptr;  // set when the input is gzip read through zlib
+    BgzfSource bgzf_;     // blocked gzip: parallel inflate, until a member that is not a BGZF block
+    bool use_bgzf_ = false, garbage_tail_ = false;
     size_t block_bytes_;
     std::shared_ptr<char> buf_;
     size_t pos_ = 0, end_ = 0;

@@ -326,6 +326,7 @@ int main(int argc, char *argv[])
         }
     }
 
+    if (opt.n_threads > 1) shkhost::set_ingest_threads(opt.n_threads);  // -t: inflate threads for blocked-gzip samples
     tstamp("reference parsed");
     std::vector<shk_ctx *> ctxs((size_t)opt.gpus, nullptr);
     for (int g = 0; g < opt.gpus; ++g) {

@@ -135,3 +135,37 @@ def test_cli_against_live_reference_binary(tmp_path):
         assert out == out0 and len(out) > 1000
         for a, b in (("m1.fq", "r1.fq"), ("m2.fq", "r2.fq")):
             assert open(str(tmp_path / a), "rb").read() == open(str(tmp_path / b), "rb").read()
+
+
+@pytest.mark.gpu
+def test_cli_blocked_gzip_inputs_parallel_inflate(tmp_path):
+    """Samples compressed as BGZF (bgzip): the CLI inflates the blocks in parallel (`-t 4` = four inflate threads per
+    file + read-ahead, csrc/host/bgzf.hpp) and must print what it prints for the plain files - and what the reference
+    prints when it reads the very same .gz files through gzread."""
+    import random
+    from test_host_ingest import _bgzf
+    import numpy as np
+    from shark_b200 import synth
+    names, bases, rec_off = synth.make_reference(60, seed=7)
+    synth.write_fasta(str(tmp_path / "ref.fa"), names, bases, rec_off)
+    n = 150000
+    seq, qual, _ = synth.make_reads(bases, 60, n, 100, True, seed=13, varied_qual=True, want_qual=True)
+    synth.write_fastq(str(tmp_path / "a_1.fq"), str(tmp_path / "a_2.fq"), seq, qual, n, 100, True)
+    rng = random.Random(3)
+    for m in ("1", "2"):
+        data = open(str(tmp_path / ("a_%s.fq" % m)), "rb").read()
+        open(str(tmp_path / ("a_%s.fq.gz" % m)), "wb").write(b"".join(_bgzf(data, rng)))
+    flags = ["-k", "21", "-q", "20"]
+    rc, out, err = run_cli(["-r", "ref.fa", "-1", "a_1.fq", "-2", "a_2.fq", "-o", "p1.fq", "-p", "p2.fq"] + flags, tmp_path)
+    assert rc == 0, err.decode()
+    rc, outz, err = run_cli(["-r", "ref.fa", "-1", "a_1.fq.gz", "-2", "a_2.fq.gz", "-o", "z1.fq", "-p", "z2.fq", "-t", "4",
+                             "--chunk-reads", "50000"] + flags, tmp_path)
+    assert rc == 0, err.decode()
+    assert outz == out and len(out) > 100000
+    for a, b in (("z1.fq", "p1.fq"), ("z2.fq", "p2.fq")):
+        assert open(str(tmp_path / a), "rb").read() == open(str(tmp_path / b), "rb").read()
+    if os.path.exists(REF):
+        rc0, out0, _ = run_cli(["-r", "ref.fa", "-1", "a_1.fq.gz", "-2", "a_2.fq.gz", "-o", "r1.fq", "-p", "r2.fq"] + flags,
+                               tmp_path, exe=REF)
+        assert rc0 == 0 and out0 == out
+        assert open(str(tmp_path / "r1.fq"), "rb").read() == open(str(tmp_path / "z1.fq"), "rb").read()
