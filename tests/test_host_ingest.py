@@ -329,3 +329,33 @@ def test_bgzf_damaged_files_fail_cleanly(tool, tmp_path, seed, monkeypatch):
             assert last in (-1, -2, -3), (name, last)
             assert sure <= count <= n_rec, (name, block, count, whole_records)
             assert h == _fnv_records(recs[:sure]), (name, block, count)
+
+
+def test_host_pack_against_the_oracle_masking_and_base_table():
+    """The split upload must carry exactly what the oracle's (= the reference's) rules make of every byte: masking
+    by shko_mask (FastqSplitter.hpp:104-109), validity and base by shko_base_code (to_int, kmer_utils.hpp:29-41)."""
+    import numpy as np
+    from oracle import pyoracle as po
+    from shark_b200 import capi
+    L = po.lib()
+    code_of = np.array([L.shko_base_code(b) for b in range(256)], np.int64)   # -1 invalid, else A C G T = 0..3
+    raw_of_code = np.array([0, 1, 3, 2])                                       # the packed code is (byte >> 1) & 3: A 0 C 1 T 2 G 3
+    rng = np.random.default_rng(21)
+    n = 20000
+    seq = rng.integers(0, 256, n, dtype=np.uint8)
+    m = rng.random(n) < 0.6
+    seq[m] = np.frombuffer(b"ACGTacgtN", np.uint8)[rng.integers(0, 9, int(m.sum()))]
+    qual = rng.integers(0, 256, n, dtype=np.uint8)
+    sh = np.arange(32, dtype=np.uint64)
+    for q in (0, 1, 20, 41, 94, 95, 127, 200, 222, 223, 255):
+        masked = po.mask(seq, qual, q) if q else seq
+        code = code_of[masked]
+        ok = code >= 0
+        want_codes = np.where(ok, raw_of_code[np.maximum(code, 0)], 0).astype(np.uint64)
+        g = (n + 31) // 32
+        pad = g * 32 - n
+        want_v = (np.concatenate([ok, np.zeros(pad, bool)]).reshape(g, 32).astype(np.uint64) << sh).sum(1).astype(np.uint32)
+        want_c = (np.concatenate([want_codes, np.zeros(pad, np.uint64)]).reshape(g, 32) << (2 * sh)).sum(1).astype(np.uint64)
+        c, v = capi.host_pack(seq, qual, q, parallel=bool(q & 1))
+        assert np.array_equal(v, want_v), q
+        assert np.array_equal(c, want_c), q
