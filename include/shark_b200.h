@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SHK_ABI_VERSION 4
+#define SHK_ABI_VERSION 5
 
 typedef enum shk_status {
     SHK_OK = 0,
@@ -65,10 +65,19 @@ typedef struct shk_params {
  * With this flag shk_reads_submit sends the first part of a chunk as it is and, WHILE that copy runs,
  * reduces the rest to what the kernels use of a text byte - one validity bit (after the -q masking rule,
  * FastqSplitter.hpp:104-109) and a 2-bit code - on the host cores (AVX2, all pack threads, blocking); that
- * part crosses the link at 0.375 bytes per base instead of 1 (2 with qualities) and a kernel expands it
- * back to text in HBM.  The split point balances host and link (measured packing rate; host_pack_permille
+ * part crosses the link at 0.375 bytes per base instead of 1 (2 with qualities) and is classified by the
+ * packed variant of the kernels (the chunk is split at a read boundary: text reads and packed reads).  The split point balances host and link (measured packing rate; host_pack_permille
  * fixes it).  Results are identical (the parity suite runs both ways). */
 #define SHK_F_HOST_PACK 4u
+/* Results stay in the compact form in which they cross the link (shk_chunk_result.gene16 / multi): assoc and
+ * keep are NULL and shk_reads_collect does no per-read host work.  Without the flag shk_reads_collect expands
+ * the compact form into assoc / keep on the calling thread (about 1 ms per million reads). */
+#define SHK_F_COMPACT_RESULTS 8u
+
+/* Compact per-read result words (shk_chunk_result.gene16). */
+#define SHK_GENE_NONE 0xFFFFu  /* no association: the read is not reported                                */
+#define SHK_GENE_MULTI 0xFFFEu /* the read's associations are in shk_chunk_result.multi (two or more
+                                  genes tie, or its single gene index is one of these two values)       */
 
 typedef struct shk_index_info {
     uint32_t n_records;  /* FASTA records given (= legend_ID.size(), FastaSplitter.hpp:48)         */
@@ -101,10 +110,10 @@ typedef struct shk_assoc {
 
 typedef struct shk_chunk_result {
     uint64_t n_assoc;       /* associations, ordered by read_idx then gene_idx                     */
-    const shk_assoc *assoc; /* library-owned pinned host memory, valid until the slot's next
-                               submit                                                                */
+    const shk_assoc *assoc; /* library-owned host memory, valid until the slot's next submit; NULL
+                               with SHK_F_COMPACT_RESULTS                                           */
     const uint8_t *keep;    /* n_reads flags: 1 = read has >= 1 association (is written to the
-                               filtered FASTQ, ReadOutput.hpp:44-47)                                */
+                               filtered FASTQ, ReadOutput.hpp:44-47); NULL with SHK_F_COMPACT_RESULTS */
     uint32_t n_reads;
     uint32_t n_slow_reads;  /* reads that took the exact large-table path                          */
     uint64_t n_probes;      /* valid k-mer windows probed (counted on the device)                  */
@@ -116,7 +125,20 @@ typedef struct shk_chunk_result {
     uint64_t n_extended;    /* probes resolved by anchor-and-extend, without a table access        */
     uint64_t n_table_loads; /* front-table entries the fast kernel loaded (extension mode only;
                                the rest of the probes were answered by the coarse miss filter)     */
+    /* The compact form - what actually crosses the link (2 bytes per read + 8 per tied association instead
+     * of 8 per association + 1 per read): what ReadOutput needs per read is "which gene, if any"
+     * (ReadOutput.hpp:37-50), and all but a few percent of the kept reads have exactly one. */
+    const uint16_t *gene16; /* n_reads words: gene index, SHK_GENE_NONE or SHK_GENE_MULTI; library-owned
+                               pinned host memory, valid until the slot's next submit               */
+    const shk_assoc *multi; /* the associations of the SHK_GENE_MULTI reads, ordered by read_idx then
+                               gene_idx (same lifetime)                                             */
+    uint64_t n_multi;
+    uint64_t n_kept;        /* reads with >= 1 association                                         */
 } shk_chunk_result;
+
+/* Expands a compact result into the association list (n_assoc entries) and the keep flags (n_reads); either
+ * output may be NULL.  Pure host function. */
+int shk_result_expand(const shk_chunk_result *result, shk_assoc *assoc, uint8_t *keep);
 
 /* ---- lifetime ------------------------------------------------------------------------ */
 
@@ -294,10 +316,20 @@ int shk_free_pinned(void *ptr);
  *   qual          same layout (joiner byte 0x1B, FastqSplitter.hpp:84); may be NULL when
  *                 min_quality == 0 (the reference never looks at qualities then)
  *   read_offsets  n_reads+1 byte offsets into seq/qual
- * Host pointers (pinned memory makes the copies asynchronous).  Asynchronous on the slot's
- * stream: returns once the work is enqueued. */
+ * Host pointers (pinned memory makes the copies asynchronous); they must stay valid until the slot is
+ * collected.  Asynchronous on the slot's stream: returns once the work is enqueued (with SHK_F_HOST_PACK the
+ * packing of the chunk's second part happens inside this call, on the pack threads).  A slot must be
+ * collected before it is submitted to again (SHK_E_STATE otherwise). */
 int shk_reads_submit(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint8_t *qual,
                      const uint32_t *read_offsets, uint32_t n_reads);
+/* The same chunk already reduced to what the kernels use of a text byte - 2-bit code and validity bit,
+ * exactly what shk_host_pack produces from (seq, qual, min_quality) of the call above: codes[ceil(n/32)]
+ * 64-bit words, valid[ceil(n/32)] 32-bit words, n = read_offsets[n_reads].  The -q masking rule
+ * (FastqSplitter.hpp:104-109) is already in the validity bits, so qualities never cross the link; the
+ * classification kernels read this form directly (0.375 bytes per base).  This is what the CLI's batcher
+ * emits while it copies records. */
+int shk_reads_submit_packed(shk_ctx *ctx, uint32_t slot, const uint64_t *codes, const uint32_t *valid,
+                            const uint32_t *read_offsets, uint32_t n_reads);
 /* Blocks until the slot's chunk is done and returns its result. */
 int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *result);
 
@@ -305,6 +337,8 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *result);
  * analyze_resident runs only the kernels on the resident chunk (repeatable). */
 int shk_reads_upload(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint8_t *qual,
                      const uint32_t *read_offsets, uint32_t n_reads);
+int shk_reads_upload_packed(shk_ctx *ctx, uint32_t slot, const uint64_t *codes, const uint32_t *valid,
+                            const uint32_t *read_offsets, uint32_t n_reads);
 int shk_reads_analyze_resident(shk_ctx *ctx, uint32_t slot);
 
 /* Device-side stopwatch over ALL slots of a context (CUDA events, no host clock): start records

@@ -25,6 +25,7 @@ EXPORTED = [
     "shk_set_options", "shk_shard_begin", "shk_shard_open", "shk_shard_close", "shk_shard_merge", "shk_shard_rank",
     "shk_shard_finish", "shk_shard_end", "shk_shard_cuts", "shk_index_build_sharded", "shk_index_save", "shk_index_load",
     "shk_host_pack", "shk_host_pack_info", "shk_h2d_bytes", "shk_d2h_bytes", "shk_set_upload_mode", "shk_upload_stats",
+    "shk_reads_submit_packed", "shk_reads_upload_packed", "shk_result_expand",
 ]
 
 
@@ -41,7 +42,8 @@ class Params(C.Structure):
                 ("host_pack_permille", C.c_uint32), ("reserved", C.c_uint32 * 6)]
 
 
-F_EXTEND_ON, F_EXTEND_OFF, F_HOST_PACK = 1, 2, 4
+F_EXTEND_ON, F_EXTEND_OFF, F_HOST_PACK, F_COMPACT_RESULTS = 1, 2, 4, 8
+GENE_NONE, GENE_MULTI = 0xFFFF, 0xFFFE
 
 
 class IndexInfo(C.Structure):
@@ -70,7 +72,9 @@ class ChunkResult(C.Structure):
     _fields_ = [("n_assoc", C.c_uint64), ("assoc", C.POINTER(Assoc)), ("keep", C.POINTER(C.c_uint8)),
                 ("n_reads", C.c_uint32), ("n_slow_reads", C.c_uint32), ("n_probes", C.c_uint64), ("n_hits", C.c_uint64),
                 ("analyze_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
-                ("probe_kernel_ms", C.c_float), ("n_extended", C.c_uint64), ("n_table_loads", C.c_uint64)]
+                ("probe_kernel_ms", C.c_float), ("n_extended", C.c_uint64), ("n_table_loads", C.c_uint64),
+                ("gene16", C.POINTER(C.c_uint16)), ("multi", C.POINTER(Assoc)), ("n_multi", C.c_uint64),
+                ("n_kept", C.c_uint64)]
 
 
 _lib = None
@@ -105,6 +109,9 @@ def load():
     L.shk_free_pinned.argtypes = [vp]
     L.shk_reads_submit.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32]
     L.shk_reads_collect.argtypes = [vp, C.c_uint32, C.POINTER(ChunkResult)]
+    L.shk_reads_submit_packed.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32]
+    L.shk_reads_upload_packed.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32]
+    L.shk_result_expand.argtypes = [C.POINTER(ChunkResult), vp, vp]
     L.shk_reads_upload.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint32]
     L.shk_reads_analyze_resident.argtypes = [vp, C.c_uint32]
     L.shk_device_timer_start.argtypes = [vp]

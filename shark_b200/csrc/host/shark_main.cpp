@@ -369,6 +369,7 @@ int main(int argc, char *argv[])
     if (!replicated)
         for (int g = 1; g < opt.gpus; ++g) SHK_TRY(ctxs[g], shk_index_replicate(ctxs[0], ctxs[g]));
     pelapsed("Second switch performed");
+    tstamp("index ready");
     std::vector<uint8_t>().swap(ref_bases);
 
     // ---- sample stage: scanners -> batcher thread -> (this thread: submit / collect) -> writer thread

@@ -50,13 +50,15 @@ static void free_slot(Slot &s)
     cudaFree(s.d_tile_sums);
     cudaFree(s.d_tile_base);
     cudaFree(s.d_counters);
-    cudaFree(s.d_assoc);
-    cudaFree(s.d_keep);
+    cudaFree(s.d_gene16);
+    cudaFree(s.d_multi);
     cudaFree(s.d_slow_table);
     cudaFree(s.d_slow_stamp);
     cudaFreeHost(s.h_counters);
-    cudaFreeHost(s.h_assoc);
-    cudaFreeHost(s.h_keep);
+    cudaFreeHost(s.h_gene16);
+    cudaFreeHost(s.h_multi);
+    free(s.h_assoc);
+    free(s.h_keep);
     cudaFreeHost(s.h_pack);
     cudaFree(s.d_pack);
     if (s.ev_start) cudaEventDestroy(s.ev_start);
@@ -190,17 +192,19 @@ static int alloc_slot(shk_ctx *ctx, Slot &s)
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_tile_sums, (tiles + 1) * 4));
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_tile_base, (tiles + 1) * 4));
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_counters, sizeof(ChunkCounters)));
-    s.assoc_cap = R + R / 4 + 1024;
-    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_assoc, s.assoc_cap * sizeof(shk_assoc)));
-    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_keep, R + 64));
+    s.multi_cap = R / 4 + 1024;
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_multi, s.multi_cap * sizeof(shk_assoc)));
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_gene16, (R + 64) * 2));
     SHK_CUDA(ctx, pinned_alloc((void **)&s.h_counters, sizeof(ChunkCounters)));
-    s.h_assoc_cap = s.assoc_cap;
-    SHK_CUDA(ctx, pinned_alloc((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
-    SHK_CUDA(ctx, pinned_alloc((void **)&s.h_keep, R + 64));
+    s.h_multi_cap = s.multi_cap;
+    SHK_CUDA(ctx, pinned_alloc((void **)&s.h_multi, s.h_multi_cap * sizeof(shk_assoc)));
+    SHK_CUDA(ctx, pinned_alloc((void **)&s.h_gene16, (R + 64) * 2));
+    // packed reads: + 2 groups so that the kernels' prefetch of the following group stays inside
+    s.pack_groups_cap = (B + 31) / 32 + 2;
+    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_pack, s.pack_groups_cap * 12));
+    SHK_CUDA(ctx, cudaMemset(s.d_pack, 0, s.pack_groups_cap * 12));
     if (ctx->host_pack) {
         start_pack_pool_numa_local();
-        s.pack_groups_cap = (B + 63) / 32;
-        SHK_CUDA(ctx, cudaMalloc((void **)&s.d_pack, s.pack_groups_cap * 12));
         SHK_CUDA(ctx, pinned_alloc((void **)&s.h_pack, s.pack_groups_cap * 12));
     }
     return SHK_OK;
@@ -213,6 +217,10 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     a.qual = s.has_qual ? s.d_qual : nullptr;
     a.off = s.d_off;
     a.n_reads = s.n_reads;
+    a.pcodes = s.d_pack;
+    a.pvalid = reinterpret_cast<const uint32_t *>(s.d_pack + s.pack_groups_cap);
+    a.pack_first = s.pack_first;
+    a.pack_base = s.pack_base;
     a.sectors = ctx->index.sectors;
     a.entries = ctx->index.entries;
     a.csr_off = ctx->index.csr_off;
@@ -244,8 +252,8 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     a.slow_stamp = s.d_slow_stamp;
     a.n_slow_slabs = ctx->n_slow_slabs;
     a.tile_base = s.d_tile_base;
-    a.assoc = s.d_assoc;
-    a.keep = s.d_keep;
+    a.gene16 = s.d_gene16;
+    a.multi = s.d_multi;
     return a;
 }
 
@@ -276,36 +284,40 @@ static int enqueue_chunk_kernels(shk_ctx *ctx, Slot &s)
 {
     SHK_CUDA(ctx, cudaMemsetAsync(s.d_counters, 0, sizeof(ChunkCounters), s.stream));
     ReadKernelArgs a = make_args(ctx, s);
-    s.launches += (uint32_t)launch_read_kernels(ctx, a, s.assoc_cap, s.stream, s.ev_k0, s.ev_ka, s.ev_k1);
+    s.launches += (uint32_t)launch_read_kernels(ctx, a, s.multi_cap, s.stream, s.ev_k0, s.ev_ka, s.ev_k1);
     SHK_CUDA(ctx, cudaGetLastError());
     SHK_CUDA(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(ChunkCounters), cudaMemcpyDeviceToHost, s.stream));
-    // Results follow on the stream, before the host knows their size: as many associations as the previous chunks
-    // produced per read (+5 %), the rest - if any - is fetched by shk_reads_collect.  This keeps the read-back
-    // off the collecting thread's critical path and lets it overlap the other slots' kernels.
-    const double per_read = ctx->assoc_per_read.load();
-    uint64_t pre = per_read < 0 ? s.n_reads : (uint64_t)(per_read * 1.05 * s.n_reads) + 4096;
-    pre = std::min(pre, std::min(s.assoc_cap, s.h_assoc_cap));
+    // Results follow on the stream, before the host knows their size: the per-read words, and as many multi
+    // entries as the previous chunks produced per read (+10 %); the rest - if any - is fetched by
+    // shk_reads_collect.  This keeps the read-back off the collecting thread's critical path and lets it
+    // overlap the other slots' kernels.
+    const double per_read = ctx->multi_per_read.load();
+    uint64_t pre = per_read < 0 ? s.n_reads / 8 : (uint64_t)(per_read * 1.10 * s.n_reads) + 1024;
+    pre = std::min(pre, std::min(s.multi_cap, s.h_multi_cap));
     if (!s.n_reads) pre = 0;
-    if (pre) SHK_CUDA(ctx, cudaMemcpyAsync(s.h_assoc, s.d_assoc, pre * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
-    if (s.n_reads) SHK_CUDA(ctx, cudaMemcpyAsync(s.h_keep, s.d_keep, s.n_reads, cudaMemcpyDeviceToHost, s.stream));
-    s.pre_assoc = pre;
-    ctx->d2h_bytes += pre * sizeof(shk_assoc) + s.n_reads + sizeof(ChunkCounters);
+    if (s.n_reads) SHK_CUDA(ctx, cudaMemcpyAsync(s.h_gene16, s.d_gene16, (size_t)s.n_reads * 2, cudaMemcpyDeviceToHost, s.stream));
+    if (pre) SHK_CUDA(ctx, cudaMemcpyAsync(s.h_multi, s.d_multi, pre * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
+    s.pre_multi = pre;
+    ctx->d2h_bytes += pre * sizeof(shk_assoc) + (uint64_t)s.n_reads * 2 + sizeof(ChunkCounters);
     SHK_CUDA(ctx, cudaEventRecord(s.ev_done, s.stream));
     return SHK_OK;
 }
 
-static int check_chunk(shk_ctx *ctx, uint32_t slot, const uint32_t *off, uint32_t n_reads, const uint8_t *qual)
+static int check_chunk(shk_ctx *ctx, uint32_t slot, const uint32_t *off, uint32_t n_reads, const uint8_t *qual,
+                       bool packed_input = false)
 {
     if (!ctx) return SHK_E_ARG;
     if (slot >= ctx->n_slots) return fail(ctx, SHK_E_ARG, "slot %u out of range (n_slots=%u)", slot, ctx->n_slots);
     if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index: call shk_index_build first");
+    if (ctx->slots[slot].pending)
+        return fail(ctx, SHK_E_STATE, "slot %u has an uncollected chunk: call shk_reads_collect first", slot);
     if (n_reads > ctx->max_reads)
         return fail(ctx, SHK_E_CAPACITY, "chunk of %u reads exceeds max_reads_per_chunk=%u", n_reads, ctx->max_reads);
     if (n_reads && !off) return fail(ctx, SHK_E_ARG, "read_offsets is NULL");
     if (n_reads && (uint64_t)off[n_reads] > ctx->max_bytes)
         return fail(ctx, SHK_E_CAPACITY, "chunk of %u bytes exceeds max_bytes_per_chunk=%llu", off[n_reads],
                     (unsigned long long)ctx->max_bytes);
-    if ((ctx->params.min_quality & 0xFF) != 0 && !qual && n_reads)
+    if (!packed_input && (ctx->params.min_quality & 0xFF) != 0 && !qual && n_reads)
         return fail(ctx, SHK_E_ARG, "min_quality != 0 needs the quality bytes");
     return SHK_OK;
 }
@@ -348,6 +360,17 @@ static double pack_fraction(shk_ctx *ctx, bool has_qual, uint64_t n)
     return pc.x;
 }
 
+// Copies `groups` code words and validity words of a packed stream into the slot's device buffers.
+static int enqueue_packed_copy(shk_ctx *ctx, Slot &s, const uint64_t *codes, const uint32_t *valid, uint64_t groups)
+{
+    if (!groups) return SHK_OK;
+    SHK_CUDA(ctx, cudaMemcpyAsync(s.d_pack, codes, groups * 8, cudaMemcpyHostToDevice, s.stream));
+    SHK_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<uint32_t *>(s.d_pack + s.pack_groups_cap), valid, groups * 4,
+                                  cudaMemcpyHostToDevice, s.stream));
+    ctx->h2d_bytes += groups * 12;
+    return SHK_OK;
+}
+
 static int enqueue_upload(shk_ctx *ctx, Slot &s, const uint8_t *seq, const uint8_t *qual, const uint32_t *off,
                           uint32_t n_reads, bool allow_pack)
 {
@@ -355,62 +378,71 @@ static int enqueue_upload(shk_ctx *ctx, Slot &s, const uint8_t *seq, const uint8
     s.n_bytes = n_reads ? off[n_reads] : 0;
     s.has_qual = (ctx->params.min_quality & 0xFF) != 0;
     s.launches = 0;
-    if (allow_pack && ctx->host_pack && s.n_bytes) {
-        // Split upload: the first S bytes of the chunk cross the link as they are (asynchronous copy from the
-        // caller's buffer), the rest is packed to 3 bits per base by the host cores WHILE that copy runs, then
-        // copied and expanded to text in HBM.  S balances the two resources (see pack_fraction()).
-        const uint64_t n = s.n_bytes;
-        const double x = pack_fraction(ctx, s.has_qual, n);
-        // multiple of 64: whole groups for the unpack kernel, and the packer's 64-byte loads never split a cache line
-        uint64_t S = (uint64_t)((1.0 - x) * (double)n) & ~63ull;
-        if (S > n) S = n & ~63ull;
-        const uint64_t groups = (n - S + 31) / 32;
-        const int mq = (int)(signed char)(unsigned char)((ctx->params.min_quality & 0xFF) + 33);
-        SHK_CUDA(ctx, cudaEventRecord(s.ev_start, s.stream));
-        SHK_CUDA(ctx, cudaMemcpyAsync(s.d_off, off, ((uint64_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s.stream));
-        if (S) {
-            SHK_CUDA(ctx, cudaMemcpyAsync(s.d_seq, seq, S, cudaMemcpyHostToDevice, s.stream));
-            if (s.has_qual) {
-                SHK_CUDA(ctx, cudaMemcpyAsync(s.d_qual, qual, S, cudaMemcpyHostToDevice, s.stream));
-                // the packed part carries its masking in the validity bits: qualities that mask nothing
-                if (n > S) SHK_CUDA(ctx, cudaMemsetAsync(s.d_qual + S, 0x7F, n - S, s.stream));
-            }
-        } else {
-            s.has_qual = false;
-        }
-        ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 4 + S * (s.has_qual ? 2 : 1) + groups * 12;
-        if (groups) {
-            uint32_t *h_valid = reinterpret_cast<uint32_t *>(s.h_pack + groups);
-            const double t0 = now_secs();
-            host_pack_parallel(seq + S, qual && (ctx->params.min_quality & 0xFF) ? qual + S : nullptr, mq, n - S, s.h_pack, h_valid);
-            const double secs = now_secs() - t0;
-            ctx->pack.last_pack_secs = secs;
-            if (secs > 0 && n - S >= (1u << 20))
-                ctx->pack.rate = ctx->pack.rate > 0 ? 0.7 * ctx->pack.rate + 0.3 * (double)(n - S) / secs : (double)(n - S) / secs;
-            SHK_CUDA(ctx, cudaMemcpyAsync(s.d_pack, s.h_pack, groups * 12, cudaMemcpyHostToDevice, s.stream));
-            s.launches += (uint32_t)launch_unpack(ctx, s.d_pack, reinterpret_cast<const uint32_t *>(s.d_pack + groups), n - S,
-                                                  s.d_seq + S, s.stream);
-            SHK_CUDA(ctx, cudaGetLastError());
-        }
-        return SHK_OK;
-    }
+    s.pack_first = 0xFFFFFFFFu;
+    s.pack_base = 0;
     SHK_CUDA(ctx, cudaEventRecord(s.ev_start, s.stream));
-    if (n_reads) {
-        ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 4 + s.n_bytes * (s.has_qual ? 2 : 1);
-        SHK_CUDA(ctx, cudaMemcpyAsync(s.d_off, off, ((uint64_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s.stream));
-        if (s.n_bytes) {
-            SHK_CUDA(ctx, cudaMemcpyAsync(s.d_seq, seq, s.n_bytes, cudaMemcpyHostToDevice, s.stream));
-            if (s.has_qual) SHK_CUDA(ctx, cudaMemcpyAsync(s.d_qual, qual, s.n_bytes, cudaMemcpyHostToDevice, s.stream));
-        }
+    if (!n_reads) return SHK_OK;
+    SHK_CUDA(ctx, cudaMemcpyAsync(s.d_off, off, ((uint64_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 4;
+    uint32_t r_split = n_reads;  // reads [0, r_split) cross the link as text, the rest packed by the host
+    if (allow_pack && ctx->host_pack && s.n_bytes) {
+        // Split upload: the first reads of the chunk cross the link as they are (asynchronous copy from the
+        // caller's buffer), the rest is packed to 3 bits per base by the host cores WHILE that copy runs and
+        // classified by the packed variant of the kernels.  The split point balances the two resources (see
+        // pack_fraction()) and sits at a read that starts a tile of kReadsPerTile reads.
+        const double x = pack_fraction(ctx, s.has_qual, s.n_bytes);
+        const uint64_t want = (uint64_t)((1.0 - x) * (double)s.n_bytes);
+        r_split = (uint32_t)(std::upper_bound(off, off + n_reads + 1, (uint32_t)std::min<uint64_t>(want, 0xFFFFFFFFull)) - off);
+        r_split = r_split ? r_split - 1 : 0;                 // last read starting at or before `want`
+        r_split = r_split / kReadsPerTile * kReadsPerTile;
+    }
+    const uint64_t S = off[r_split];  // text bytes
+    if (S) {
+        SHK_CUDA(ctx, cudaMemcpyAsync(s.d_seq, seq, S, cudaMemcpyHostToDevice, s.stream));
+        if (s.has_qual) SHK_CUDA(ctx, cudaMemcpyAsync(s.d_qual, qual, S, cudaMemcpyHostToDevice, s.stream));
+        ctx->h2d_bytes += S * (s.has_qual ? 2 : 1);
+    }
+    if (r_split == 0) s.has_qual = false;  // nothing is text: the packed part carries its masking
+    if (r_split < n_reads) {
+        const uint64_t n = s.n_bytes - S;
+        const uint64_t groups = (n + 31) / 32;
+        const int mq = (int)(signed char)(unsigned char)((ctx->params.min_quality & 0xFF) + 33);
+        uint32_t *h_valid = reinterpret_cast<uint32_t *>(s.h_pack + s.pack_groups_cap);
+        const double t0 = now_secs();
+        host_pack_parallel(seq + S, qual && (ctx->params.min_quality & 0xFF) ? qual + S : nullptr, mq, n, s.h_pack, h_valid);
+        const double secs = now_secs() - t0;
+        ctx->pack.last_pack_secs = secs;
+        if (secs > 0 && n >= (1u << 20))
+            ctx->pack.rate = ctx->pack.rate > 0 ? 0.7 * ctx->pack.rate + 0.3 * (double)n / secs : (double)n / secs;
+        s.pack_first = r_split;
+        s.pack_base = (uint32_t)S;
+        return enqueue_packed_copy(ctx, s, s.h_pack, h_valid, groups);
     }
     return SHK_OK;
+}
+
+// A chunk that arrives packed (shk_reads_submit_packed / shk_reads_upload_packed).
+static int enqueue_upload_packed(shk_ctx *ctx, Slot &s, const uint64_t *codes, const uint32_t *valid, const uint32_t *off,
+                                 uint32_t n_reads)
+{
+    s.n_reads = n_reads;
+    s.n_bytes = n_reads ? off[n_reads] : 0;
+    s.has_qual = false;
+    s.launches = 0;
+    s.pack_first = 0;
+    s.pack_base = 0;
+    SHK_CUDA(ctx, cudaEventRecord(s.ev_start, s.stream));
+    if (!n_reads) return SHK_OK;
+    SHK_CUDA(ctx, cudaMemcpyAsync(s.d_off, off, ((uint64_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 4;
+    return enqueue_packed_copy(ctx, s, codes, valid, (s.n_bytes + 31) / 32);
 }
 
 }  // namespace shk
 
 using namespace shk;
 
-static_assert(sizeof(shk_index_info) == 88 && sizeof(shk_shard_mem) == 240, "layouts mirrored in shark_b200/capi.py");
+static_assert(sizeof(shk_index_info) == 88 && sizeof(shk_shard_mem) == 240 && sizeof(shk_chunk_result) == 112, "layouts mirrored in shark_b200/capi.py");
 
 extern "C" {
 
@@ -427,7 +459,8 @@ int shk_create(const shk_params *p, shk_ctx **out)
     if (p->bf_bits < 64) return fail(nullptr, SHK_E_ARG, "bf_bits must be >= 64");
     if ((p->flags & SHK_F_EXTEND_ON) && (p->flags & SHK_F_EXTEND_OFF))
         return fail(nullptr, SHK_E_ARG, "SHK_F_EXTEND_ON and SHK_F_EXTEND_OFF are exclusive");
-    if (p->flags & ~(SHK_F_EXTEND_ON | SHK_F_EXTEND_OFF | SHK_F_HOST_PACK)) return fail(nullptr, SHK_E_ARG, "unknown flag bits");
+    if (p->flags & ~(SHK_F_EXTEND_ON | SHK_F_EXTEND_OFF | SHK_F_HOST_PACK | SHK_F_COMPACT_RESULTS))
+        return fail(nullptr, SHK_E_ARG, "unknown flag bits");
     const uint64_t n_words = (p->bf_bits + 31) / 32;
     const uint64_t n_sectors = (n_words + kWordsPerSector - 1) / kWordsPerSector;
     if (n_sectors * 8 > 0xFFFFFFFFull)
@@ -446,6 +479,7 @@ int shk_create(const shk_params *p, shk_ctx **out)
     ctx->params = *p;
     ctx->device = p->device;
     ctx->host_pack = (p->flags & SHK_F_HOST_PACK) != 0;
+    ctx->compact_results = (p->flags & SHK_F_COMPACT_RESULTS) != 0;
     if (const char *ev = getenv("SHK_HOST_PACK")) ctx->host_pack = atoi(ev) != 0;  // tuning override
     int rc = SHK_OK;
     auto bail = [&](int code) {
@@ -997,6 +1031,22 @@ int shk_reads_submit(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint
     return SHK_OK;
 }
 
+int shk_reads_submit_packed(shk_ctx *ctx, uint32_t slot, const uint64_t *codes, const uint32_t *valid, const uint32_t *off,
+                            uint32_t n_reads)
+{
+    int rc = check_chunk(ctx, slot, off, n_reads, nullptr, true);
+    if (rc) return rc;
+    if (n_reads && off[n_reads] && (!codes || !valid)) return fail(ctx, SHK_E_ARG, "codes / valid is NULL");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    rc = enqueue_upload_packed(ctx, s, codes, valid, off, n_reads);
+    if (rc) return rc;
+    rc = enqueue_chunk_kernels(ctx, s);
+    if (rc) return rc;
+    s.pending = true;
+    return SHK_OK;
+}
+
 int shk_reads_upload(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint8_t *qual, const uint32_t *off,
                      uint32_t n_reads)
 {
@@ -1004,7 +1054,22 @@ int shk_reads_upload(shk_ctx *ctx, uint32_t slot, const uint8_t *seq, const uint
     if (rc) return rc;
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[slot];
-    rc = enqueue_upload(ctx, s, seq, qual, off, n_reads, false);  // kernel-only timing: always the plain text
+    rc = enqueue_upload(ctx, s, seq, qual, off, n_reads, false);  // kernel-only timing of the text form
+    if (rc) return rc;
+    SHK_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    s.pending = false;
+    return SHK_OK;
+}
+
+int shk_reads_upload_packed(shk_ctx *ctx, uint32_t slot, const uint64_t *codes, const uint32_t *valid, const uint32_t *off,
+                            uint32_t n_reads)
+{
+    int rc = check_chunk(ctx, slot, off, n_reads, nullptr, true);
+    if (rc) return rc;
+    if (n_reads && off[n_reads] && (!codes || !valid)) return fail(ctx, SHK_E_ARG, "codes / valid is NULL");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    rc = enqueue_upload_packed(ctx, s, codes, valid, off, n_reads);
     if (rc) return rc;
     SHK_CUDA(ctx, cudaStreamSynchronize(s.stream));
     s.pending = false;
@@ -1017,11 +1082,32 @@ int shk_reads_analyze_resident(shk_ctx *ctx, uint32_t slot)
     if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index");
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[slot];
+    if (s.pending) return fail(ctx, SHK_E_STATE, "slot %u has an uncollected chunk: call shk_reads_collect first", slot);
     s.launches = 0;
     SHK_CUDA(ctx, cudaEventRecord(s.ev_start, s.stream));
     int rc = enqueue_chunk_kernels(ctx, s);
     if (rc) return rc;
     s.pending = true;
+    return SHK_OK;
+}
+
+int shk_result_expand(const shk_chunk_result *res, shk_assoc *assoc, uint8_t *keep)
+{
+    if (!res || (res->n_reads && !res->gene16) || (res->n_multi && !res->multi)) return fail(nullptr, SHK_E_ARG, "bad result");
+    uint64_t o = 0, m = 0;
+    for (uint32_t r = 0; r < res->n_reads; ++r) {
+        const uint32_t g = res->gene16[r];
+        if (keep) keep[r] = g != SHK_GENE_NONE;
+        if (g == SHK_GENE_NONE) continue;
+        if (g != SHK_GENE_MULTI) {
+            if (assoc) assoc[o] = shk_assoc{r, g};
+            ++o;
+        } else {
+            for (; m < res->n_multi && res->multi[m].read_idx == r; ++m, ++o)
+                if (assoc) assoc[o] = res->multi[m];
+        }
+    }
+    if (o != res->n_assoc || m != res->n_multi) return fail(nullptr, SHK_E_STATE, "inconsistent compact result");
     return SHK_OK;
 }
 
@@ -1049,44 +1135,46 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
             if (rc) return rc;
             continue;
         }
-        if (c.n_assoc > s.assoc_cap) {
-            uint64_t want = c.n_assoc + c.n_assoc / 8 + 1024;
-            cudaFree(s.d_assoc);
-            s.d_assoc = nullptr;
-            SHK_CUDA(ctx, cudaMalloc((void **)&s.d_assoc, want * sizeof(shk_assoc)));
-            s.assoc_cap = want;
+        if (c.n_multi > s.multi_cap) {
+            uint64_t want = c.n_multi + c.n_multi / 8 + 1024;
+            cudaFree(s.d_multi);
+            s.d_multi = nullptr;
+            SHK_CUDA(ctx, cudaMalloc((void **)&s.d_multi, want * sizeof(shk_assoc)));
+            s.multi_cap = want;
             ReadKernelArgs a = make_args(ctx, s);
-            s.launches += (uint32_t)launch_scatter(ctx, a, s.assoc_cap, s.stream);
+            s.launches += (uint32_t)launch_scatter(ctx, a, s.multi_cap, s.stream);
             SHK_CUDA(ctx, cudaGetLastError());
             SHK_CUDA(ctx, cudaEventRecord(s.ev_done, s.stream));
-            s.pre_assoc = 0;  // the list was rebuilt in a new buffer: fetch all of it below
+            s.pre_multi = 0;  // the list was rebuilt in a new buffer: fetch all of it below
             continue;
         }
         break;
     }
     const ChunkCounters c = *s.h_counters;
-    if (c.n_assoc > s.h_assoc_cap) {
-        cudaFreeHost(s.h_assoc);
-        s.h_assoc = nullptr;
-        s.h_assoc_cap = c.n_assoc + c.n_assoc / 8 + 1024;
-        SHK_CUDA(ctx, pinned_alloc((void **)&s.h_assoc, s.h_assoc_cap * sizeof(shk_assoc)));
-        s.pre_assoc = 0;
+    if (c.n_multi > s.h_multi_cap) {
+        cudaFreeHost(s.h_multi);
+        s.h_multi = nullptr;
+        s.h_multi_cap = c.n_multi + c.n_multi / 8 + 1024;
+        SHK_CUDA(ctx, pinned_alloc((void **)&s.h_multi, s.h_multi_cap * sizeof(shk_assoc)));
+        s.pre_multi = 0;
     }
-    if (c.n_assoc > s.pre_assoc) {  // what the read-back enqueued with the kernels did not cover
-        SHK_CUDA(ctx, cudaMemcpyAsync(s.h_assoc + s.pre_assoc, s.d_assoc + s.pre_assoc,
-                                      (c.n_assoc - s.pre_assoc) * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
-        ctx->d2h_bytes += (c.n_assoc - s.pre_assoc) * sizeof(shk_assoc);
+    if (c.n_multi > s.pre_multi) {  // what the read-back enqueued with the kernels did not cover
+        SHK_CUDA(ctx, cudaMemcpyAsync(s.h_multi + s.pre_multi, s.d_multi + s.pre_multi,
+                                      (c.n_multi - s.pre_multi) * sizeof(shk_assoc), cudaMemcpyDeviceToHost, s.stream));
+        ctx->d2h_bytes += (c.n_multi - s.pre_multi) * sizeof(shk_assoc);
         SHK_CUDA(ctx, cudaStreamSynchronize(s.stream));
     }
-    if (s.n_reads) ctx->assoc_per_read.store((double)c.n_assoc / (double)s.n_reads);
+    if (s.n_reads) ctx->multi_per_read.store((double)c.n_multi / (double)s.n_reads);
     float k_ms = 0, t_ms = 0, p_ms = 0;
     cudaEventElapsedTime(&k_ms, s.ev_k0, s.ev_k1);
     cudaEventElapsedTime(&p_ms, s.ev_k0, s.ev_ka);
     cudaEventElapsedTime(&t_ms, s.ev_start, s.ev_done);
     memset(out, 0, sizeof *out);
     out->n_assoc = c.n_assoc;
-    out->assoc = s.h_assoc;
-    out->keep = s.h_keep;
+    out->gene16 = s.h_gene16;
+    out->multi = s.h_multi;
+    out->n_multi = c.n_multi;
+    out->n_kept = c.n_kept;
     out->n_reads = s.n_reads;
     out->n_slow_reads = c.n_slow;
     out->n_probes = c.n_probes;
@@ -1098,6 +1186,23 @@ int shk_reads_collect(shk_ctx *ctx, uint32_t slot, shk_chunk_result *out)
     out->n_extended = c.n_extended;
     out->n_table_loads = c.n_table_loads;
     s.pending = false;
+    if (!ctx->compact_results) {
+        // the classic form of the ABI: association list + keep flags, expanded here on the calling thread
+        if (c.n_assoc > s.h_assoc_cap || !s.h_assoc) {
+            free(s.h_assoc);
+            s.h_assoc_cap = c.n_assoc + c.n_assoc / 8 + 1024;
+            s.h_assoc = (shk_assoc *)malloc(s.h_assoc_cap * sizeof(shk_assoc));
+            if (!s.h_assoc) return fail(ctx, SHK_E_NOMEM, "out of host memory");
+        }
+        if (!s.h_keep) {
+            s.h_keep = (uint8_t *)malloc((size_t)ctx->max_reads + 64);
+            if (!s.h_keep) return fail(ctx, SHK_E_NOMEM, "out of host memory");
+        }
+        if (shk_result_expand(out, s.h_assoc, s.h_keep) != SHK_OK)
+            return fail(ctx, SHK_E_STATE, "inconsistent compact result on slot %u", slot);
+        out->assoc = s.h_assoc;
+        out->keep = s.h_keep;
+    }
     return SHK_OK;
 }
 
@@ -1166,10 +1271,7 @@ int shk_set_upload_mode(shk_ctx *ctx, uint32_t host_pack, uint32_t permille)
     if (host_pack)
         for (uint32_t i = 0; i < ctx->n_slots; ++i) {
             Slot &s = ctx->slots[i];
-            if (s.d_pack) continue;
-            s.pack_groups_cap = (ctx->max_bytes + 63) / 32;
-            SHK_CUDA(ctx, cudaMalloc((void **)&s.d_pack, s.pack_groups_cap * 12));
-            SHK_CUDA(ctx, pinned_alloc((void **)&s.h_pack, s.pack_groups_cap * 12));
+            if (!s.h_pack) SHK_CUDA(ctx, pinned_alloc((void **)&s.h_pack, s.pack_groups_cap * 12));
         }
     ctx->host_pack = host_pack != 0;
     ctx->params.host_pack_permille = permille;

@@ -42,6 +42,8 @@ struct ChunkCounters {
     unsigned int n_slow2;     // reads the middle path handed on to the exact path
     unsigned long long n_extended;    // windows resolved by extension (no table access)
     unsigned long long n_table_loads; // front-table entries loaded by the fast kernel (extension mode)
+    unsigned long long n_multi;       // entries of the `multi` list (associations of reads marked kGeneMulti)
+    unsigned long long n_kept;        // reads with at least one association
 };
 
 struct ReadKernelArgs {
@@ -50,6 +52,13 @@ struct ReadKernelArgs {
     const uint8_t *qual;  // nullptr when min_quality == 0
     const uint32_t *off;
     uint32_t n_reads;
+    // packed part of the chunk: reads [pack_first, n_reads) live in the packed stream (2-bit code + validity bit
+    // per base, shk_hostpack.h), whose position 0 is text offset pack_base = off[pack_first]; reads before
+    // pack_first are text.  pack_first is a multiple of kReadsPerTile (or >= n_reads: no packed part).
+    const uint64_t *pcodes;
+    const uint32_t *pvalid;
+    uint32_t pack_first, pack_base;
+    uint32_t r0, r1;  // reads [r0, r1) of one launch of the fast kernel (r0 a multiple of kReadsPerTile)
     // index
     const uint32_t *sectors;
     const uint64_t *entries;
@@ -78,16 +87,16 @@ struct ReadKernelArgs {
     uint32_t pool_cap;
     uint32_t *slow_list;     // read indices the fast path gave up on (middle path input)
     uint32_t *slow2_list;    // read indices the middle path gave up on (exact path input)
-    uint32_t *tile_sums;     // associations per tile of kReadsPerTile reads
+    uint32_t *tile_sums;     // `multi` entries per tile of kReadsPerTile reads
     ChunkCounters *counters;
     // exact-path scratch
     uint4 *slow_table;       // n_slow_slabs * n_genes entries {stamp, cov, hits, last}
     uint32_t *slow_stamp;    // per slab
     uint32_t n_slow_slabs;
-    // compaction outputs
+    // compaction outputs (compact result form, include/shark_b200.h)
     uint32_t *tile_base;
-    shk_assoc *assoc;
-    uint8_t *keep;
+    uint16_t *gene16;        // per read: gene index, SHK_GENE_NONE or SHK_GENE_MULTI
+    shk_assoc *multi;        // associations of the SHK_GENE_MULTI reads, ordered by read then gene
 };
 
 constexpr uint32_t kReadsPerTile = 128;  // one CTA of the fast kernel: 128 threads = 128 reads
@@ -105,20 +114,26 @@ struct Slot {
     uint32_t *d_slow_list = nullptr, *d_slow2_list = nullptr;
     uint32_t *d_tile_sums = nullptr, *d_tile_base = nullptr;
     ChunkCounters *d_counters = nullptr;
-    shk_assoc *d_assoc = nullptr;
-    uint64_t assoc_cap = 0;
-    uint8_t *d_keep = nullptr;
+    uint16_t *d_gene16 = nullptr;    // compact per-read results
+    shk_assoc *d_multi = nullptr;    // associations of the SHK_GENE_MULTI reads
+    uint64_t multi_cap = 0;
     uint4 *d_slow_table = nullptr;   // exact-path tables: private to the slot (slots run concurrently)
     uint32_t *d_slow_stamp = nullptr;
     // pinned host
     ChunkCounters *h_counters = nullptr;
+    uint16_t *h_gene16 = nullptr;
+    shk_assoc *h_multi = nullptr;
+    uint64_t h_multi_cap = 0;
+    uint64_t pre_multi = 0;  // multi entries whose read-back was enqueued with the kernels
+    // ordinary host memory: the expanded form (without SHK_F_COMPACT_RESULTS), filled by shk_reads_collect
     shk_assoc *h_assoc = nullptr;
     uint64_t h_assoc_cap = 0;
-    uint64_t pre_assoc = 0;  // associations whose read-back was enqueued with the kernels
     uint8_t *h_keep = nullptr;
-    // host-packed upload (SHK_F_HOST_PACK): codes (8 bytes per 32 bases) then validity words (4 bytes)
+    // packed reads: codes (8 bytes per 32 bases) then validity words (4 bytes); d_pack always exists,
+    // h_pack is the pinned staging of the split upload (SHK_F_HOST_PACK)
     uint64_t *h_pack = nullptr, *d_pack = nullptr;
     uint64_t pack_groups_cap = 0;
+    uint32_t pack_first = 0xFFFFFFFFu, pack_base = 0;  // this chunk: reads >= pack_first are packed
     // state
     uint32_t n_reads = 0;
     uint64_t n_bytes = 0;
@@ -178,7 +193,8 @@ struct shk_ctx {
     bool host_pack = false;                // shk_reads_submit packs the text on the host cores first
     std::atomic<uint64_t> h2d_bytes{0};    // bytes shk_reads_submit / upload copied to the device
     std::atomic<uint64_t> d2h_bytes{0};    // result bytes copied back
-    std::atomic<double> assoc_per_read{-1.0};  // last chunk's associations per read: sizes the early read-back
+    std::atomic<double> multi_per_read{-1.0};  // last chunk's multi entries per read: sizes the early read-back
+    bool compact_results = false;          // SHK_F_COMPACT_RESULTS
     shk::PackControl pack;                 // split upload: feedback state of the packed share
     char err[512] = {0};
 };
@@ -227,8 +243,5 @@ int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_ca
                         cudaEvent_t ev_ka, cudaEvent_t ev_k1);
 int launch_scatter(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st);
 int fetch_cache_policies(shk_ctx *ctx);
-// host-packed reads (shk_hostpack.h) -> text in d_seq; returns the number of launches
-int launch_unpack(shk_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_bytes, uint8_t *d_seq,
-                  cudaStream_t st);
 
 }  // namespace shk

@@ -19,6 +19,12 @@ namespace shk {
 
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
+// Does a read's result fit the compact per-read form (one 16-bit word), or does it go to the `multi` list?
+__device__ __forceinline__ uint32_t multi_entries(uint32_t count, uint32_t payload)
+{
+    return (count >= 2u || (count == 1u && payload >= SHK_GENE_MULTI)) ? count : 0u;
+}
+
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
 {
     uint32_t lo = __shfl_sync(kFull, (uint32_t)v, src);
@@ -36,21 +42,33 @@ struct ChunkState {
 
 template <bool HAS_QUAL, int MOD>
 __device__ __forceinline__ bool chunk_window(const ReadKernelArgs &a, uint32_t off0, uint32_t n, int chunk, int lane,
-                                             ChunkState &cs, uint32_t &len, uint32_t &pw, uint32_t &bit)
+                                             ChunkState &cs, uint32_t &len, uint32_t &pw, uint32_t &bit, bool packed)
 {
     const uint32_t pos = (uint32_t)chunk * 32u + (uint32_t)lane;
-    uint32_t ch = 0;
-    if (pos < n) {
-        ch = a.seq[off0 + pos];
-        if (HAS_QUAL) {
-            int q = (int)(signed char)a.qual[off0 + pos];
-            if (q < a.mq) ch = (ch - 64u) & 0xFFu;  // seq[i] = seq[i] - 64
+    bool valid = false;
+    uint32_t code = 0;
+    if (packed) {  // warp-uniform: the read lives in the packed stream (masking already folded into the validity bits)
+        if (pos < n) {
+            const uint32_t ap = off0 - a.pack_base + pos;
+            const uint32_t raw = (uint32_t)(a.pcodes[ap >> 5] >> (2u * (ap & 31u))) & 3u;  // A0 C1 T2 G3
+            valid = (a.pvalid[ap >> 5] >> (ap & 31u)) & 1u;
+            code = raw ^ (raw >> 1);
         }
+    } else {
+        uint32_t ch = 0;
+        if (pos < n) {
+            ch = a.seq[off0 + pos];
+            if (HAS_QUAL) {
+                int q = (int)(signed char)a.qual[off0 + pos];
+                if (q < a.mq) ch = (ch - 64u) & 0xFFu;  // seq[i] = seq[i] - 64
+            }
+        }
+        valid = base_valid(ch);
+        code = base_code(ch);
     }
-    const bool valid = base_valid(ch);
     const uint32_t V = __ballot_sync(kFull, valid);
     len += __popc(V);  // ReadAnalyzer.hpp:46-49
-    const uint32_t val = valid ? base_code(ch) << (30 - 2 * (lane & 15)) : 0u;
+    const uint32_t val = valid ? code << (30 - 2 * (lane & 15)) : 0u;
     const uint32_t hiw = __reduce_or_sync(kFull, lane < 16 ? val : 0u);
     const uint32_t low = __reduce_or_sync(kFull, lane >= 16 ? val : 0u);
     const uint64_t P = ((uint64_t)hiw << 32) | low;
@@ -245,13 +263,19 @@ struct Mru4 {
 #ifndef SHK_EXT_MIN_BLOCKS
 #define SHK_EXT_MIN_BLOCKS 6
 #endif
-template <bool HAS_QUAL, int MOD, bool EXT>
+//
+// PACKED: the read comes from the packed stream (64-bit code words + 32-bit validity words per 32 bases,
+// shk_hostpack.h) instead of text: no text or quality loads, no byte-parallel decode; the -q masking rule is
+// already in the validity bits.  Everything from the rolling k-mers on is the same code.
+template <bool HAS_QUAL, int MOD, bool EXT, bool PACKED>
 __global__ void __launch_bounds__(kFastThreads, EXT ? SHK_EXT_MIN_BLOCKS : SHK_FAST_MIN_BLOCKS)
 analyze_reads_kernel(const ReadKernelArgs a)
 {
+    static_assert(!(PACKED && HAS_QUAL), "packed reads carry their masking in the validity bits");
     constexpr uint32_t S = EXT ? 2u : 1u;  // uint4s per front-table entry
     const int lane = threadIdx.x & 31;
-    const uint32_t r = blockIdx.x * kFastThreads + threadIdx.x;
+    const uint32_t r = a.r0 + blockIdx.x * kFastThreads + threadIdx.x;
+    const uint32_t tile = a.r0 / kReadsPerTile + blockIdx.x;
 #if SHK_POLICY_ARGS
     const uint64_t pol_first = a.pol_first, pol_last = a.pol_last;
 #else
@@ -267,7 +291,7 @@ analyze_reads_kernel(const ReadKernelArgs a)
     uint32_t count = 0, payload = 0, my_probes = 0, my_hits = 0, my_ext = 0, my_loads = 0;
     bool slow = false;
 
-    if (r < a.n_reads) {
+    if (r < a.r1) {
         const uint32_t off0 = a.off[r];
         const uint32_t n = a.off[r + 1] - off0;
         if (n > kMaxFastLen) {
@@ -282,37 +306,67 @@ analyze_reads_kernel(const ReadKernelArgs a)
             uint32_t anc_t = 0, anc_dir = 0, prevA = kFrontEmpty, prevB = kFrontEmpty;
             bool anc_on = false;
             uint64_t ew = 0;
-            const uint32_t head = off0 & 3u;
-            const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.seq) + (off0 >> 2);
-            const uint32_t *qualw = HAS_QUAL ? reinterpret_cast<const uint32_t *>(a.qual) + (off0 >> 2) : nullptr;
+            // text: 4 bases = one 32-bit word of the chunk's text; packed: 4 bases = one byte of a code word and
+            // one nibble of a validity word.  Either way the walk is over ALIGNED 4-base words; positions of the
+            // first and last word that lie outside the read are made invalid.
+            const uint32_t src0 = PACKED ? off0 - a.pack_base : off0;
+            const uint32_t head = src0 & 3u;
+            const uint32_t *seqw = reinterpret_cast<const uint32_t *>(a.seq) + (src0 >> 2);
+            const uint32_t *qualw = HAS_QUAL ? reinterpret_cast<const uint32_t *>(a.qual) + (src0 >> 2) : nullptr;
             const uint32_t n_words = (head + n + 3u) >> 2;
             uint32_t w_next = 0, q_next = 0;
+            // packed: current and prefetched (code word, validity word) of the 32-base group
+            uint32_t pg = (src0 >> 2) >> 3;
+            uint64_t cw = 0, cw_next = 0;
+            uint32_t vw = 0, vw_next = 0;
             if (n_words) {
-                w_next = ld_text_word(seqw, pol_first);
-                if (HAS_QUAL) q_next = ld_text_word(qualw, pol_first);
+                if (PACKED) {
+                    cw_next = ld_u64_hint(a.pcodes + pg, pol_first);
+                    vw_next = ld_text_word(a.pvalid + pg, pol_first);
+                } else {
+                    w_next = ld_text_word(seqw, pol_first);
+                    if (HAS_QUAL) q_next = ld_text_word(qualw, pol_first);
+                }
             }
             for (uint32_t j = 0; j < n_words && !tab.overflow; ++j) {
-                uint32_t w = w_next;
-                const uint32_t qw = q_next;
-                if (j + 1 < n_words) {
-                    w_next = ld_text_word(seqw + j + 1, pol_first);
-                    if (HAS_QUAL) q_next = ld_text_word(qualw + j + 1, pol_first);
-                }
-                if (HAS_QUAL) w = sub_bytes4(w, qual_mask4(qw, mq4b));
+                // per base b of the word: validity and 2-bit code (A0 C1 G2 T3)
                 uint32_t code4, x;
-                codes4(w, code4, x);
+                if (PACKED) {
+                    const uint32_t nib = ((src0 >> 2) + j) & 7u;
+                    if (j == 0 || nib == 0) {
+                        cw = cw_next;
+                        vw = vw_next;
+                        if (j + (8u - nib) < n_words) {  // the read goes on into the next group
+                            ++pg;
+                            cw_next = ld_u64_hint(a.pcodes + pg, pol_first);
+                            vw_next = ld_text_word(a.pvalid + pg, pol_first);
+                        }
+                    }
+                    const uint32_t c8 = (uint32_t)(cw >> (8u * nib)) & 0xFFu;
+                    code4 = c8 ^ ((c8 >> 1) & 0x55u);       // A0 C1 T2 G3 -> A0 C1 G2 T3, base b at bits 2b
+                    x = (vw >> (4u * nib)) & 0xFu;          // bit b = base b is valid
+                } else {
+                    uint32_t w = w_next;
+                    const uint32_t qw = q_next;
+                    if (j + 1 < n_words) {
+                        w_next = ld_text_word(seqw + j + 1, pol_first);
+                        if (HAS_QUAL) q_next = ld_text_word(qualw + j + 1, pol_first);
+                    }
+                    if (HAS_QUAL) w = sub_bytes4(w, qual_mask4(qw, mq4b));
+                    codes4(w, code4, x);                    // byte b of x == 0 iff base b is valid
+                }
                 const uint32_t pos0 = 4u * j - head;  // position of byte 0 (wraps before the read)
                 if (j == 0 || j + 1 == n_words) {     // bytes outside the read are not bases
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
-                        if (pos0 + (uint32_t)b >= n) x |= 0xFFu << (8 * b);
+                        if (pos0 + (uint32_t)b >= n) x = PACKED ? (x & ~(1u << b)) : (x | (0xFFu << (8 * b)));
                 }
 #if SHK_SKIP_WORDS
                 if (run + 4u < k) {  // no window can complete in this word (start of a mate): roll only
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const bool valid = ((x >> (8 * b)) & 0xFFu) == 0u;
-                        const uint64_t code = (code4 >> (8 * b)) & 3u;
+                        const bool valid = PACKED ? ((x >> b) & 1u) != 0u : ((x >> (8 * b)) & 0xFFu) == 0u;
+                        const uint64_t code = PACKED ? (code4 >> (2 * b)) & 3u : (code4 >> (8 * b)) & 3u;
                         fwd = ((fwd << 2) | code) & kmask2;
                         rc = (rc >> 2) | ((3ULL ^ code) << rc_shift);
                         run = valid ? run + 1u : 0u;
@@ -325,8 +379,8 @@ analyze_reads_kernel(const ReadKernelArgs a)
                 bool wv[4], ex[4];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const bool valid = ((x >> (8 * b)) & 0xFFu) == 0u;
-                    const uint64_t code = (code4 >> (8 * b)) & 3u;
+                    const bool valid = PACKED ? ((x >> b) & 1u) != 0u : ((x >> (8 * b)) & 0xFFu) == 0u;
+                    const uint64_t code = PACKED ? (code4 >> (2 * b)) & 3u : (code4 >> (8 * b)) & 3u;
                     fwd = ((fwd << 2) | code) & kmask2;            // lsappend, kmer_utils.hpp:73-75
                     rc = (rc >> 2) | ((3ULL ^ code) << rc_shift);  // rsprepend(reverse_char), 77-79
                     run = valid ? run + 1u : 0u;                   // build_kmer restart, 57-71
@@ -510,9 +564,12 @@ analyze_reads_kernel(const ReadKernelArgs a)
     // every warp retires on its own (tile_sums is zeroed before the launch): no warp of a CTA
     // waits at a barrier for its slowest sibling
     const uint32_t wa = __reduce_add_sync(kFull, count), wp = __reduce_add_sync(kFull, my_probes),
-                   wh = __reduce_add_sync(kFull, my_hits);
+                   wh = __reduce_add_sync(kFull, my_hits), wm = __reduce_add_sync(kFull, multi_entries(count, payload)),
+                   wk = __popc(__ballot_sync(kFull, count != 0u));
     if (lane == 0) {
-        if (wa) atomicAdd(&a.tile_sums[blockIdx.x], wa);
+        if (wm) atomicAdd(&a.tile_sums[tile], wm);
+        if (wa) atomicAdd(&a.counters->n_assoc, (unsigned long long)wa);
+        if (wk) atomicAdd(&a.counters->n_kept, (unsigned long long)wk);
         if (wp) atomicAdd(&a.counters->n_probes, (unsigned long long)wp);
         if (wh) atomicAdd(&a.counters->n_hits, (unsigned long long)wh);
     }
@@ -549,12 +606,13 @@ __global__ void __launch_bounds__(kMidWarps * 32) analyze_mid_kernel(const ReadK
     uint4 *tab = tables[warp];
     uint32_t *keys = reinterpret_cast<uint32_t *>(tab);  // key of slot s = keys[4 * s]
     const uint32_t k = (uint32_t)a.k;
-    unsigned long long probes = 0, hits_total = 0;
+    unsigned long long probes = 0, hits_total = 0, assoc_total = 0, kept_total = 0;
 
     for (uint32_t i = blockIdx.x * kMidWarps + warp; i < n_slow; i += total_warps) {
         const uint32_t r = a.slow_list[i];
         const uint32_t off0 = a.off[r];
         const uint32_t n = a.off[r + 1] - off0;
+        const bool packed = r >= a.pack_first;
         for (uint32_t s = lane; s < kMidSlots; s += 32) tab[s] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
         __syncwarp();
         uint32_t n_used = 0;
@@ -565,7 +623,7 @@ __global__ void __launch_bounds__(kMidWarps * 32) analyze_mid_kernel(const ReadK
         unsigned long long my_probes = 0, my_hits = 0;
         for (int c = 0; c < nch && !overflow; ++c) {
             uint32_t pw, bit;
-            const bool wv = chunk_window<HAS_QUAL, MOD>(a, off0, n, c, lane, cs, len, pw, bit);
+            const bool wv = chunk_window<HAS_QUAL, MOD>(a, off0, n, c, lane, cs, len, pw, bit, packed);
             const uint32_t w = wv ? ld_filter_word(a.sectors + pw, pol_first) : 0u;
             const bool hit = wv && ((w >> bit) & 1u);
             my_probes += __popc(__ballot_sync(kFull, wv));
@@ -673,13 +731,17 @@ __global__ void __launch_bounds__(kMidWarps * 32) analyze_mid_kernel(const ReadK
         }
         if (lane == 0) {
             a.rec[r] = make_uint2(count, payload);
-            if (count) atomicAdd(&a.tile_sums[r / kReadsPerTile], count);
+            if (multi_entries(count, payload)) atomicAdd(&a.tile_sums[r / kReadsPerTile], count);
+            assoc_total += count;
+            kept_total += count ? 1u : 0u;
         }
         __syncwarp();
     }
     if (lane == 0) {
         if (probes) atomicAdd(&a.counters->n_probes, probes);
         if (hits_total) atomicAdd(&a.counters->n_hits, hits_total);
+        if (assoc_total) atomicAdd(&a.counters->n_assoc, assoc_total);
+        if (kept_total) atomicAdd(&a.counters->n_kept, kept_total);
     }
 }
 
@@ -702,12 +764,13 @@ __global__ void __launch_bounds__(128) analyze_slow_kernel(const ReadKernelArgs 
     uint4 *table = a.slow_table + (uint64_t)slab * a.n_genes;
     uint32_t stamp = a.slow_stamp[slab];
     const uint32_t k = (uint32_t)a.k;
-    unsigned long long probes = 0, hits_total = 0;
+    unsigned long long probes = 0, hits_total = 0, assoc_total = 0, kept_total = 0;
 
     for (uint32_t i = slab; i < n_slow; i += a.n_slow_slabs) {
         const uint32_t r = a.slow2_list[i];
         const uint32_t off0 = a.off[r];
         const uint32_t n = a.off[r + 1] - off0;
+        const bool packed = r >= a.pack_first;
         if (++stamp == 0) {  // stamp wrapped: clear the slab once
             for (uint32_t g = lane; g < a.n_genes; g += 32) table[g] = make_uint4(0, 0, 0, 0);
             stamp = 1;
@@ -718,7 +781,7 @@ __global__ void __launch_bounds__(128) analyze_slow_kernel(const ReadKernelArgs 
         uint32_t len = 0;
         for (int c = 0; c < nch; ++c) {
             uint32_t pw, bit;
-            const bool wv = chunk_window<HAS_QUAL, MOD>(a, off0, n, c, lane, cs, len, pw, bit);
+            const bool wv = chunk_window<HAS_QUAL, MOD>(a, off0, n, c, lane, cs, len, pw, bit, packed);
             const uint32_t w = wv ? ld_filter_word(a.sectors + pw, pol_first) : 0u;
             const bool hit = wv && ((w >> bit) & 1u);
             probes += __popc(__ballot_sync(kFull, wv));
@@ -801,7 +864,9 @@ __global__ void __launch_bounds__(128) analyze_slow_kernel(const ReadKernelArgs 
         }
         if (lane == 0) {
             a.rec[r] = make_uint2(count, payload);
-            if (count) atomicAdd(&a.tile_sums[r / kReadsPerTile], count);
+            if (multi_entries(count, payload)) atomicAdd(&a.tile_sums[r / kReadsPerTile], count);
+            assoc_total += count;
+            kept_total += count ? 1u : 0u;
         }
         __syncwarp();
     }
@@ -809,53 +874,72 @@ __global__ void __launch_bounds__(128) analyze_slow_kernel(const ReadKernelArgs 
         a.slow_stamp[slab] = stamp;
         if (probes) atomicAdd(&a.counters->n_probes, probes);
         if (hits_total) atomicAdd(&a.counters->n_hits, hits_total);
+        if (assoc_total) atomicAdd(&a.counters->n_assoc, assoc_total);
+        if (kept_total) atomicAdd(&a.counters->n_kept, kept_total);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K7: ordered output.  tile_base = exclusive scan of the per-tile counts (scan_tile_sums_kernel);
-// every tile then scans its 64 reads and writes its associations in read order, genes ascending
-// (the order ReadOutput prints them, ReadOutput.hpp:40-49), plus the per-read keep flag.
+// K7: ordered output in the compact result form.  Per read one 16-bit word: the gene index of its single
+// association, SHK_GENE_NONE, or SHK_GENE_MULTI = "see the multi list" (two or more winners - ties - or a
+// single gene index that collides with the two marker values).  tile_base = exclusive scan of the per-tile
+// multi counts (scan_tile_sums_kernel); every tile then scans its reads and writes the multi entries in read
+// order, genes ascending (the order ReadOutput prints them, ReadOutput.hpp:40-49).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kReadsPerTile)
-scatter_assoc_kernel(const ReadKernelArgs a, uint64_t assoc_cap, const uint32_t *total)
+scatter_assoc_kernel(const ReadKernelArgs a, uint64_t multi_cap, const uint32_t *total)
 {
     __shared__ uint32_t warp_tot[kReadsPerTile / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kReadsPerTile + threadIdx.x;
     uint2 rc = make_uint2(0u, 0u);
     if (r < a.n_reads) rc = a.rec[r];
-    const uint32_t incl = warp_incl_scan(rc.x, lane);
+    const uint32_t m = multi_entries(rc.x, rc.y);
+    const uint32_t incl = warp_incl_scan(m, lane);
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    uint32_t o = a.tile_base[blockIdx.x] + incl - rc.x;
+    uint32_t o = a.tile_base[blockIdx.x] + incl - m;
     for (int w = 0; w < warp; ++w) o += warp_tot[w];
     if (r < a.n_reads) {
-        a.keep[r] = rc.x ? 1 : 0;
-        if ((uint64_t)o + rc.x <= assoc_cap) {
+        a.gene16[r] = (uint16_t)(rc.x == 0u ? SHK_GENE_NONE : (m ? SHK_GENE_MULTI : rc.y));
+        if (m && (uint64_t)o + m <= multi_cap) {
             if (rc.x == 1) {
-                a.assoc[o] = shk_assoc{r, rc.y};
+                a.multi[o] = shk_assoc{r, rc.y};
             } else if ((uint64_t)rc.y + rc.x <= a.pool_cap) {  // pool overflow: the host re-runs the chunk
-                for (uint32_t t = 0; t < rc.x; ++t) a.assoc[o + t] = shk_assoc{r, a.pool[rc.y + t]};
+                for (uint32_t t = 0; t < rc.x; ++t) a.multi[o + t] = shk_assoc{r, a.pool[rc.y + t]};
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.counters->n_assoc = *total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.counters->n_multi = *total;
 }
 
 template <bool HAS_QUAL, int MOD>
-static void launch_typed(const ReadKernelArgs &a, cudaStream_t st, unsigned tiles, unsigned slow_blocks, cudaEvent_t ev_ka)
+static void launch_typed(const ReadKernelArgs &a0, cudaStream_t st, unsigned tiles, unsigned slow_blocks, cudaEvent_t ev_ka)
 {
     // middle path: a grid-stride loop over the slow list (its length is only known on the device)
     const unsigned mid_blocks = std::min<unsigned>((tiles * kReadsPerTile + kMidWarps - 1) / kMidWarps, 148u * 8u);
-    if (a.estream) analyze_reads_kernel<HAS_QUAL, MOD, true><<<tiles, kFastThreads, 0, st>>>(a);
-    else analyze_reads_kernel<HAS_QUAL, MOD, false><<<tiles, kFastThreads, 0, st>>>(a);
+    ReadKernelArgs a = a0;
+    const uint32_t split = std::min(a.pack_first, a.n_reads);
+    if (split > 0) {  // text part
+        a.r0 = 0;
+        a.r1 = split;
+        const unsigned blocks = (split + kReadsPerTile - 1) / kReadsPerTile;
+        if (a.estream) analyze_reads_kernel<HAS_QUAL, MOD, true, false><<<blocks, kFastThreads, 0, st>>>(a);
+        else analyze_reads_kernel<HAS_QUAL, MOD, false, false><<<blocks, kFastThreads, 0, st>>>(a);
+    }
+    if (split < a.n_reads) {  // packed part
+        a.r0 = split;
+        a.r1 = a.n_reads;
+        const unsigned blocks = (a.n_reads - split + kReadsPerTile - 1) / kReadsPerTile;
+        if (a.estream) analyze_reads_kernel<false, MOD, true, true><<<blocks, kFastThreads, 0, st>>>(a);
+        else analyze_reads_kernel<false, MOD, false, true><<<blocks, kFastThreads, 0, st>>>(a);
+    }
     if (ev_ka) cudaEventRecord(ev_ka, st);
     analyze_mid_kernel<HAS_QUAL, MOD><<<mid_blocks, kMidWarps * 32, 0, st>>>(a);
     analyze_slow_kernel<HAS_QUAL, MOD><<<slow_blocks, 128, 0, st>>>(a);
 }
 
-int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st, cudaEvent_t ev_k0,
+int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t multi_cap, cudaStream_t st, cudaEvent_t ev_k0,
                         cudaEvent_t ev_ka, cudaEvent_t ev_k1)
 {
     if (ev_k0) cudaEventRecord(ev_k0, st);
@@ -873,9 +957,10 @@ int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_ca
         // tile_base <- exclusive scan(tile_sums); the grand total lands in tile_base[tiles]
         cudaMemcpyAsync(a.tile_base, a.tile_sums, (size_t)tiles * 4, cudaMemcpyDeviceToDevice, st);
         scan_tile_sums_kernel<<<1, 1024, 0, st>>>(a.tile_base, tiles, a.tile_base + tiles);
-        scatter_assoc_kernel<<<tiles, kReadsPerTile, 0, st>>>(a, assoc_cap, a.tile_base + tiles);
-        launched = 5;
-        ctx->launches += 5;
+        scatter_assoc_kernel<<<tiles, kReadsPerTile, 0, st>>>(a, multi_cap, a.tile_base + tiles);
+        const uint32_t split = std::min(a.pack_first, a.n_reads);
+        launched = 4 + (split > 0 ? 1 : 0) + (split < a.n_reads ? 1 : 0);
+        ctx->launches += launched;
     }
     else if (ev_ka) cudaEventRecord(ev_ka, st);
     if (ev_k1) cudaEventRecord(ev_k1, st);
@@ -886,46 +971,6 @@ __global__ void fetch_policies_kernel(uint64_t *out)
 {
     out[0] = make_policy_evict_first();
     out[1] = make_policy_evict_last();
-}
-
-// Expands host-packed reads (shk_hostpack.h: 2-bit code + validity bit per base) back to text in HBM:
-// valid -> 'A','C','T','G' by code, invalid -> 'N'.  The classification kernels only look at a byte's
-// validity and code (to_int, kmer_utils.hpp:29-41), and the quality masking is already folded into the
-// validity bits, so they run on this text without qualities and produce the same results.
-// One thread = one group of 32 bases = 32 output bytes (two 16-byte stores).
-__global__ void __launch_bounds__(256)
-unpack_reads_kernel(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ valid, uint64_t groups, uint4 *text)
-{
-    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= groups) return;
-    const uint64_t c = codes[g];
-    const uint32_t v = valid[g];
-    uint32_t w[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int i = j * 4 + b;
-            const uint32_t code = (uint32_t)(c >> (2 * i)) & 3u;
-            const uint32_t ch = ((v >> i) & 1u) ? ((0x47544341u >> (8 * code)) & 0xFFu) : (uint32_t)'N';  // A C T G
-            word |= ch << (8 * b);
-        }
-        w[j] = word;
-    }
-    text[2 * g] = make_uint4(w[0], w[1], w[2], w[3]);
-    text[2 * g + 1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
-
-int launch_unpack(shk_ctx *ctx, const uint64_t *d_codes, const uint32_t *d_valid, uint64_t n_bytes, uint8_t *d_seq,
-                  cudaStream_t st)
-{
-    const uint64_t groups = (n_bytes + 31) / 32;
-    if (!groups) return 0;
-    unpack_reads_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(d_codes, d_valid, groups,
-                                                                          reinterpret_cast<uint4 *>(d_seq));
-    ctx->launches += 1;
-    return 1;
 }
 
 int fetch_cache_policies(shk_ctx *ctx)
@@ -942,11 +987,11 @@ int fetch_cache_policies(shk_ctx *ctx)
 }
 
 // Re-runs only the scatter (after the host grew the association buffer).
-int launch_scatter(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st)
+int launch_scatter(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t multi_cap, cudaStream_t st)
 {
     if (a.n_reads == 0) return 0;
     const unsigned tiles = (a.n_reads + kReadsPerTile - 1) / kReadsPerTile;
-    scatter_assoc_kernel<<<tiles, kReadsPerTile, 0, st>>>(a, assoc_cap, a.tile_base + tiles);
+    scatter_assoc_kernel<<<tiles, kReadsPerTile, 0, st>>>(a, multi_cap, a.tile_base + tiles);
     ctx->launches += 1;
     return 1;
 }

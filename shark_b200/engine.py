@@ -15,11 +15,15 @@ from . import capi
 
 class Shark:
     def __init__(self, k=17, c=0.6, bf_bits=1 << 33, min_quality=0, single=False, device=0, n_slots=2,
-                 max_reads_per_chunk=1 << 20, max_bytes_per_chunk=0, extend=None, host_pack=False):
+                 max_reads_per_chunk=1 << 20, max_bytes_per_chunk=0, extend=None, host_pack=False, compact=False):
         """extend: None = automatic (anchor-and-extend when the front table is DRAM-sized), True /
-        False = force it on / off (results are identical; tests run both)."""
+        False = force it on / off (results are identical; tests run both).  compact: results stay in the
+        compact form (gene16 / multi), shk_reads_collect does no per-read host work."""
         self.lib = capi.load()
         flags = 0 if extend is None else (capi.F_EXTEND_ON if extend else capi.F_EXTEND_OFF)
+        if compact:
+            flags |= capi.F_COMPACT_RESULTS
+        self.compact = bool(compact)
         permille = 0
         if host_pack:  # split upload: part of every chunk is packed to 3 bits per base by the host cores
             flags |= capi.F_HOST_PACK
@@ -229,6 +233,13 @@ class Shark:
         self._check(self.lib.shk_reads_submit(self.ctx, slot, capi.ptr(seq), capi.ptr(qual) if qual is not None else None,
                                               capi.ptr(off32), n_reads))
 
+    def submit_packed(self, slot, codes, valid, off32, n_reads):
+        """The chunk in the packed form of capi.host_pack (masking already applied)."""
+        self._check(self.lib.shk_reads_submit_packed(self.ctx, slot, capi.ptr(codes), capi.ptr(valid), capi.ptr(off32), n_reads))
+
+    def upload_packed(self, slot, codes, valid, off32, n_reads):
+        self._check(self.lib.shk_reads_upload_packed(self.ctx, slot, capi.ptr(codes), capi.ptr(valid), capi.ptr(off32), n_reads))
+
     def upload(self, slot, seq, qual, off32, n_reads):
         self._check(self.lib.shk_reads_upload(self.ctx, slot, capi.ptr(seq), capi.ptr(qual) if qual is not None else None,
                                               capi.ptr(off32), n_reads))
@@ -237,21 +248,46 @@ class Shark:
         self._check(self.lib.shk_reads_analyze_resident(self.ctx, slot))
 
     def collect(self, slot, copy=True):
-        """-> dict(read_idx, gene_idx, keep, n_probes, n_hits, analyze_ms, ...)"""
+        """-> dict(read_idx, gene_idx, keep, gene16, multi, n_probes, n_hits, analyze_ms, ...); with compact=True
+        the expanded arrays (read_idx, gene_idx, keep) are None."""
         res = capi.ChunkResult()
         self._check(self.lib.shk_reads_collect(self.ctx, slot, C.byref(res)))
         n = res.n_assoc
-        if n:
-            a = np.ctypeslib.as_array(C.cast(res.assoc, C.POINTER(C.c_uint32)), shape=(n, 2))
+        gene16 = np.ctypeslib.as_array(res.gene16, shape=(max(res.n_reads, 1),))[: res.n_reads]
+        if res.n_multi:
+            multi = np.ctypeslib.as_array(C.cast(res.multi, C.POINTER(C.c_uint32)), shape=(res.n_multi, 2))
         else:
-            a = np.zeros((0, 2), np.uint32)
-        keep = np.ctypeslib.as_array(res.keep, shape=(max(res.n_reads, 1),))[: res.n_reads]
+            multi = np.zeros((0, 2), np.uint32)
         if copy:
-            a, keep = a.copy(), keep.copy()
-        return dict(read_idx=a[:, 0], gene_idx=a[:, 1], keep=keep, n_assoc=int(n), n_reads=res.n_reads,
+            gene16, multi = gene16.copy(), multi.copy()
+        a = keep = None
+        if not self.compact:
+            if n:
+                a = np.ctypeslib.as_array(C.cast(res.assoc, C.POINTER(C.c_uint32)), shape=(n, 2))
+            else:
+                a = np.zeros((0, 2), np.uint32)
+            keep = np.ctypeslib.as_array(res.keep, shape=(max(res.n_reads, 1),))[: res.n_reads]
+            if copy:
+                a, keep = a.copy(), keep.copy()
+        return dict(read_idx=None if a is None else a[:, 0], gene_idx=None if a is None else a[:, 1], keep=keep,
+                    gene16=gene16, multi=multi, n_multi=int(res.n_multi), n_kept=int(res.n_kept),
+                    n_assoc=int(n), n_reads=res.n_reads,
                     n_slow_reads=res.n_slow_reads, n_probes=res.n_probes, n_hits=res.n_hits,
                     analyze_ms=res.analyze_ms, total_ms=res.total_ms, kernel_launches=res.kernel_launches,
                     probe_kernel_ms=res.probe_kernel_ms, n_extended=res.n_extended, n_table_loads=res.n_table_loads)
+
+    @staticmethod
+    def expand(result):
+        """Compact result dict -> (read_idx uint32[n_assoc], gene_idx uint32[n_assoc], keep uint8[n_reads]),
+        vectorised (what shk_result_expand does in C)."""
+        g = result["gene16"].astype(np.uint32)
+        keep = (g != capi.GENE_NONE).astype(np.uint8)
+        single = np.nonzero(g < capi.GENE_MULTI)[0].astype(np.uint32)
+        multi = result["multi"]
+        ridx = np.concatenate([single, multi[:, 0]])
+        gidx = np.concatenate([g[single], multi[:, 1]])
+        order = np.lexsort((gidx, ridx))
+        return ridx[order], gidx[order], keep
 
     def timer_start(self):
         """Device stopwatch (CUDA events) over all slot streams of this context."""
@@ -316,10 +352,12 @@ class Shark:
             i = j
         return chunks
 
-    def analyze(self, seq, off, qual=None):
+    def analyze(self, seq, off, qual=None, packed=False):
         """Classifies reads given as SoA (seq uint8, off uint64/uint32 [n+1], qual uint8|None):
         chunks them, streams the chunks through the slots (pinned staging, double buffered) and
-        returns (keep uint8[n], assoc_read uint64[m], assoc_gene uint32[m], stats)."""
+        returns (keep uint8[n], assoc_read uint64[m], assoc_gene uint32[m], stats).  packed=True: every
+        chunk is reduced to codes + validity bits with shk_host_pack first and goes through
+        shk_reads_submit_packed (what the CLI's batcher does)."""
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         off = np.ascontiguousarray(off)
         n = len(off) - 1
@@ -336,6 +374,9 @@ class Shark:
         def drain():
             slot, first = pending.pop(0)
             r = self.collect(slot)
+            if self.compact:
+                r["read_idx"], r["gene_idx"], r["keep"] = self.expand(r)
+                assert len(r["read_idx"]) == r["n_assoc"] and int(r["keep"].sum()) == r["n_kept"]
             keep[first:first + r["n_reads"]] = r["keep"]
             out_r.append(r["read_idx"].astype(np.uint64) + np.uint64(first))
             out_g.append(r["gene_idx"])
@@ -351,12 +392,22 @@ class Shark:
             base = int(off[a])
             nb = int(off[b]) - base
             s_seq, s_qual, s_off = self._stage(slot, nb, b - a, with_qual)
-            s_seq.u8[:nb] = seq[base:base + nb]
-            if with_qual:
-                s_qual.u8[:nb] = qual[base:base + nb]
             o32 = s_off.view(np.uint32, b - a + 1)
             o32[:] = (off[a:b + 1] - off[a]).astype(np.uint32)
-            self.submit(slot, s_seq.u8, s_qual.u8 if with_qual else None, o32, b - a)
+            if packed:
+                codes, valid = capi.host_pack(seq[base:base + nb], qual[base:base + nb] if with_qual else None,
+                                              self.min_quality)
+                g = len(codes)
+                s_seq.u8[:g * 8] = codes.view(np.uint8)      # the staging buffers are pinned: reuse them
+                pv = s_seq.u8[((g * 8 + 63) // 64) * 64:][:g * 4]
+                pv[:] = valid.view(np.uint8)
+                self.submit_packed(slot, s_seq.u8[:g * 8].view(np.uint64) if g else s_seq.u8[:0].view(np.uint64),
+                                   pv.view(np.uint32), o32, b - a)
+            else:
+                s_seq.u8[:nb] = seq[base:base + nb]
+                if with_qual:
+                    s_qual.u8[:nb] = qual[base:base + nb]
+                self.submit(slot, s_seq.u8, s_qual.u8 if with_qual else None, o32, b - a)
             pending.append((slot, a))
         while pending:
             drain()
@@ -364,13 +415,14 @@ class Shark:
         ag = np.concatenate(out_g) if out_g else np.zeros(0, np.uint32)
         return keep, ar, ag, stats
 
-    def analyze_chunks(self, chunks, copy=True, on_result=None):
+    def analyze_chunks(self, chunks, copy=True, on_result=None, packed=False):
         """Streams pre-chunked host inputs through the slots, double buffered: chunk i+1 is
         submitted (H2D + kernels enqueued) before chunk i is collected.  `chunks` is a sequence
         of (seq uint8, qual uint8|None, off32 uint32[n+1], n_reads) whose arrays should live in
         pinned memory (capi.PinnedBuffer) so that the copies are asynchronous - this is what the
-        FASTQ batcher of the host side produces.  Returns the per-chunk result dicts in order
-        (or feeds them to on_result)."""
+        FASTQ batcher of the host side produces.  packed=True: the chunks are (codes uint64, valid uint32,
+        off32, n_reads) in the packed form and go through shk_reads_submit_packed.  Returns the per-chunk
+        result dicts in order (or feeds them to on_result)."""
         results, pending = [], []
 
         def drain():
@@ -385,7 +437,10 @@ class Shark:
             slot = ci % self.n_slots
             if len(pending) == self.n_slots:
                 drain()
-            self.submit(slot, seq, qual, off32, n_reads)
+            if packed:
+                self.submit_packed(slot, seq, qual, off32, n_reads)
+            else:
+                self.submit(slot, seq, qual, off32, n_reads)
             pending.append(slot)
         while pending:
             drain()

@@ -144,3 +144,50 @@ def write_fastq(path1, path2, seq, qual, n_reads, L, paired, first_name=0):
     f1.close()
     if f2:
         f2.close()
+
+
+def fastq_records(mate, qual, first_name):
+    """Fixed-length reads (uint8[n, L]) -> uint8[n, R] of FASTQ records `@r%09d\nSEQ\n+\nQUAL\n`, built with
+    array operations (the per-read loop of write_fastq manages ~0.5 M reads/s; this writes tens of millions)."""
+    n, L = mate.shape
+    R = 12 + L + 3 + L + 1
+    rec = np.empty((n, R), np.uint8)
+    rec[:, 0] = ord("@")
+    rec[:, 1] = ord("r")
+    idx = np.arange(first_name, first_name + n, dtype=np.int64)
+    for d in range(9):
+        rec[:, 10 - d] = (idx % 10 + ord("0")).astype(np.uint8)
+        idx //= 10
+    rec[:, 11] = ord("\n")
+    rec[:, 12:12 + L] = mate
+    rec[:, 12 + L:15 + L] = np.frombuffer(b"\n+\n", np.uint8)
+    rec[:, 15 + L:15 + 2 * L] = qual if qual is not None else ord("I")
+    rec[:, 15 + 2 * L] = ord("\n")
+    return rec
+
+
+def write_fastq_fast(path1, path2, seq, qual, n_reads, L, paired, first_name=0, append=False, piece=1 << 20):
+    """Same files as write_fastq, vectorised; `append` adds to existing files."""
+    W = 2 * L + 1 if paired else L
+    t = np.asarray(seq[: n_reads * W]).reshape(n_reads, W)
+    q = np.asarray(qual[: n_reads * W]).reshape(n_reads, W) if qual is not None else None
+    mode = "ab" if append else "wb"
+    with open(path1, mode) as f1:
+        f2 = open(path2, mode) if paired else None
+        for a in range(0, n_reads, piece):
+            b = min(a + piece, n_reads)
+            fastq_records(t[a:b, :L], None if q is None else q[a:b, :L], first_name + a).tofile(f1)
+            if paired:
+                fastq_records(t[a:b, L + 1:], None if q is None else q[a:b, L + 1:], first_name + a).tofile(f2)
+        if f2:
+            f2.close()
+
+
+def fastq_bytes(seq, qual, n_reads, L, paired, first_name=0):
+    """-> (bytes of mate-1 FASTQ, bytes of mate-2 FASTQ | None) for n_reads reads, in memory."""
+    W = 2 * L + 1 if paired else L
+    t = np.asarray(seq[: n_reads * W]).reshape(n_reads, W)
+    q = np.asarray(qual[: n_reads * W]).reshape(n_reads, W) if qual is not None else None
+    b1 = fastq_records(t[:, :L], None if q is None else q[:, :L], first_name).tobytes()
+    b2 = fastq_records(t[:, L + 1:], None if q is None else q[:, L + 1:], first_name).tobytes() if paired else None
+    return b1, b2

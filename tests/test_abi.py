@@ -33,7 +33,7 @@ def test_binding_matches_header(lib_path):
     from shark_b200 import capi
     assert sorted(capi.EXPORTED) == _declared()
     L = capi.load()
-    assert L.shk_abi_version() == 4
+    assert L.shk_abi_version() == 5
 
 
 def test_struct_sizes():
@@ -42,7 +42,7 @@ def test_struct_sizes():
     assert ctypes.sizeof(capi.Params) == 88
     assert ctypes.sizeof(capi.IndexInfo) == 88
     assert ctypes.sizeof(capi.Assoc) == 8
-    assert ctypes.sizeof(capi.ChunkResult) == 80
+    assert ctypes.sizeof(capi.ChunkResult) == 112
     assert ctypes.sizeof(capi.IndexViews) == 64 + 64 + 88
     assert ctypes.sizeof(capi.ShardMem) == 24 + 192 + 8 + 16
 
