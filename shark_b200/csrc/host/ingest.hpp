@@ -1,6 +1,6 @@
 // Block-wise FASTQ/FASTA ingest for the host side of shark-b200.
 //
-// FastqScanner yields exactly the sequence of kseq_read() outcomes that FastxReader (fastx.hpp,
+// FastqScanner yields exactly the sequence of kseq_read() outcomes that FastxReader (tests/host_tools/fastx.hpp,
 // the record-at-a-time restatement of kseq.h:177-218) yields on the same bytes, but works on
 // 8 MiB blocks: a record in the strict four-line shape
 //        @name[ comment]\n  SEQ\n  +[anything]\n  QUAL\n        with |QUAL| == |SEQ|
@@ -44,6 +44,7 @@ struct Block {
     size_t arena_used = 0, arena_cap = 0;
     std::vector<Rec> recs;
     bool has_nul = false;  // some buffer byte is 0: consumers apply C-string semantics per field
+    bool all_ok = false;   // every outcome is a record (status >= 0) and no byte is 0: bulk consumers may take it whole
 
     char *arena_alloc(size_t n)
     {
@@ -101,12 +102,75 @@ private:
     std::vector<char *> free_;
 };
 
+// One record in the strict four-line shape at base[pos..end):
+//        @name[ comment]\n  SEQ\n  +[anything]\n  QUAL\n        with |QUAL| == |SEQ|
+// kStrictOk: r filled (pointers into base), next = position after the record.  kStrictNeedMore: the bytes up
+// to `end` do not hold the whole record.  kStrictFormat: not this shape - the character-level state machine
+// decides.  Four memchr calls, no copy.
+enum { kStrictOk = 0, kStrictNeedMore = 1, kStrictFormat = 2 };
+inline int parse_strict(const char *base, size_t pos, size_t end, Rec &r, size_t &next)
+{
+    const char *p = base + pos, *e = base + end;
+    if (p >= e) return kStrictNeedMore;
+    if (*p != '@') return kStrictFormat;
+    // header line: short, scanned once for both the end of the name and the end of the line
+    const char *n0 = p + 1, *n1 = nullptr, *l1 = n0;
+    for (;; ++l1) {
+        if (l1 >= e) return kStrictNeedMore;
+        const unsigned char c = (unsigned char)*l1;
+        if (c > ' ') continue;  // isspace() bytes are all <= ' '
+        if (c == '\n') break;
+        if (!n1 && isspace(c)) {
+            n1 = l1;
+            const char *nl = (const char *)memchr(l1, '\n', (size_t)(e - l1));  // comment: skip it
+            if (!nl) return kStrictNeedMore;
+            l1 = nl;
+            break;
+        }
+    }
+    if (!n1) n1 = l1;
+    const char *s = l1 + 1;
+    if (s >= e) return kStrictNeedMore;
+    if (*s == '\n' || *s == '>' || *s == '+' || *s == '@') return kStrictFormat;
+    const char *l2 = (const char *)memchr(s, '\n', (size_t)(e - s));
+    if (!l2) return kStrictNeedMore;
+    if (l2[-1] == '\r') return kStrictFormat;
+    const char *t = l2 + 1;
+    if (e - t < 2) return kStrictNeedMore;
+    if (*t != '+') return kStrictFormat;
+    const char *l3 = t[1] == '\n' ? t + 1 : (const char *)memchr(t, '\n', (size_t)(e - t));
+    if (!l3) return kStrictNeedMore;
+    const char *q = l3 + 1;
+    const size_t sl = (size_t)(l2 - s);
+    if ((size_t)(e - q) <= sl) return kStrictNeedMore;  // the quality line and its '\n' must be here
+    if (q[sl] != '\n') return kStrictFormat;            // shorter (a '\n' earlier is caught below) or longer
+    if (memchr(q, '\n', sl) != nullptr || q[sl - 1] == '\r') return kStrictFormat;
+    r.name = n0;
+    r.name_len = (uint32_t)(n1 - n0);
+    r.seq = s;
+    r.seq_len = (uint32_t)sl;
+    r.qual = q;
+    r.qual_len = (uint32_t)sl;
+    r.status = (int32_t)sl;
+    next = (size_t)(q + sl + 1 - base);
+    return kStrictOk;
+}
+
 class FastqScanner {
 public:
-    explicit FastqScanner(const char *path, size_t block_bytes = 8u << 20) : block_bytes_(block_bytes)
+    // start_offset: plain (uncompressed) files only - continue at that byte, at a record boundary (the parallel
+    // scanner of fastpipe.hpp hands its tail over this way)
+    explicit FastqScanner(const char *path, size_t block_bytes = 8u << 20, uint64_t start_offset = 0) : block_bytes_(block_bytes)
     {
         fd_ = open(path, O_RDONLY);
         if (fd_ < 0) return;
+        if (start_offset) {
+            if (lseek(fd_, (off_t)start_offset, SEEK_SET) < 0) {
+                close(fd_);
+                fd_ = -1;
+            }
+            return;
+        }
         // gzip or plain, like gzopen/gzread; a plain file is then read with read(2) directly
         unsigned char magic[2] = {0, 0};
         const ssize_t m = pread(fd_, magic, 2, 0);
@@ -152,6 +216,12 @@ public:
             if (r == -1 || r == -3) break;  // sticky: do not spin at end of file
         }
         blk_ = nullptr;
+        blk->all_ok = !blk->has_nul;
+        for (const Rec &r : blk->recs)
+            if (r.status < 0) {
+                blk->all_ok = false;
+                break;
+            }
         return blk;
     }
 
@@ -234,52 +304,12 @@ private:
     int fast_record()
     {
         if (!buf_) return kNeedMore;
-        const char *base = buf_.get();
-        const char *p = base + pos_, *e = base + end_;
-        if (p >= e) return kNeedMore;
-        if (*p != '@') return kFormat;
-        // header line: short, scanned once for both the end of the name and the end of the line
-        const char *n0 = p + 1, *n1 = nullptr, *l1 = n0;
-        for (;; ++l1) {
-            if (l1 >= e) return kNeedMore;
-            const unsigned char c = (unsigned char)*l1;
-            if (c > ' ') continue;  // isspace() bytes are all <= ' '
-            if (c == '\n') break;
-            if (!n1 && isspace(c)) {
-                n1 = l1;
-                const char *nl = (const char *)memchr(l1, '\n', (size_t)(e - l1));  // comment: skip it
-                if (!nl) return kNeedMore;
-                l1 = nl;
-                break;
-            }
-        }
-        if (!n1) n1 = l1;
-        const char *s = l1 + 1;
-        if (s >= e) return kNeedMore;
-        if (*s == '\n' || *s == '>' || *s == '+' || *s == '@') return kFormat;
-        const char *l2 = (const char *)memchr(s, '\n', (size_t)(e - s));
-        if (!l2) return kNeedMore;
-        if (l2[-1] == '\r') return kFormat;
-        const char *t = l2 + 1;
-        if (e - t < 2) return kNeedMore;
-        if (*t != '+') return kFormat;
-        const char *l3 = t[1] == '\n' ? t + 1 : (const char *)memchr(t, '\n', (size_t)(e - t));
-        if (!l3) return kNeedMore;
-        const char *q = l3 + 1;
-        const size_t sl = (size_t)(l2 - s);
-        if ((size_t)(e - q) <= sl) return kNeedMore;  // the quality line and its '\n' must be here
-        if (q[sl] != '\n') return kFormat;            // shorter (a '\n' earlier is caught below) or longer
-        if (memchr(q, '\n', sl) != nullptr || q[sl - 1] == '\r') return kFormat;
         Rec r;
-        r.name = n0;
-        r.name_len = (uint32_t)(n1 - n0);
-        r.seq = s;
-        r.seq_len = (uint32_t)sl;
-        r.qual = q;
-        r.qual_len = (uint32_t)sl;
-        r.status = (int32_t)sl;
+        size_t next = 0;
+        const int st = parse_strict(buf_.get(), pos_, end_, r, next);
+        if (st != kStrictOk) return st == kStrictNeedMore ? kNeedMore : kFormat;
         blk_->recs.push_back(r);
-        pos_ = (size_t)(q + sl + 1 - base);
+        pos_ = next;
         return kOk;
     }
 

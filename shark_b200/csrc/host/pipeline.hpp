@@ -1,16 +1,28 @@
 // Host pipeline stages of shark-b200 around the device calls:
 //
-//   RecordStream x {1,2}  ->  Batcher  ->  [shk_reads_submit / shk_reads_collect]  ->  Writer
-//   (ingest.hpp, a thread     (a thread)     (the caller's thread)                     (a thread)
-//    per input file)
+//   RecordSource x {1,2}  ->  Batcher  ->  [shk_reads_submit_packed / shk_reads_collect]  ->  Writer
+//   (fastpipe.hpp: parallel    (a thread +    (the caller's thread)                            (a thread +
+//    scan of mapped files)      the pool)                                                       the pool)
 //
 // Batcher = FastqSplitter::operator() called until it returns an empty batch (main.cpp:66-77,
-// FastqSplitter.hpp:47-93): whole 50 000-read batches are packed into one chunk in the SoA layout
-// of shk_reads_submit; what ReadOutput prints later (names, qualities) is kept as pointers into
-// the scanner blocks, which the chunk keeps alive.  Writer = ReadOutput::operator()
-// (ReadOutput.hpp:37-50) per batch, with its own buffers and write(2).
-// `Alloc` provides the staging memory (pinned, from the library, in the CLI).
+// FastqSplitter.hpp:47-93).  Every chunk leaves the batcher in the PACKED form of shk_reads_submit_packed
+// (2-bit code + validity bit per base, the -q masking rule of FastqSplitter.hpp:104-109 folded in): the
+// device never sees text or qualities.  Two ways to build a chunk:
+//   bulk   runs of plain records (status >= 0, no NUL bytes - all of a well-formed FASTQ file): offsets by a
+//          parallel prefix sum over the record lengths, then the pool packs 64 KiB pieces of the chunk's
+//          joined text (mate1 [+ 'N' + mate2]) straight from the mapped input; no text staging, the writer
+//          later takes names, sequences and qualities from the records themselves;
+//   exact  outcome by outcome, with the reference's behaviour at failed reads, NUL bytes (C-string
+//          semantics of FastqSplitter.hpp:56) and the end of the input; builds the text in a staging buffer
+//          and packs that.  A bulk chunk ends where the next outcome needs this path.
+// Batches: ReadOutput's consecutive-name dedup resets per 50 000-read batch (ReadOutput.hpp:41); a batch may
+// span chunks (chunks are bounded by reads AND by bytes), so the batcher marks the batch starts inside every
+// chunk and the writer carries the last kept name across chunks.
+// Writer = ReadOutput::operator() (ReadOutput.hpp:37-50): formats ranges of a chunk's reads in parallel from
+// the compact results (one 16-bit word per read + a list for ties), writes with pwrite at precomputed
+// offsets when the descriptor is seekable, in order otherwise.
 #pragma once
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -21,15 +33,21 @@
 #include <string>
 #include <vector>
 
-#include "ingest.hpp"
+#include "fastpipe.hpp"
 
 namespace shkhost {
 
 constexpr unsigned kBatch = 50000;  // FastqSplitter batch (main.cpp:215): ReadOutput's dedup resets per batch
+constexpr uint32_t kGeneNone = 0xFFFFu, kGeneMulti = 0xFFFEu;  // SHK_GENE_NONE / SHK_GENE_MULTI
 
 struct AssocPair {  // layout of shk_assoc
     uint32_t read_idx, gene_idx;
 };
+
+// shk_host_pack(seq, qual, min_quality, n, codes, valid, parallel = 0): the library's packer, or a restatement
+// where the library is not linked (host_tools)
+using PackFn = void (*)(const uint8_t *seq, const uint8_t *qual, int32_t min_quality, uint64_t n, uint64_t *codes,
+                        uint32_t *valid);
 
 template <class Alloc>
 struct Staging {
@@ -54,7 +72,7 @@ struct Staging {
     }
 };
 
-// What ReadOutput needs for one read besides the sequence text (which is in Chunk::seq).
+// What ReadOutput needs for one read of an exact-path chunk besides the sequence text (which is in Chunk::seq).
 struct ReadMeta {
     const char *name1 = nullptr, *qual1 = nullptr, *name2 = nullptr, *qual2 = nullptr;
     uint32_t nlen1 = 0, qlen1 = 0, nlen2 = 0, qlen2 = 0;
@@ -63,33 +81,48 @@ struct ReadMeta {
 
 template <class Alloc>
 struct Chunk {
-    Staging<Alloc> seq, qual, off;      // text (mate1 [+ 'N' + mate2]), qualities (+ 0x1B), uint32 offsets
+    // what the device gets (both kinds of chunk)
+    Staging<Alloc> off, codes, valid;   // uint32 offsets [n + 1], uint64 code words, uint32 validity words
+    // bulk chunks: the records themselves
+    bool bulk = false;
+    std::vector<const Rec *> r1, r2;
+    // exact chunks: joined text, qualities for the packer, per-read output fields
+    Staging<Alloc> seq, qual;
     std::vector<ReadMeta> meta;
     std::vector<uint32_t> batch_start;  // read indices where a 50 000-read batch begins
     std::vector<std::shared_ptr<Block>> keep;
-    std::vector<AssocPair> assoc;       // results, copied out of the slot before the slot is reused
+    // results, copied out of the slot before the slot is reused (compact form)
+    std::vector<uint16_t> gene16;
+    std::vector<AssocPair> multi;
     uint32_t n = 0;
     uint64_t bytes = 0;
     bool last = false;
     uint64_t index = 0;
     void clear()
     {
+        r1.clear();
+        r2.clear();
         meta.clear();
         batch_start.clear();
         keep.clear();
-        assoc.clear();
+        gene16.clear();
+        multi.clear();
+        bulk = false;
         n = 0;
         bytes = 0;
         last = false;
     }
+    const uint32_t *offsets() const { return (const uint32_t *)off.p; }
+    uint64_t groups() const { return (bytes + 31) / 32; }
 };
 
 template <class Alloc>
 class Batcher {
 public:
-    Batcher(const char *path1, const char *path2, bool with_qual_gpu) : s1_(path1), with_qual_gpu_(with_qual_gpu)
+    Batcher(const char *path1, const char *path2, int32_t min_quality, PackFn pack)
+        : s1_(path1), min_quality_(min_quality), with_qual_((min_quality & 0xFF) != 0), pack_(pack)
     {
-        if (path2) s2_.reset(new RecordStream(path2));
+        if (path2) s2_.reset(new RecordSource(path2));
     }
     bool files_ok() const { return s1_.ok() && (!s2_ || s2_->ok()); }
     void start()
@@ -98,54 +131,248 @@ public:
         if (s2_) s2_->start();
     }
 
-    // Fills one chunk with whole batches; returns false when the input is exhausted (the chunk
-    // may still hold reads).  A failed read ends the CURRENT batch only (FastqSplitter.hpp:53,61).
+    // Fills one chunk (at most max_reads reads and max_bytes bytes of joined text); returns false when the
+    // input is exhausted (the chunk may still hold reads).
     bool fill(Chunk<Alloc> &ch, unsigned max_reads, uint64_t max_bytes)
     {
         ch.clear();
-        max_reads_ = max_reads;
-        max_bytes_ = max_bytes;
-        uint64_t last_batch_bytes = 0;
-        while ((ch.n + kBatch <= max_reads && ch.bytes + last_batch_bytes + last_batch_bytes / 4 <= max_bytes) || ch.n == 0) {
-            ch.batch_start.push_back(ch.n);
-            const uint64_t bytes0 = ch.bytes;
-            unsigned got = 0;
-            while (got < kBatch) {
-                const Rec a = s1_.peek();
-                if (a.status < 0) {
-                    s1_.consume();
-                    break;
-                }
-                const std::shared_ptr<Block> &ba = s1_.block();
-                hold(ch, ba);
-                const bool nul_a = ba->has_nul;
-                s1_.consume();
-                Rec b;
-                bool nul_b = false;
-                if (s2_) {
-                    b = s2_->peek();
-                    if (b.status < 0) {  // mate 1 is dropped (FastqSplitter.hpp:61)
-                        s2_->consume();
-                        break;
-                    }
-                    const std::shared_ptr<Block> &bb = s2_->block();
-                    hold(ch, bb);
-                    nul_b = bb->has_nul;
-                    s2_->consume();
-                }
-                append(ch, a, nul_a, b, nul_b);
-                ++got;
-            }
-            if (got == 0) {
-                ch.batch_start.pop_back();
-                return false;  // empty batch: the reference's worker returns (main.cpp:70)
-            }
-            last_batch_bytes = ch.bytes - bytes0;
+        if (finished_) return false;
+        static const bool no_bulk = getenv("SHK_NO_BULK") && atoi(getenv("SHK_NO_BULK")) != 0;
+        size_t n = no_bulk ? 0 : s1_.clean_run(max_reads);
+        if (s2_ && n) n = std::min(n, s2_->clean_run(n));
+        if (n) {
+            fill_bulk(ch, n, max_bytes);
+            if (ch.n) return true;  // (a first read longer than max_bytes: the exact path reports it)
         }
-        return true;
+        return fill_exact(ch, max_reads, max_bytes);
     }
+    const char *error() const { return error_.empty() ? nullptr : error_.c_str(); }
 
 private:
+    // ---- bulk ----------------------------------------------------------------------------------------------
+    void fill_bulk(Chunk<Alloc> &ch, size_t n, uint64_t max_bytes)
+    {
+        const bool paired = (bool)s2_;
+        // the records, without consuming them yet: the byte bound may cut the chunk short
+        std::vector<Span> sp1, sp2;
+        std::vector<std::shared_ptr<Block>> keep1, keep2;
+        peek_spans(s1_, n, sp1, keep1);
+        if (paired) peek_spans(*s2_, n, sp2, keep2);
+        ch.r1.resize(n);
+        if (paired) ch.r2.resize(n);
+        flatten(sp1, ch.r1);
+        if (paired) flatten(sp2, ch.r2);
+        // offsets: per-range byte sums, their prefix, then the fill - all ranges in parallel
+        ch.off.reserve((n + 2) * 4, 0);
+        uint32_t *off = (uint32_t *)ch.off.p;
+        const size_t n_ranges = std::min<size_t>(64, (n + 4095) / 4096);
+        const size_t per = (n + n_ranges - 1) / n_ranges;
+        std::vector<uint64_t> sum(n_ranges + 1, 0);
+        auto len_of = [&](size_t i) -> uint64_t {
+            return paired ? (uint64_t)ch.r1[i]->seq_len + 1 + ch.r2[i]->seq_len : ch.r1[i]->seq_len;
+        };
+        WorkPool::instance().run(n_ranges, [&](size_t t) {
+            uint64_t s = 0;
+            for (size_t i = t * per, e = std::min(n, i + per); i < e; ++i) s += len_of(i);
+            sum[t + 1] = s;
+        });
+        for (size_t t = 0; t < n_ranges; ++t) sum[t + 1] += sum[t];
+        // byte bound: the longest prefix of reads whose text fits (ranges first, then inside the range)
+        size_t n_fit = n;
+        if (sum[n_ranges] > max_bytes) {
+            size_t t = 0;
+            while (sum[t + 1] <= max_bytes) ++t;
+            uint64_t s = sum[t];
+            size_t i = t * per;
+            for (; i < n && s + len_of(i) <= max_bytes; ++i) s += len_of(i);
+            n_fit = i;
+        }
+        if (n_fit == 0) {
+            ch.clear();
+            return;
+        }
+        WorkPool::instance().run(n_ranges, [&](size_t t) {
+            uint64_t s = sum[t];
+            for (size_t i = t * per, e = std::min(n_fit, i + per); i < e; ++i) {
+                off[i] = (uint32_t)s;
+                s += len_of(i);
+            }
+        });
+        uint64_t total = 0;
+        {
+            const size_t t = (n_fit - 1) / per;
+            total = sum[t];
+            for (size_t i = t * per; i < n_fit; ++i) total += len_of(i);
+        }
+        off[n_fit] = (uint32_t)total;
+        n = n_fit;
+        ch.r1.resize(n);
+        if (paired) ch.r2.resize(n);
+        // consume what the chunk holds
+        {
+            std::vector<Span> dummy;
+            s1_.take(n, dummy, ch.keep);
+            if (paired) {
+                dummy.clear();
+                s2_->take(n, dummy, ch.keep);
+            }
+        }
+        ch.bulk = true;
+        ch.n = (uint32_t)n;
+        ch.bytes = total;
+        for (size_t i = (kBatch - batch_got_) % kBatch; i < n; i += kBatch) ch.batch_start.push_back((uint32_t)i);
+        batch_got_ = (unsigned)((batch_got_ + n) % kBatch);
+        pack_bulk(ch);
+    }
+    static void peek_spans(RecordSource &s, size_t n, std::vector<Span> &spans, std::vector<std::shared_ptr<Block>> &keep)
+    {
+        s.peek_run(n, spans, keep);
+    }
+    static void flatten(const std::vector<Span> &spans, std::vector<const Rec *> &out)
+    {
+        // ranges of the flat array in parallel; a span is found by binary search over the span starts
+        std::vector<size_t> start(spans.size() + 1, 0);
+        for (size_t i = 0; i < spans.size(); ++i) start[i + 1] = start[i] + spans[i].n;
+        const size_t n = out.size();
+        const size_t n_ranges = std::min<size_t>(64, (n + 8191) / 8192);
+        const size_t per = (n + n_ranges - 1) / n_ranges;
+        WorkPool::instance().run(n_ranges, [&](size_t t) {
+            size_t i = t * per;
+            const size_t e = std::min(n, i + per);
+            size_t sp = (size_t)(std::upper_bound(start.begin(), start.end(), i) - start.begin()) - 1;
+            while (i < e) {
+                const size_t in_span = i - start[sp], m = std::min(e - i, spans[sp].n - in_span);
+                const Rec *r = spans[sp].recs + in_span;
+                for (size_t j = 0; j < m; ++j) out[i + j] = r + j;
+                i += m;
+                ++sp;
+            }
+        });
+    }
+    // Bytes [a, b) of the joined text / quality string of a bulk chunk, gathered from the records.
+    void gather(const Chunk<Alloc> &ch, uint64_t a, uint64_t b, uint8_t *seq, uint8_t *qual) const
+    {
+        const bool paired = (bool)s2_;
+        const uint32_t *off = ch.offsets();
+        size_t i = (size_t)(std::upper_bound(off, off + ch.n + 1, (uint32_t)a) - off) - 1;
+        uint64_t pos = a;
+        while (pos < b) {
+            const Rec &x = *ch.r1[i];
+            const uint64_t r0 = off[i], r_end = off[i + 1];
+            const uint64_t lo = pos - r0, hi = std::min(b, r_end) - r0;  // range inside this read's text
+            auto piece = [&](const char *src, uint64_t at, uint64_t len, uint8_t *dst_base) {  // src covers [at, at + len)
+                const uint64_t s = std::max(lo, at), e = std::min(hi, at + len);
+                if (s < e) memcpy(dst_base + (r0 + s - a), src + (s - at), e - s);
+            };
+            piece(x.seq, 0, x.seq_len, seq);
+            if (paired) {
+                const Rec &y = *ch.r2[i];
+                if (lo <= x.seq_len && x.seq_len < hi) seq[r0 + x.seq_len - a] = 'N';  // FastqSplitter.hpp:63,83
+                piece(y.seq, (uint64_t)x.seq_len + 1, y.seq_len, seq);
+            }
+            if (qual) {
+                // string(qual1) [+ "\33" + string(qual2)] (FastqSplitter.hpp:84); mask_seq walks the QUAL string
+                // (FastqSplitter.hpp:104-108): positions it does not reach are never masked -> 0x7f
+                const uint64_t total = r_end - r0;
+                memset(qual + (r0 + lo - a), 0x7f, hi - lo);
+                const uint64_t c1 = std::min<uint64_t>(x.qual_len, total);
+                piece(x.qual, 0, c1, qual);
+                if (paired) {
+                    const Rec &y = *ch.r2[i];
+                    uint64_t w = c1;
+                    if (w < total) {
+                        if (lo <= w && w < hi) qual[r0 + w - a] = 0x1B;
+                        ++w;
+                    }
+                    piece(y.qual, w, std::min<uint64_t>(y.qual_len, total - w), qual);
+                }
+            }
+            pos = r0 + hi;
+            ++i;
+        }
+    }
+    void pack_bulk(Chunk<Alloc> &ch)
+    {
+        const uint64_t groups = ch.groups();
+        ch.codes.reserve(groups * 8 + 64, 0);
+        ch.valid.reserve(groups * 4 + 64, 0);
+        constexpr uint64_t kPiece = 64u << 10;  // bytes of text per task (a multiple of 32)
+        const size_t n_pieces = (size_t)((ch.bytes + kPiece - 1) / kPiece);
+        WorkPool::instance().run(n_pieces, [&](size_t t) {
+            thread_local std::vector<uint8_t> stage_seq, stage_qual;
+            const uint64_t a = (uint64_t)t * kPiece, b = std::min(ch.bytes, a + kPiece);
+            stage_seq.resize(kPiece + 64);
+            if (with_qual_) stage_qual.resize(kPiece + 64);
+            gather(ch, a, b, stage_seq.data(), with_qual_ ? stage_qual.data() : nullptr);
+            pack_(stage_seq.data(), with_qual_ ? stage_qual.data() : nullptr, min_quality_, b - a,
+                  (uint64_t *)ch.codes.p + a / 32, (uint32_t *)ch.valid.p + a / 32);
+        });
+    }
+
+    // ---- exact -----------------------------------------------------------------------------------------------
+    // One batch at most (the bulk path takes over again at the next batch start if the stream is plain there).
+    bool fill_exact(Chunk<Alloc> &ch, unsigned max_reads, uint64_t max_bytes)
+    {
+        max_reads_ = max_reads;
+        max_bytes_ = max_bytes;
+        if (batch_got_ == 0) ch.batch_start.push_back(0);
+        bool more = true;
+        while (ch.n < max_reads) {
+            const Rec a = s1_.peek();
+            if (a.status < 0) {
+                s1_.consume();
+                if (!end_batch()) more = false;
+                break;
+            }
+            const std::shared_ptr<Block> ba = s1_.block();
+            Rec b;
+            std::shared_ptr<Block> bb;
+            if (s2_) {
+                b = s2_->peek();
+                if (b.status < 0) {  // mate 1 is dropped (FastqSplitter.hpp:61)
+                    s1_.consume();
+                    s2_->consume();
+                    if (!end_batch()) more = false;
+                    break;
+                }
+                bb = s2_->block();
+            }
+            const uint32_t l1 = clen(a.seq, a.seq_len, ba->has_nul), l2 = s2_ ? clen(b.seq, b.seq_len, bb->has_nul) : 0;
+            const uint64_t total = s2_ ? (uint64_t)l1 + 1 + l2 : l1;
+            if (total > max_bytes) {
+                error_ = "a read of " + std::to_string(total) + " bytes exceeds the chunk capacity of " + std::to_string(max_bytes) +
+                         " bytes (--chunk-reads sizes it)";
+                finished_ = true;
+                return false;
+            }
+            if (ch.bytes + total > max_bytes) break;  // chunk full: the batch goes on in the next chunk
+            hold(ch, ba);
+            if (s2_) hold(ch, bb);
+            s1_.consume();
+            if (s2_) s2_->consume();
+            append(ch, a, ba->has_nul, b, s2_ ? bb->has_nul : false);
+            if (++batch_got_ == kBatch) {
+                batch_got_ = 0;
+                break;  // a batch start: the bulk path may take over
+            }
+        }
+        if (!more) finished_ = true;
+        if (ch.n) {
+            const uint64_t groups = ch.groups();
+            ch.codes.reserve(groups * 8 + 64, 0);
+            ch.valid.reserve(groups * 4 + 64, 0);
+            pack_(ch.seq.p, with_qual_ ? ch.qual.p : nullptr, min_quality_, ch.bytes, (uint64_t *)ch.codes.p, (uint32_t *)ch.valid.p);
+        }
+        return more;
+    }
+    // A failed read ends the current batch (FastqSplitter.hpp:53,61); a batch that ends empty ends the input
+    // (the reference's worker returns, main.cpp:70).
+    bool end_batch()
+    {
+        if (batch_got_ == 0) return false;
+        batch_got_ = 0;
+        return true;
+    }
     static void hold(Chunk<Alloc> &ch, const std::shared_ptr<Block> &b)
     {
         // blocks arrive in order per stream: at most the last two entries can be this block
@@ -167,17 +394,12 @@ private:
         const uint32_t l1 = clen(a.seq, a.seq_len, nul_a), l2 = paired ? clen(b.seq, b.seq_len, nul_b) : 0;
         const size_t total = paired ? (size_t)l1 + 1 + l2 : l1;
         if (ch.n == 0) {
-            // size the staging buffers once from the first read (reads of a run have similar lengths)
-            const uint64_t guess = std::min<uint64_t>(max_bytes_ + 64, (uint64_t)(total + 8) * max_reads_ * 9 / 8 + (1u << 16));
-            ch.seq.reserve(guess, 0);
-            if (with_qual_gpu_) ch.qual.reserve(guess, 0);
-            ch.off.reserve(((size_t)max_reads_ + 2) * 4, 0);
+            ch.off.reserve(((size_t)std::min<unsigned>(max_reads_, kBatch) + 2) * 4, 0);
             ((uint32_t *)ch.off.p)[0] = 0;
-            ch.meta.reserve(max_reads_);
         }
         ch.off.reserve(((size_t)ch.n + 2) * 4, ((size_t)ch.n + 1) * 4);
         uint32_t *off = (uint32_t *)ch.off.p;
-        ch.seq.reserve(ch.bytes + total + 8, ch.bytes);
+        ch.seq.reserve(ch.bytes + total + 64, ch.bytes);
         uint8_t *d = ch.seq.p + ch.bytes;
         memcpy(d, a.seq, l1);
         if (paired) {
@@ -187,8 +409,8 @@ private:
         // qualities: mask_seq walks the QUAL string (FastqSplitter.hpp:104-108); positions it does
         // not reach are never masked -> pad with 0x7f, which is not < any mq
         const uint32_t ql1 = clen(a.qual, a.qual_len, nul_a), ql2 = paired ? clen(b.qual, b.qual_len, nul_b) : 0;
-        if (with_qual_gpu_) {
-            ch.qual.reserve(ch.bytes + total + 8, ch.bytes);
+        if (with_qual_) {
+            ch.qual.reserve(ch.bytes + total + 64, ch.bytes);
             uint8_t *q = ch.qual.p + ch.bytes;
             if (!paired) {
                 const size_t c1 = ql1 < total ? ql1 : total;
@@ -225,11 +447,16 @@ private:
         off[ch.n] = (uint32_t)ch.bytes;
     }
 
-    RecordStream s1_;
-    std::unique_ptr<RecordStream> s2_;
-    bool with_qual_gpu_;
+    RecordSource s1_;
+    std::unique_ptr<RecordSource> s2_;
+    int32_t min_quality_;
+    bool with_qual_;
+    PackFn pack_;
     unsigned max_reads_ = 0;
     uint64_t max_bytes_ = 0;
+    unsigned batch_got_ = 0;  // reads of the running batch so far
+    bool finished_ = false;
+    std::string error_;
 };
 
 // Buffered writer over a file descriptor.
@@ -259,6 +486,7 @@ public:
         if (len_) raw(buf_.get(), len_);
         len_ = 0;
     }
+    int fd() const { return fd_; }
 
 private:
     void raw(const void *p, size_t n)
@@ -279,14 +507,21 @@ private:
     size_t cap_, len_ = 0;
 };
 
-// ReadOutput::operator() (ReadOutput.hpp:37-50) for one chunk's associations.
+// ReadOutput::operator() (ReadOutput.hpp:37-50) for one chunk's results in the compact form.
 template <class Alloc>
 class Writer {
 public:
     Writer(int fd_ssv, int fd_out1, int fd_out2, const std::vector<std::string> &legend, bool paired)
         : legend_(legend), paired_(paired), ssv_(fd_ssv), out1_(fd_out1), out2_(fd_out2), has1_(fd_out1 >= 0),
-          has2_(fd_out2 >= 0)
+          has2_(fd_out2 >= 0 && paired)
     {
+        for (const std::string &g : legend_) legend_len_.push_back((uint32_t)strlen(g.c_str()));
+        seekable_[0] = fd_ssv >= 0 && lseek(fd_ssv, 0, SEEK_CUR) >= 0;
+        seekable_[1] = has1_ && lseek(fd_out1, 0, SEEK_CUR) >= 0;
+        seekable_[2] = has2_ && lseek(fd_out2, 0, SEEK_CUR) >= 0;
+        // only regular files are written through mappings / pwrite (a FIFO or a tty is not seekable; /dev/null is,
+        // but cannot be mapped - the fallbacks below cover it)
+        if (const char *ev = getenv("SHK_OUT")) out_mode_ = !strcmp(ev, "pwrite") ? 1 : (!strcmp(ev, "write") ? 2 : 0);
     }
     void flush()
     {
@@ -296,54 +531,204 @@ public:
     }
     void write(const Chunk<Alloc> &ch)
     {
-        const uint32_t *off = (const uint32_t *)ch.off.p;
-        size_t next_batch = 0;
-        const char *previd = "";  // `string previd = ""` per ReadOutput call = per batch
-        uint32_t prevlen = 0;
-        for (const AssocPair &as : ch.assoc) {
-            const uint32_t r = as.read_idx, g = as.gene_idx;
-            while (next_batch < ch.batch_start.size() && ch.batch_start[next_batch] <= r) {
-                previd = "";
-                prevlen = 0;
-                ++next_batch;
-            }
-            const ReadMeta &m = ch.meta[r];
-            ssv_.put(m.name1, m.nlen1);
-            ssv_.putc(' ');
-            if (g < legend_.size()) ssv_.put(legend_[g].data(), strlen(legend_[g].c_str()));
-            ssv_.putc('\n');
-            if (prevlen != m.nlen1 || memcmp(previd, m.name1, prevlen) != 0) {
-                const char *s = (const char *)ch.seq.p + off[r];
-                if (has1_) {
-                    out1_.putc('@');
-                    out1_.put(m.name1, m.nlen1);
-                    out1_.putc('\n');
-                    out1_.put(s, m.len1);
-                    out1_.put("\n+\n", 3);
-                    out1_.put(m.qual1, m.qlen1);
-                    out1_.putc('\n');
+        if (ch.n == 0) return;
+        // ranges of reads, formatted in parallel into private buffers
+        const size_t n_ranges = std::min<size_t>((size_t)WorkPool::instance().size() * 4, ((size_t)ch.n + 8191) / 8192);
+        const size_t per = ((size_t)ch.n + n_ranges - 1) / n_ranges;
+        if (bufs_.size() < n_ranges) bufs_.resize(n_ranges);
+        WorkPool::instance().run(n_ranges, [&](size_t t) {
+            const uint32_t a = (uint32_t)(t * per), b = (uint32_t)std::min<size_t>(ch.n, (t + 1) * per);
+            format(ch, a, b, bufs_[t]);
+        });
+        // out: in parallel at the offsets the sizes give when the descriptor is a seekable file - memcpy into a
+        // shared mapping of the grown file (page faults of different threads proceed in parallel; pwrite to one
+        // file serialises on the inode lock), or pwrite (SHK_OUT=pwrite) - else in order
+        OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
+        for (int f = 0; f < 3; ++f) {
+            if (f == 1 && !has1_) continue;
+            if (f == 2 && !has2_) continue;
+            OutBuf &ob = *outs[f];
+            size_t total = 0;
+            for (size_t t = 0; t < n_ranges; ++t) total += bufs_[t].s[f].size();
+            if (!total) continue;
+            bool done = false;
+            if (seekable_[f] && n_ranges > 1 && total >= (1u << 20)) {
+                ob.flush();
+                const off_t base = lseek(ob.fd(), 0, SEEK_CUR);
+                std::vector<off_t> at(n_ranges + 1, base);
+                for (size_t t = 0; t < n_ranges; ++t) at[t + 1] = at[t] + (off_t)bufs_[t].s[f].size();
+                if (out_mode_ == 0 && base >= 0) {
+                    const off_t page = (off_t)sysconf(_SC_PAGESIZE), m0 = base / page * page;
+                    char *m = nullptr;
+                    if (ftruncate(ob.fd(), at[n_ranges]) == 0) {
+                        void *mm = mmap(nullptr, (size_t)(at[n_ranges] - m0), PROT_READ | PROT_WRITE, MAP_SHARED, ob.fd(), m0);
+                        if (mm != MAP_FAILED) m = (char *)mm;
+                    }
+                    if (m) {
+                        WorkPool::instance().run(n_ranges, [&](size_t t) {
+                            const std::vector<char> &v = bufs_[t].s[f];
+                            if (!v.empty()) memcpy(m + (at[t] - m0), v.data(), v.size());
+                        });
+                        munmap(m, (size_t)(at[n_ranges] - m0));
+                        lseek(ob.fd(), at[n_ranges], SEEK_SET);
+                        done = true;
+                    }
                 }
-                if (has2_ && paired_) {
-                    const uint32_t l2 = off[r + 1] - off[r] - m.len1 - 1;
-                    out2_.putc('@');
-                    out2_.put(m.name2, m.nlen2);
-                    out2_.putc('\n');
-                    out2_.put(s + m.len1 + 1, l2);
-                    out2_.put("\n+\n", 3);
-                    out2_.put(m.qual2, m.qlen2);
-                    out2_.putc('\n');
+                if (!done && out_mode_ <= 1 && base >= 0) {
+                    WorkPool::instance().run(n_ranges, [&](size_t t) {
+                        const std::vector<char> &v = bufs_[t].s[f];
+                        size_t w_done = 0;
+                        while (w_done < v.size()) {
+                            const ssize_t w = pwrite(ob.fd(), v.data() + w_done, v.size() - w_done, at[t] + (off_t)w_done);
+                            if (w <= 0) {
+                                if (w < 0 && errno == EINTR) continue;
+                                return;  // like the reference, output errors are not reported
+                            }
+                            w_done += (size_t)w;
+                        }
+                    });
+                    lseek(ob.fd(), at[n_ranges], SEEK_SET);
+                    done = true;
                 }
             }
-            previd = m.name1;
-            prevlen = m.nlen1;
+            if (!done)
+                for (size_t t = 0; t < n_ranges; ++t) ob.put(bufs_[t].s[f].data(), bufs_[t].s[f].size());
         }
+        // the name ReadOutput's `previd` holds at the end of this chunk, for the first read of the next one
+        update_carry(ch);
     }
 
 private:
+    struct RangeBufs {
+        std::vector<char> s[3];
+    };
+    struct Fields {
+        const char *name1, *seq1, *qual1, *name2, *seq2, *qual2;
+        uint32_t nlen1, slen1, qlen1, nlen2, slen2, qlen2;
+    };
+    static Fields fields(const Chunk<Alloc> &ch, uint32_t r, bool paired)
+    {
+        Fields f{};
+        if (ch.bulk) {
+            const Rec &x = *ch.r1[r];
+            f.name1 = x.name, f.nlen1 = x.name_len, f.seq1 = x.seq, f.slen1 = x.seq_len, f.qual1 = x.qual, f.qlen1 = x.qual_len;
+            if (paired) {
+                const Rec &y = *ch.r2[r];
+                f.name2 = y.name, f.nlen2 = y.name_len, f.seq2 = y.seq, f.slen2 = y.seq_len, f.qual2 = y.qual, f.qlen2 = y.qual_len;
+            }
+        } else {
+            const ReadMeta &m = ch.meta[r];
+            const uint32_t *off = ch.offsets();
+            const char *s = (const char *)ch.seq.p + off[r];
+            f.name1 = m.name1, f.nlen1 = m.nlen1, f.seq1 = s, f.slen1 = m.len1, f.qual1 = m.qual1, f.qlen1 = m.qlen1;
+            if (paired) {
+                f.name2 = m.name2, f.nlen2 = m.nlen2, f.seq2 = s + m.len1 + 1, f.slen2 = off[r + 1] - off[r] - m.len1 - 1;
+                f.qual2 = m.qual2, f.qlen2 = m.qlen2;
+            }
+        }
+        return f;
+    }
+    static void put(std::vector<char> &v, const void *p, size_t n)
+    {
+        const size_t at = v.size();
+        v.resize(at + n);
+        memcpy(v.data() + at, p, n);
+    }
+    // start of the batch that read r belongs to, or -1 when that batch began in an earlier chunk
+    static int64_t batch_begin(const Chunk<Alloc> &ch, uint32_t r)
+    {
+        auto it = std::upper_bound(ch.batch_start.begin(), ch.batch_start.end(), r);
+        return it == ch.batch_start.begin() ? -1 : (int64_t) * (it - 1);
+    }
+    void format(const Chunk<Alloc> &ch, uint32_t a, uint32_t b, RangeBufs &out) const
+    {
+        for (auto &v : out.s) v.clear();
+        // ReadOutput's previd (ReadOutput.hpp:41,44-48) entering this range: the name of the previous kept read of
+        // the same batch - earlier in this chunk, or carried over from the previous chunk
+        const char *previd = "";  // `string previd = ""`: an empty name at the start of a batch equals it
+        uint32_t prevlen = 0;
+        {
+            const int64_t bb = batch_begin(ch, a);
+            int64_t i = (int64_t)a - 1;
+            for (; i >= 0 && i >= bb; --i)
+                if (ch.gene16[(size_t)i] != kGeneNone) break;
+            if (i >= 0 && i >= bb) {
+                const Fields f = fields(ch, (uint32_t)i, paired_);
+                previd = f.name1, prevlen = f.nlen1;
+            } else if (bb < 0 && carry_valid_) {
+                previd = carry_.data(), prevlen = (uint32_t)carry_.size();
+            }
+        }
+        size_t next_batch = (size_t)(std::upper_bound(ch.batch_start.begin(), ch.batch_start.end(), a) - ch.batch_start.begin());
+        auto m_it = std::lower_bound(ch.multi.begin(), ch.multi.end(), a,
+                                     [](const AssocPair &p, uint32_t r) { return p.read_idx < r; });
+        for (uint32_t r = a; r < b; ++r) {
+            if (next_batch < ch.batch_start.size() && ch.batch_start[next_batch] == r) {
+                previd = "", prevlen = 0;  // `string previd = ""` per ReadOutput call = per batch
+                ++next_batch;
+            }
+            const uint32_t g16 = ch.gene16[r];
+            if (g16 == kGeneNone) continue;
+            const Fields f = fields(ch, r, paired_);
+            auto line = [&](uint32_t g) {
+                put(out.s[0], f.name1, f.nlen1);
+                out.s[0].push_back(' ');
+                if (g < legend_.size()) put(out.s[0], legend_[g].data(), legend_len_[g]);
+                out.s[0].push_back('\n');
+            };
+            if (g16 != kGeneMulti) {
+                line(g16);
+            } else {
+                for (; m_it != ch.multi.end() && m_it->read_idx == r; ++m_it) line(m_it->gene_idx);
+            }
+            // FASTQ once per read unless its name equals the previous printed id (ReadOutput.hpp:44-48)
+            const bool same = prevlen == f.nlen1 && memcmp(previd, f.name1, prevlen) == 0;
+            if (!same) {
+                if (has1_) record(out.s[1], f.name1, f.nlen1, f.seq1, f.slen1, f.qual1, f.qlen1);
+                if (has2_) record(out.s[2], f.name2, f.nlen2, f.seq2, f.slen2, f.qual2, f.qlen2);
+            }
+            previd = f.name1, prevlen = f.nlen1;
+        }
+    }
+    static void record(std::vector<char> &v, const char *name, uint32_t nlen, const char *seq, uint32_t slen, const char *qual,
+                       uint32_t qlen)
+    {
+        const size_t at = v.size();
+        v.resize(at + 1 + nlen + 1 + slen + 3 + qlen + 1);
+        char *d = v.data() + at;
+        *d++ = '@';
+        memcpy(d, name, nlen), d += nlen;
+        *d++ = '\n';
+        memcpy(d, seq, slen), d += slen;
+        memcpy(d, "\n+\n", 3), d += 3;
+        memcpy(d, qual, qlen), d += qlen;
+        *d = '\n';
+    }
+    void update_carry(const Chunk<Alloc> &ch)
+    {
+        const int64_t bb = batch_begin(ch, ch.n - 1);  // the batch that is running at the end of the chunk
+        int64_t i = (int64_t)ch.n - 1;
+        for (; i >= 0 && i >= bb; --i)
+            if (ch.gene16[(size_t)i] != kGeneNone) break;
+        if (i >= 0 && i >= bb) {
+            const Fields f = fields(ch, (uint32_t)i, paired_);
+            carry_.assign(f.name1, f.nlen1);
+            carry_valid_ = true;
+        } else if (bb >= 0) {
+            carry_valid_ = false;  // a batch began in this chunk and has printed nothing yet
+        }  // else: the batch came from an earlier chunk and printed nothing here - the carry stands
+    }
+
     const std::vector<std::string> &legend_;
+    std::vector<uint32_t> legend_len_;
     bool paired_;
     OutBuf ssv_, out1_, out2_;
     bool has1_, has2_;
+    bool seekable_[3] = {false, false, false};
+    int out_mode_ = 0;  // 0 mapping (then pwrite, then write as fallbacks), 1 pwrite, 2 write
+    std::vector<RangeBufs> bufs_;
+    std::string carry_;
+    bool carry_valid_ = false;
 };
 
 }  // namespace shkhost

@@ -2,18 +2,21 @@
 // C ABI of libshark_b200.so.  Same options (argument_parser.hpp:29-174), same stdout ssv
 // (ReadOutput.hpp:43), same filtered FASTQ files (ReadOutput.hpp:44-47), same stderr stage
 // stamps.  The host does what the north star leaves on the host: FASTA/FASTQ parsing
-// (fastx.hpp), batching into pinned SoA chunks (FastaSplitter.hpp / FastqSplitter.hpp) and
-// output (ReadOutput.hpp); everything between goes through shk_index_build / shk_reads_submit /
+// (ingest.hpp, fastpipe.hpp), batching into packed chunks (FastaSplitter.hpp / FastqSplitter.hpp) and
+// output (ReadOutput.hpp); everything between goes through shk_index_build / shk_reads_submit_packed /
 // shk_reads_collect.  Extensions (not in the reference): --gpus N, --chunk-reads N, --sharded-build
 // (with --gpus N: every GPU indexes one gene shard, filters OR-merged over NVLink, instead of build +
 // replicate), --save-index FILE / --load-index FILE (the reference rebuilds its index on every run;
 // the gene names still come from -r).
 //
-// Pipeline (pipeline.hpp, ingest.hpp): one scanner thread per input file turns 8 MiB blocks into
-// record outcomes without copying; a batcher thread packs whole 50 000-read batches into pinned
-// chunk buffers; the main thread submits chunk i+1 to a free slot before it collects chunk i
-// (double buffering per GPU, chunks round-robin over GPUs); a writer thread prints results in
-// chunk order, which reproduces the reference's `-t 1` output order.
+// Pipeline (pipeline.hpp, fastpipe.hpp, ingest.hpp): plain input files are memory-mapped and scanned by
+// the host pool in parallel (compressed ones by a streaming scanner per file); a batcher thread turns runs
+// of records into chunks in the packed form of shk_reads_submit_packed (2-bit code + validity bit per base,
+// the pool packs 64 KiB pieces straight from the mapped input); the main thread submits chunk i+1 to a free
+// slot before it collects chunk i (double buffering per GPU, chunks round-robin over GPUs); a writer thread
+// formats the compact results in parallel and writes them in chunk order, which reproduces the reference's
+// `-t 1` output order.  Scanning and packing start with the process, concurrently with CUDA start-up and
+// the index build.
 #include <fcntl.h>
 #include <getopt.h>
 #include <unistd.h>
@@ -35,7 +38,6 @@
 #include <vector>
 
 #include "../../../include/shark_b200.h"
-#include "fastx.hpp"
 #include "pipeline.hpp"
 
 namespace {
@@ -71,98 +73,105 @@ struct Options {
     bool single = false, verbose = false;
     int n_threads = 1;
     int gpus = 1;                   // extension
-    unsigned chunk_reads = 1000000; // extension; rounded to a multiple of the 50 000-read batch
+    unsigned chunk_reads = 1000000; // extension
     bool sharded_build = false;     // extension
     std::string save_index, load_index;  // extensions
 };
 
-// argument_parser.hpp:84-174, option by option (istringstream extraction included, so that e.g.
-// "-k 17abc" parses like the reference does).
+[[noreturn]] void usage_error(const char *msg, bool with_usage)
+{
+    if (with_usage) std::cerr << USAGE_MESSAGE;
+    std::cerr << msg << std::endl << "aborting..." << std::endl;
+    exit(EXIT_FAILURE);
+}
+
+// The reference's options (argument_parser.hpp:65-82) and ours, one row each: getopt value, long name, whether
+// it takes an argument, and what it does with the argument (an istringstream, so that e.g. "-k 17abc" parses
+// like the reference does; validation and messages as in argument_parser.hpp:84-166).
+struct OptionRow {
+    int key;
+    const char *long_name;
+    bool has_arg;
+    void (*apply)(Options &, std::istringstream &);
+};
+const OptionRow kOptions[] = {
+    {'r', "reference", true, [](Options &o, std::istringstream &a) { a >> o.fasta_path; }},
+    {'t', "threads", true,
+     [](Options &o, std::istringstream &a) {
+         a >> o.n_threads;
+         if (o.n_threads <= 0) {
+             std::cerr << "USAGE_MESSAGE";  // sic: argument_parser.hpp:94
+             usage_error("shark: at least 1 thread is required.", false);
+         }
+     }},
+    {'1', "sample1", true, [](Options &o, std::istringstream &a) { a >> o.sample1_path; }},
+    {'2', "sample2", true,
+     [](Options &o, std::istringstream &a) {
+         a >> o.sample2_path;
+         o.paired = true;
+     }},
+    {'o', "out1", true, [](Options &o, std::istringstream &a) { a >> o.out1_path; }},
+    {'p', "out2", true, [](Options &o, std::istringstream &a) { a >> o.out2_path; }},
+    {'k', "kmer-size", true,
+     [](Options &o, std::istringstream &a) {
+         a >> o.k;
+         if (o.k == 0 || o.k > 31) usage_error("shark: k must be in the range [1, 31].", true);
+     }},
+    {'c', "confidence", true,
+     [](Options &o, std::istringstream &a) {
+         a >> o.c;
+         if (o.c < 0 || o.c > 1) usage_error("shark: c must be in the range [0, 1].", false);
+     }},
+    {'b', "bf-size", true,
+     [](Options &o, std::istringstream &a) {
+         a >> o.bf_size;
+         o.bf_size = o.bf_size * (1ull << 33);  // "GB": argument_parser.hpp:130-134
+     }},
+    {'q', "min-base-quality", true,
+     [](Options &o, std::istringstream &a) {
+         int mq = 0;
+         a >> mq;
+         if (mq < 0) usage_error("shark: q must be a positive value.", true);
+         o.min_quality = static_cast<char>(mq);
+     }},
+    {'s', "single", false, [](Options &o, std::istringstream &) { o.single = true; }},
+    {'v', "verbose", false, [](Options &o, std::istringstream &) { o.verbose = true; }},
+    {'h', "help", false,
+     [](Options &, std::istringstream &) {
+         std::cerr << USAGE_MESSAGE;
+         exit(EXIT_SUCCESS);
+     }},
+    {1000, "gpus", true, [](Options &o, std::istringstream &a) { a >> o.gpus; }},
+    {1001, "chunk-reads", true, [](Options &o, std::istringstream &a) { a >> o.chunk_reads; }},
+    {1002, "sharded-build", false, [](Options &o, std::istringstream &) { o.sharded_build = true; }},
+    {1003, "save-index", true, [](Options &o, std::istringstream &a) { a >> o.save_index; }},
+    {1004, "load-index", true, [](Options &o, std::istringstream &a) { a >> o.load_index; }},
+};
+
 Options parse_arguments(int argc, char **argv)
 {
     Options opt;
-    static const char *shortopts = "t:r:1:2:o:p:k:c:b:q:svh";
-    static const struct option longopts[] = {{"reference", required_argument, nullptr, 'r'},
-                                             {"threads", required_argument, nullptr, 't'},
-                                             {"sample1", required_argument, nullptr, '1'},
-                                             {"sample2", required_argument, nullptr, '2'},
-                                             {"out1", required_argument, nullptr, 'o'},
-                                             {"out2", required_argument, nullptr, 'p'},
-                                             {"kmer-size", required_argument, nullptr, 'k'},
-                                             {"confidence", required_argument, nullptr, 'c'},
-                                             {"bf-size", required_argument, nullptr, 'b'},
-                                             {"min-base-quality", required_argument, nullptr, 'q'},
-                                             {"single", no_argument, nullptr, 's'},
-                                             {"verbose", no_argument, nullptr, 'v'},
-                                             {"help", no_argument, nullptr, 'h'},
-                                             {"gpus", required_argument, nullptr, 1000},
-                                             {"chunk-reads", required_argument, nullptr, 1001},
-                                             {"sharded-build", no_argument, nullptr, 1002},
-                                             {"save-index", required_argument, nullptr, 1003},
-                                             {"load-index", required_argument, nullptr, 1004},
-                                             {nullptr, 0, nullptr, 0}};
-    for (int ch; (ch = getopt_long(argc, argv, shortopts, longopts, nullptr)) != -1;) {
-        std::istringstream arg(optarg != nullptr ? optarg : "");
-        switch (ch) {
-        case 'r': arg >> opt.fasta_path; break;
-        case 't':
-            arg >> opt.n_threads;
-            if (opt.n_threads <= 0) {
-                std::cerr << "USAGE_MESSAGE";  // sic: argument_parser.hpp:94
-                std::cerr << "shark: at least 1 thread is required." << std::endl << "aborting..." << std::endl;
-                exit(EXIT_FAILURE);
-            }
-            break;
-        case '1': arg >> opt.sample1_path; break;
-        case '2':
-            arg >> opt.sample2_path;
-            opt.paired = true;
-            break;
-        case 'o': arg >> opt.out1_path; break;
-        case 'p': arg >> opt.out2_path; break;
-        case 'k':
-            arg >> opt.k;
-            if (opt.k == 0 || opt.k > 31) {
-                std::cerr << USAGE_MESSAGE;
-                std::cerr << "shark: k must be in the range [1, 31]." << std::endl << "aborting..." << std::endl;
-                exit(EXIT_FAILURE);
-            }
-            break;
-        case 'c':
-            arg >> opt.c;
-            if (opt.c < 0 || opt.c > 1) {
-                std::cerr << "shark: c must be in the range [0, 1]." << std::endl << "aborting..." << std::endl;
-                exit(EXIT_FAILURE);
-            }
-            break;
-        case 'b':
-            arg >> opt.bf_size;
-            opt.bf_size = opt.bf_size * (1ull << 33);  // "GB": argument_parser.hpp:130-134
-            break;
-        case 'q': {
-            int mq = 0;
-            arg >> mq;
-            if (mq < 0) {
-                std::cerr << USAGE_MESSAGE;
-                std::cerr << "shark: q must be a positive value." << std::endl << "aborting..." << std::endl;
-                exit(EXIT_FAILURE);
-            }
-            opt.min_quality = static_cast<char>(mq);
-            break;
+    std::string shortopts;
+    std::vector<struct option> longopts;
+    for (const OptionRow &row : kOptions) {
+        if (row.key < 256) {
+            shortopts += (char)row.key;
+            if (row.has_arg) shortopts += ':';
         }
-        case 's': opt.single = true; break;
-        case 'v': opt.verbose = true; break;
-        case 'h': std::cerr << USAGE_MESSAGE; exit(EXIT_SUCCESS);
-        case 1000: arg >> opt.gpus; break;
-        case 1001: arg >> opt.chunk_reads; break;
-        case 1002: opt.sharded_build = true; break;
-        case 1003: arg >> opt.save_index; break;
-        case 1004: arg >> opt.load_index; break;
-        default:
+        longopts.push_back({row.long_name, row.has_arg ? required_argument : no_argument, nullptr, row.key});
+    }
+    longopts.push_back({nullptr, 0, nullptr, 0});
+    for (int ch; (ch = getopt_long(argc, argv, shortopts.c_str(), longopts.data(), nullptr)) != -1;) {
+        std::istringstream arg(optarg != nullptr ? optarg : "");
+        const OptionRow *row = nullptr;
+        for (const OptionRow &r : kOptions)
+            if (r.key == ch) row = &r;
+        if (!row) {
             std::cerr << "shark : unknown argument" << std::endl;
             std::cerr << "\n" << USAGE_MESSAGE;
             exit(EXIT_FAILURE);
         }
+        row->apply(opt, arg);
     }
     if (opt.fasta_path.empty() || opt.sample1_path.empty()) {
         std::cerr << "shark : missing required files" << std::endl;
@@ -202,11 +211,10 @@ void tstamp(const char *what)
 
 using shkhost::kBatch;
 
-// Staging memory of the chunks.  The files are parsed at ~2 GB/s per input file, far below what
-// even a pageable host-to-device copy sustains, while CUDA start-up takes 1-2 s on these boxes: the
-// chunks therefore live in ordinary memory, so that scanning and packing run from the first
-// millisecond, concurrently with the creation of the device context and the index build
-// (SHK_PINNED=1 switches to the library's pinned allocator; bench.py measures that path).
+// Staging memory of the chunks (offsets and packed reads: 0.375 bytes per base).  CUDA start-up takes about a
+// second on these boxes: the chunks live in ordinary memory, so that scanning and packing run from the first
+// millisecond, concurrently with the creation of the device context and the index build (SHK_PINNED=1 switches
+// to the library's pinned allocator).
 struct PinnedAlloc {
     static bool pinned()
     {
@@ -233,6 +241,12 @@ using Chunk = shkhost::Chunk<PinnedAlloc>;
 using Batcher = shkhost::Batcher<PinnedAlloc>;
 using Writer = shkhost::Writer<PinnedAlloc>;
 static_assert(sizeof(shkhost::AssocPair) == sizeof(shk_assoc), "AssocPair mirrors shk_assoc");
+static_assert(shkhost::kGeneNone == SHK_GENE_NONE && shkhost::kGeneMulti == SHK_GENE_MULTI, "compact result markers");
+
+void pack_piece(const uint8_t *seq, const uint8_t *qual, int32_t min_quality, uint64_t n, uint64_t *codes, uint32_t *valid)
+{
+    shk_host_pack(seq, qual, min_quality, n, codes, valid, 0);  // the caller is one of the pool's threads already
+}
 
 // Simple blocking queue for the hand-offs between the pipeline threads.
 template <class T>
@@ -281,15 +295,23 @@ int main(int argc, char *argv[])
         std::cerr << "Minimum base quality: " << static_cast<int>(opt.min_quality) << std::endl;
         std::cerr << std::endl;
     }
+    if (opt.n_threads > 1) shkhost::set_ingest_threads(opt.n_threads);  // -t: inflate threads for blocked-gzip samples
+    // the driver initialises every visible device: name only the ones this run uses (a second per GPU saved on
+    // an 8-GPU box); a CUDA_VISIBLE_DEVICES set by the user stands
+    {
+        std::string vis;
+        for (int g = 0; g < opt.gpus; ++g) vis += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
+    }
 
-    // The sample files are scanned ahead by their own threads from the start (they run into a
-    // bounded queue while the index is being built).
-    Batcher batcher(opt.sample1_path.c_str(), opt.paired ? opt.sample2_path.c_str() : nullptr, opt.min_quality != 0);
+    // The sample files are scanned ahead from the start (into a bounded queue while the index is being built).
+    const int32_t min_quality = (int32_t)(unsigned char)opt.min_quality;
+    Batcher batcher(opt.sample1_path.c_str(), opt.paired ? opt.sample2_path.c_str() : nullptr, min_quality, pack_piece);
     if (batcher.files_ok()) batcher.start();
     else die("cannot open sample file(s)");
-    const unsigned chunk_reads = std::max(kBatch, opt.chunk_reads / kBatch * kBatch);
+    const unsigned chunk_reads = std::max(1000u, opt.chunk_reads);
     // slot buffers are sized by this; a chunk is closed early when its text would not fit
-    const uint64_t max_chunk_bytes = std::min<uint64_t>(0xF0000000ull, std::max<uint64_t>((uint64_t)chunk_reads * 640, 256ull << 20));
+    const uint64_t max_chunk_bytes = std::min<uint64_t>(0xF0000000ull, std::max<uint64_t>((uint64_t)chunk_reads * 640, 64ull << 20));
     const size_t n_bufs = (size_t)opt.gpus * 2 + 3;
     std::vector<std::unique_ptr<Chunk>> pool;
     Channel<Chunk *> free_q, ready_q, write_q;
@@ -297,11 +319,12 @@ int main(int argc, char *argv[])
         pool.emplace_back(new Chunk);
         free_q.push(pool.back().get());
     }
-    std::thread parser([&] {  // packs chunks while the device context and the index are being set up
+    std::thread parser([&] {  // builds chunks while the device context and the index are being set up
         uint64_t idx = 0;
         for (;;) {
             Chunk *ch = free_q.pop();
             const bool more = batcher.fill(*ch, chunk_reads, max_chunk_bytes);
+            if (batcher.error()) die(batcher.error());
             ch->index = idx++;
             ch->last = !more;
             ready_q.push(ch);
@@ -315,18 +338,21 @@ int main(int argc, char *argv[])
     std::vector<uint8_t> ref_bases;
     std::vector<uint64_t> rec_off{0};
     {
-        shkhost::FastxReader ref(opt.fasta_path.c_str());
+        shkhost::RecordSource ref(opt.fasta_path.c_str());
         if (!ref.ok()) die("cannot open reference " + opt.fasta_path);
-        std::string name, seq, qual;
-        while (ref.read(name, seq, qual) >= 0) {
-            legend_ID.emplace_back(name.c_str());
-            const size_t l = strlen(seq.c_str());  // `seq->seq.s` as a C string (KmerBuilder input)
-            ref_bases.insert(ref_bases.end(), seq.data(), seq.data() + l);
+        ref.start();
+        for (;;) {
+            const shkhost::Rec r = ref.peek();
+            if (r.status < 0) break;  // `while ((seq_len = kseq_read(seq)) >= 0)`, FastaSplitter.hpp:46
+            // `seq->name.s` / `seq->seq.s` as C strings (FastaSplitter.hpp:48-49)
+            const void *zn = memchr(r.name, 0, r.name_len), *zs = memchr(r.seq, 0, r.seq_len);
+            legend_ID.emplace_back(r.name, zn ? (size_t)((const char *)zn - r.name) : r.name_len);
+            const size_t l = zs ? (size_t)((const char *)zs - r.seq) : r.seq_len;
+            ref_bases.insert(ref_bases.end(), r.seq, r.seq + l);
             rec_off.push_back(ref_bases.size());
+            ref.consume();
         }
     }
-
-    if (opt.n_threads > 1) shkhost::set_ingest_threads(opt.n_threads);  // -t: inflate threads for blocked-gzip samples
     tstamp("reference parsed");
     std::vector<shk_ctx *> ctxs((size_t)opt.gpus, nullptr);
     for (int g = 0; g < opt.gpus; ++g) {
@@ -335,12 +361,13 @@ int main(int argc, char *argv[])
         p.k = opt.k;
         p.c = opt.c;
         p.bf_bits = opt.bf_size;
-        p.min_quality = (int32_t)(unsigned char)opt.min_quality;
+        p.min_quality = min_quality;
         p.single = opt.single ? 1 : 0;
         p.device = g;
         p.n_slots = 2;
         p.max_reads_per_chunk = chunk_reads;
         p.max_bytes_per_chunk = max_chunk_bytes;
+        p.flags = SHK_F_COMPACT_RESULTS;
         if (shk_create(&p, &ctxs[g]) != SHK_OK) die(std::string("shk_create: ") + shk_last_error(nullptr));
     }
     tstamp("contexts created");
@@ -395,15 +422,16 @@ int main(int argc, char *argv[])
     };
     std::deque<InFlight> inflight;
     const size_t max_inflight = (size_t)opt.gpus * 2;
-    uint64_t submitted = 0;
+    uint64_t submitted = 0, total_reads = 0;
     auto drain_one = [&] {
         InFlight f = inflight.front();
         inflight.pop_front();
         shk_chunk_result res;
         SHK_TRY(ctxs[f.gpu], shk_reads_collect(ctxs[f.gpu], f.slot, &res));
-        // the slot's result buffers are reused by its next submit: take the list with the chunk
-        const shkhost::AssocPair *as = reinterpret_cast<const shkhost::AssocPair *>(res.assoc);
-        f.ch->assoc.assign(as, as + res.n_assoc);
+        // the slot's result buffers are reused by its next submit: the compact results travel with the chunk
+        f.ch->gene16.assign(res.gene16, res.gene16 + res.n_reads);
+        const shkhost::AssocPair *mu = reinterpret_cast<const shkhost::AssocPair *>(res.multi);
+        f.ch->multi.assign(mu, mu + res.n_multi);
         write_q.push(f.ch);
     };
     for (bool done = false; !done;) {
@@ -418,10 +446,11 @@ int main(int argc, char *argv[])
         if (inflight.size() == max_inflight) drain_one();
         const int gpu = (int)(submitted % (uint64_t)opt.gpus);
         const uint32_t slot = (uint32_t)((submitted / (uint64_t)opt.gpus) % 2);
-        SHK_TRY(ctxs[gpu], shk_reads_submit(ctxs[gpu], slot, ch->seq.p, opt.min_quality != 0 ? ch->qual.p : nullptr,
-                                            (const uint32_t *)ch->off.p, ch->n));
+        SHK_TRY(ctxs[gpu], shk_reads_submit_packed(ctxs[gpu], slot, (const uint64_t *)ch->codes.p, (const uint32_t *)ch->valid.p,
+                                                   ch->offsets(), ch->n));
         inflight.push_back({ch, gpu, slot});
         ++submitted;
+        total_reads += ch->n;
     }
     while (!inflight.empty()) drain_one();
     tstamp("last chunk collected");
@@ -431,9 +460,17 @@ int main(int argc, char *argv[])
     if (fd1 >= 0) close(fd1);
     if (fd2 >= 0) close(fd2);
     tstamp("output written");
-    pool.clear();  // pinned staging goes back before the contexts do
-    tstamp("staging freed");
+    if (g_timing) fprintf(stderr, "[shark-b200/timing] reads %llu in %llu chunks, %d host threads\n", (unsigned long long)total_reads,
+                          (unsigned long long)submitted, shkhost::host_threads());
     pelapsed("Sample completed");
+    fflush(nullptr);
+    // the process ends here: the context, the mappings and the staging memory go with it (tearing them down one
+    // by one costs tens of milliseconds a user would wait for)
+    if (!getenv("SHK_CLEAN_EXIT")) {
+        pelapsed("Association done");
+        _exit(0);
+    }
+    pool.clear();
     for (auto *c : ctxs) shk_destroy(c);
     pelapsed("Association done");
     return 0;

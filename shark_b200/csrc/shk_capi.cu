@@ -181,8 +181,8 @@ static int alloc_slot(shk_ctx *ctx, Slot &s)
     SHK_CUDA(ctx, cudaEventCreate(&s.ev_ka));
     SHK_CUDA(ctx, cudaEventCreate(&s.ev_k1));
     SHK_CUDA(ctx, cudaEventCreate(&s.ev_done));
-    SHK_CUDA(ctx, cudaMalloc((void **)&s.d_seq, B + 64));
-    if ((ctx->params.min_quality & 0xFF) != 0) SHK_CUDA(ctx, cudaMalloc((void **)&s.d_qual, B + 64));
+    // d_seq / d_qual (text chunks) are allocated by the first text submit: a caller that only ever submits packed
+    // chunks (the CLI) neither waits for them at start-up nor holds them
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_off, (R + 1) * 4));
     SHK_CUDA(ctx, cudaMalloc((void **)&s.d_rec, R * sizeof(uint2)));
     s.pool_cap = (uint32_t)std::max<uint64_t>(R / 2, 4096);
@@ -397,6 +397,8 @@ static int enqueue_upload(shk_ctx *ctx, Slot &s, const uint8_t *seq, const uint8
         r_split = r_split / kReadsPerTile * kReadsPerTile;
     }
     const uint64_t S = off[r_split];  // text bytes
+    if (S && !s.d_seq) SHK_CUDA(ctx, cudaMalloc((void **)&s.d_seq, ctx->max_bytes + 64));
+    if (S && s.has_qual && !s.d_qual) SHK_CUDA(ctx, cudaMalloc((void **)&s.d_qual, ctx->max_bytes + 64));
     if (S) {
         SHK_CUDA(ctx, cudaMemcpyAsync(s.d_seq, seq, S, cudaMemcpyHostToDevice, s.stream));
         if (s.has_qual) SHK_CUDA(ctx, cudaMemcpyAsync(s.d_qual, qual, S, cudaMemcpyHostToDevice, s.stream));

@@ -315,36 +315,32 @@ analyze_reads_kernel(const ReadKernelArgs a)
             const uint32_t *qualw = HAS_QUAL ? reinterpret_cast<const uint32_t *>(a.qual) + (src0 >> 2) : nullptr;
             const uint32_t n_words = (head + n + 3u) >> 2;
             uint32_t w_next = 0, q_next = 0;
-            // packed: current and prefetched (code word, validity word) of the 32-base group
-            uint32_t pg = (src0 >> 2) >> 3;
-            uint64_t cw = 0, cw_next = 0;
-            uint32_t vw = 0, vw_next = 0;
-            if (n_words) {
-                if (PACKED) {
-                    cw_next = ld_u64_hint(a.pcodes + pg, pol_first);
-                    vw_next = ld_text_word(a.pvalid + pg, pol_first);
-                } else {
-                    w_next = ld_text_word(seqw, pol_first);
-                    if (HAS_QUAL) q_next = ld_text_word(qualw, pol_first);
-                }
+            // packed: the next (up to) 8 words of this read - 8 code bytes and 8 validity nibbles - shifted down as
+            // they are used.  Every lane reloads at the same iterations (j % 8 == 0), whatever its alignment in the
+            // stream: two aligned words each, funnel-shifted to the lane's position.
+            uint64_t cw = 0;
+            uint32_t vw = 0;
+            if (n_words && !PACKED) {
+                w_next = ld_text_word(seqw, pol_first);
+                if (HAS_QUAL) q_next = ld_text_word(qualw, pol_first);
             }
             for (uint32_t j = 0; j < n_words && !tab.overflow; ++j) {
                 // per base b of the word: validity and 2-bit code (A0 C1 G2 T3)
                 uint32_t code4, x;
                 if (PACKED) {
-                    const uint32_t nib = ((src0 >> 2) + j) & 7u;
-                    if (j == 0 || nib == 0) {
-                        cw = cw_next;
-                        vw = vw_next;
-                        if (j + (8u - nib) < n_words) {  // the read goes on into the next group
-                            ++pg;
-                            cw_next = ld_u64_hint(a.pcodes + pg, pol_first);
-                            vw_next = ld_text_word(a.pvalid + pg, pol_first);
-                        }
+                    if ((j & 7u) == 0u) {
+                        const uint32_t wi = (src0 >> 2) + j;  // this 4-base word = byte wi of the code array
+                        const uint32_t gi = wi >> 3, sh = (wi & 7u) * 8u;
+                        const uint64_t c_lo = ld_u64_hint(a.pcodes + gi, pol_first), c_hi = ld_u64_hint(a.pcodes + gi + 1, pol_first);
+                        const uint32_t v_lo = ld_text_word(a.pvalid + gi, pol_first), v_hi = ld_text_word(a.pvalid + gi + 1, pol_first);
+                        cw = sh ? (c_lo >> sh) | (c_hi << (64u - sh)) : c_lo;
+                        vw = __funnelshift_r(v_lo, v_hi, sh >> 1);
                     }
-                    const uint32_t c8 = (uint32_t)(cw >> (8u * nib)) & 0xFFu;
-                    code4 = c8 ^ ((c8 >> 1) & 0x55u);       // A0 C1 T2 G3 -> A0 C1 G2 T3, base b at bits 2b
-                    x = (vw >> (4u * nib)) & 0xFu;          // bit b = base b is valid
+                    const uint32_t c8 = (uint32_t)cw & 0xFFu;
+                    cw >>= 8;
+                    code4 = c8 ^ ((c8 >> 1) & 0x55u);  // A0 C1 T2 G3 -> A0 C1 G2 T3, base b at bits 2b
+                    x = vw & 0xFu;                      // bit b = base b is valid
+                    vw >>= 4;
                 } else {
                     uint32_t w = w_next;
                     const uint32_t qw = q_next;

@@ -1,6 +1,8 @@
-"""Host ingest (shark_b200/csrc/host/ingest.hpp): the block scanner must yield exactly the kseq_read()
-outcome stream of the record-at-a-time reader (fastx.hpp, itself pinned against the reference binary
-by the CLI goldens) on well-formed and on hostile inputs, for any block size."""
+"""Host ingest (shark_b200/csrc/host/ingest.hpp, fastpipe.hpp, pipeline.hpp): the block scanner and the parallel
+scanner of mapped files must yield exactly the kseq_read() outcome stream of the record-at-a-time reader
+(tests/host_tools/fastx.hpp, itself pinned against the reference binary by the CLI goldens) on well-formed and on
+hostile inputs, for any block / segment size; the batcher and the writer must produce the packed chunks and
+the output bytes that the text-level oracle gives for the same results."""
 import gzip
 import os
 import random
@@ -11,19 +13,30 @@ import pytest
 from helpers import ROOT
 
 HOST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shark_b200", "csrc", "host")
+TOOLS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_tools")
 
 
 @pytest.fixture(scope="module")
 def tool(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("host") / "host_tools")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-pthread", os.path.join(HOST, "host_tools.cpp"), "-o", out, "-lz"])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-pthread", "-I", HOST, os.path.join(TOOLS, "host_tools.cpp"),
+                           "-o", out, "-lz"])
     return out
 
 
 def _check(tool, path, block):
     r = subprocess.run([tool, "scan-check", path, str(block)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.startswith("OK"), (path, block, r.stdout, r.stderr)
-    return int(r.stdout.split()[1])
+    n = int(r.stdout.split()[1])
+    if not path.endswith(".gz"):
+        # the same file through the parallel scanner of the mapped file: segment size = the block size (tiny
+        # segments put a guessed record start on every line), outcome by outcome and with bulk takes in between
+        for seg, bulk in ((max(block, 16), 0), (max(block, 16), 37), (1 << 22, 5)):
+            r = subprocess.run([tool, "pscan-check", path, str(seg), str(bulk)], capture_output=True, text=True, timeout=120,
+                               env=dict(os.environ, SHK_HOST_THREADS="4"))
+            assert r.returncode == 0 and r.stdout.startswith("OK"), (path, seg, bulk, r.stdout, r.stderr)
+            assert int(r.stdout.split()[1]) >= n - 2   # (the checkers stop after three end-of-file outcomes; bulk takes skip none)
+    return n
 
 
 def _rec(rng, L=None, qual_delta=0, crlf=False, comment=False, plus_text=False, wrap=0):
@@ -359,3 +372,152 @@ def test_host_pack_against_the_oracle_masking_and_base_table():
         c, v = capi.host_pack(seq, qual, q, parallel=bool(q & 1))
         assert np.array_equal(v, want_v), q
         assert np.array_equal(c, want_c), q
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batcher + writer (pipeline.hpp) against the text-level oracle: packed chunks and output bytes
+# ---------------------------------------------------------------------------------------------------------
+def _expected_pipe(path1, path2, q):
+    """What host_tools pipe-check must print: the reference's ReadOutput (ReadOutput.hpp:37-50, previd reset per
+    50 000-read batch) for the faked results `read i -> gene gA; every 7th (i % 7 == 3) dropped; i % 5 == 1 ->
+    gA and gB`, plus the joined text of all reads for the packed chunks."""
+    from oracle import shark_text as st
+    pairs, bid = st.load_sample(path1, path2)
+    seq, qual, off = st.join_reads(pairs, q > 0)
+    ssv, o1, o2 = [], [], []
+    prev, prev_batch = b"", 0
+    for i, (a, b) in enumerate(pairs):
+        if i % 7 == 3:
+            continue
+        if bid[i] != prev_batch:
+            prev, prev_batch = b"", bid[i]
+        name = st._cstr(a[0])
+        for g in ((b"gA", b"gB") if i % 5 == 1 else (b"gA",)):
+            ssv.append(name + b" " + g + b"\n")
+        if prev != name:
+            o1.append(b"@" + name + b"\n" + st._cstr(a[1]) + b"\n+\n" + st._cstr(a[2]) + b"\n")
+            if b is not None:
+                o2.append(b"@" + st._cstr(b[0]) + b"\n" + st._cstr(b[1]) + b"\n+\n" + st._cstr(b[2]) + b"\n")
+        prev = name
+    return b"".join(ssv), b"".join(o1), b"".join(o2), seq, qual, off, bid
+
+
+def _fnv(h, data):
+    for byte in data:
+        h = ((h ^ byte) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _run_pipe(tool, tmp_path, f1, f2, q, chunk, max_bytes, env_extra):
+    o1, o2 = str(tmp_path / "o1.fq"), str(tmp_path / "o2.fq")
+    for p in (o1, o2):
+        if os.path.exists(p):
+            os.unlink(p)
+    cmd = [tool, "pipe-check", f1] + ([f2] if f2 else []) + ["--qual", str(q), "--chunk", str(chunk), "--bytes", str(max_bytes)]
+    ssv_path = str(tmp_path / "o.ssv")
+    with open(ssv_path, "wb") as fo:
+        r = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE, timeout=300, env=dict(os.environ, OUT1=o1, OUT2=o2, **env_extra))
+    assert r.returncode == 0, r.stderr.decode()[-500:]
+    chunks = []
+    for ln in r.stderr.decode().splitlines():
+        if ln.startswith("CHUNK"):
+            kv = dict(x.split("=") for x in ln.split()[1:])
+            chunks.append((int(kv["n"]), int(kv["bytes"]), int(kv["bulk"]), [int(x) for x in kv["batches"].split(",") if x],
+                           int(kv["hash"], 16)))
+    return open(ssv_path, "rb").read(), open(o1, "rb").read(), (open(o2, "rb").read() if f2 else b""), chunks
+
+
+def _check_pipe(tool, tmp_path, f1, f2, q, chunk, max_bytes=10 ** 9, env_extra=None, want_bulk=None):
+    import numpy as np
+    from shark_b200 import capi
+    ssv0, a0, b0, seq, qual, off, bid = _expected_pipe(f1, f2, q)
+    ssv, a, b, chunks = _run_pipe(tool, tmp_path, f1, f2, q, chunk, max_bytes, env_extra or {})
+    assert ssv == ssv0
+    assert a == a0
+    if f2:
+        assert b == b0
+    # the chunks cover the reads in order, respect both bounds, mark the batch starts, and carry the packed text
+    r = 0
+    for n, nbytes, bulk, batches, h in chunks:
+        assert 0 < n <= chunk and nbytes <= max_bytes
+        lo, hi = int(off[r]), int(off[r + n])
+        assert nbytes == hi - lo
+        assert batches == [i for i in range(n) if r + i == 0 or bid[r + i] != bid[r + i - 1]]
+        codes, valid = capi.host_pack(seq[lo:hi], qual[lo:hi] if q else None, q)
+        o32 = (off[r:r + n + 1] - off[r]).astype(np.uint32)
+        assert h == _fnv(_fnv(_fnv(0xCBF29CE484222325, o32.tobytes()), codes.tobytes()), valid.tobytes())
+        r += n
+    assert r == len(off) - 1
+    if want_bulk is not None:
+        assert (sum(c[0] for c in chunks if c[2]) > 0) == want_bulk
+    return chunks
+
+
+def _write_fastq(path, rng, n, name_run=3, Lmin=18, Lmax=40, seed_names=0):
+    with open(path, "w") as f:
+        for i in range(n):
+            L = rng.randint(Lmin, Lmax)
+            f.write("@r%d%s\n%s\n+\n%s\n" % (seed_names + i // name_run, " x" if i % 11 == 0 else "",
+                                               "".join(rng.choice("ACGTN") for _ in range(L)),
+                                               "".join(chr(rng.randint(33, 74)) for _ in range(L))))
+
+
+@pytest.mark.parametrize("paired,q", [(False, 0), (True, 0), (True, 25), (False, 30)])
+def test_pipeline_bulk_chunks_batches_and_dedup(tool, tmp_path, paired, q):
+    """120 000 short reads whose names repeat in runs of three (ReadOutput's consecutive-name dedup, also across
+    range, chunk and batch boundaries), through chunk sizes that do and do not divide the 50 000-read batch, with a
+    byte bound that cuts chunks short, in parallel and with one thread."""
+    rng = random.Random(7 + q + paired)
+    f1, f2 = str(tmp_path / "a_1.fq"), (str(tmp_path / "a_2.fq") if paired else None)
+    _write_fastq(f1, rng, 120000)
+    if paired:
+        _write_fastq(f2, rng, 120000, name_run=2, seed_names=10 ** 6)
+    for chunk, max_bytes, env in ((1000000, 10 ** 9, {}), (30000, 10 ** 9, {"SHK_HOST_THREADS": "4"}), (50000, 10 ** 9, {"SHK_HOST_THREADS": "1"}),
+                                  (17777, 700000, {"SHK_HOST_THREADS": "3", "SHK_OUT": "pwrite"}), (40000, 10 ** 9, {"SHK_NO_BULK": "1", "SHK_OUT": "write"})):
+        chunks = _check_pipe(tool, tmp_path, f1, f2, q, chunk, max_bytes, env, want_bulk="SHK_NO_BULK" not in env)
+        assert len(chunks) >= 120000 // chunk
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_pipeline_hostile_inputs(tool, tmp_path, seed):
+    """Failed reads, NUL bytes, FASTA records, wrapped lines, truncated tails, files of different lengths: the
+    exact path takes over wherever the bulk path may not run, output and packed text stay those of the oracle."""
+    rng = random.Random(300 + seed)
+
+    def hostile(n):
+        parts = []
+        for _ in range(n):
+            u = rng.random()
+            if u < 0.80:
+                parts.append(_rec(rng, comment=rng.random() < 0.2))
+            elif u < 0.84:
+                parts.append(_rec(rng, crlf=True))
+            elif u < 0.88:
+                parts.append(_rec(rng, qual_delta=rng.choice([-2, 3])))
+            elif u < 0.91:
+                parts.append(_rec(rng, L=rng.randint(30, 90), wrap=20))
+            elif u < 0.94:
+                parts.append(">fa%d d\nACGTTGCA\nACG\n" % rng.randint(0, 9))
+            elif u < 0.97:
+                parts.append("@nul%d\nAC\x00GT\n+\nII\x00II\n" % rng.randint(0, 9))
+            else:
+                parts.append(rng.choice(["\n", "junk\n", "@\n"]))
+        return "".join(parts)
+
+    f1, f2 = str(tmp_path / "h_1.fq"), str(tmp_path / "h_2.fq")
+    d1, d2 = hostile(3000), hostile(2500 + 200 * seed)
+    if seed % 2:
+        d1 = d1[: len(d1) - rng.randint(1, 40)]
+    open(f1, "wb").write(d1.encode("latin-1"))
+    open(f2, "wb").write(d2.encode("latin-1"))
+    for q in (0, 20):
+        _check_pipe(tool, tmp_path, f1, None, q, 700, env_extra={"SHK_SCAN_SEGMENT": "4096", "SHK_HOST_THREADS": "4"})
+        _check_pipe(tool, tmp_path, f1, f2, q, 1000, env_extra={"SHK_SCAN_SEGMENT": "1000", "SHK_HOST_THREADS": "3"})
+
+
+def test_pipeline_read_longer_than_chunk_fails_cleanly(tool, tmp_path):
+    """a read that cannot fit a chunk must end the run with a message, not overflow the 32-bit offsets."""
+    f1 = str(tmp_path / "long.fq")
+    open(f1, "w").write("@a\nACGT\n+\nIIII\n@b\n" + "ACGT" * 500 + "\n+\n" + "IIII" * 500 + "\n@c\nAC\n+\nII\n")
+    r = subprocess.run([tool, "pipe-check", f1, "--chunk", "100", "--bytes", "1000"], capture_output=True, timeout=60)
+    assert r.returncode == 3 and b"exceeds the chunk capacity" in r.stderr
