@@ -22,11 +22,14 @@
 // the compact results (one 16-bit word per read + a list for ties), writes with pwrite at precomputed
 // offsets when the descriptor is seekable, in order otherwise.
 #pragma once
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -36,6 +39,20 @@
 #include "fastpipe.hpp"
 
 namespace shkhost {
+
+// SHK_TIMING: seconds spent per host stage (diagnostics; printed by the CLI at exit)
+struct StageTimes {
+    double scan_wait = 0, flatten = 0, offsets = 0, pack = 0, exact = 0, format = 0, output = 0;
+};
+inline StageTimes &stage_times()
+{
+    static StageTimes t;
+    return t;
+}
+inline double stage_now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 constexpr unsigned kBatch = 50000;  // FastqSplitter batch (main.cpp:215): ReadOutput's dedup resets per batch
 constexpr uint32_t kGeneNone = 0xFFFFu, kGeneMulti = 0xFFFEu;  // SHK_GENE_NONE / SHK_GENE_MULTI
@@ -138,13 +155,18 @@ public:
         ch.clear();
         if (finished_) return false;
         static const bool no_bulk = getenv("SHK_NO_BULK") && atoi(getenv("SHK_NO_BULK")) != 0;
+        const double t0 = stage_now();
         size_t n = no_bulk ? 0 : s1_.clean_run(max_reads);
         if (s2_ && n) n = std::min(n, s2_->clean_run(n));
+        stage_times().scan_wait += stage_now() - t0;
         if (n) {
             fill_bulk(ch, n, max_bytes);
             if (ch.n) return true;  // (a first read longer than max_bytes: the exact path reports it)
         }
-        return fill_exact(ch, max_reads, max_bytes);
+        const double t1 = stage_now();
+        const bool more = fill_exact(ch, max_reads, max_bytes);
+        stage_times().exact += stage_now() - t1;
+        return more;
     }
     const char *error() const { return error_.empty() ? nullptr : error_.c_str(); }
 
@@ -154,6 +176,7 @@ private:
     {
         const bool paired = (bool)s2_;
         // the records, without consuming them yet: the byte bound may cut the chunk short
+        const double t_a = stage_now();
         std::vector<Span> sp1, sp2;
         std::vector<std::shared_ptr<Block>> keep1, keep2;
         peek_spans(s1_, n, sp1, keep1);
@@ -162,6 +185,8 @@ private:
         if (paired) ch.r2.resize(n);
         flatten(sp1, ch.r1);
         if (paired) flatten(sp2, ch.r2);
+        const double t_b = stage_now();
+        stage_times().flatten += t_b - t_a;
         // offsets: per-range byte sums, their prefix, then the fill - all ranges in parallel
         ch.off.reserve((n + 2) * 4, 0);
         uint32_t *off = (uint32_t *)ch.off.p;
@@ -222,7 +247,10 @@ private:
         ch.bytes = total;
         for (size_t i = (kBatch - batch_got_) % kBatch; i < n; i += kBatch) ch.batch_start.push_back((uint32_t)i);
         batch_got_ = (unsigned)((batch_got_ + n) % kBatch);
+        const double t_c = stage_now();
+        stage_times().offsets += t_c - t_b;
         pack_bulk(ch);
+        stage_times().pack += stage_now() - t_c;
     }
     static void peek_spans(RecordSource &s, size_t n, std::vector<Span> &spans, std::vector<std::shared_ptr<Block>> &keep)
     {
@@ -516,12 +544,14 @@ public:
           has2_(fd_out2 >= 0 && paired)
     {
         for (const std::string &g : legend_) legend_len_.push_back((uint32_t)strlen(g.c_str()));
-        seekable_[0] = fd_ssv >= 0 && lseek(fd_ssv, 0, SEEK_CUR) >= 0;
-        seekable_[1] = has1_ && lseek(fd_out1, 0, SEEK_CUR) >= 0;
-        seekable_[2] = has2_ && lseek(fd_out2, 0, SEEK_CUR) >= 0;
-        // only regular files are written through mappings / pwrite (a FIFO or a tty is not seekable; /dev/null is,
-        // but cannot be mapped - the fallbacks below cover it)
-        if (const char *ev = getenv("SHK_OUT")) out_mode_ = !strcmp(ev, "pwrite") ? 1 : (!strcmp(ev, "write") ? 2 : 0);
+        // regular files are written through mappings (SHK_OUT=write: always write(2), in order)
+        const bool want_map = !(getenv("SHK_OUT") && !strcmp(getenv("SHK_OUT"), "write"));
+        const int fds[3] = {fd_ssv, has1_ ? fd_out1 : -1, has2_ ? fd_out2 : -1};
+        for (int f = 0; f < 3; ++f) {
+            struct stat st;
+            mappable_[f] = want_map && fds[f] >= 0 && fstat(fds[f], &st) == 0 && S_ISREG(st.st_mode) &&
+                           lseek(fds[f], 0, SEEK_CUR) >= 0 && (fcntl(fds[f], F_GETFL) & O_ACCMODE) == O_RDWR;
+        }
     }
     void flush()
     {
@@ -532,75 +562,88 @@ public:
     void write(const Chunk<Alloc> &ch)
     {
         if (ch.n == 0) return;
-        // ranges of reads, formatted in parallel into private buffers
+        // ranges of reads; pass 1 sizes every range's share of the three outputs, pass 2 formats it in place:
+        // straight into a shared mapping of the grown file when the descriptor is a regular file (page faults of
+        // different threads proceed in parallel, whereas write / pwrite to one file serialise on the inode
+        // lock), else into a private buffer that is then written in order
         const size_t n_ranges = std::min<size_t>((size_t)WorkPool::instance().size() * 4, ((size_t)ch.n + 8191) / 8192);
         const size_t per = ((size_t)ch.n + n_ranges - 1) / n_ranges;
-        if (bufs_.size() < n_ranges) bufs_.resize(n_ranges);
+        const double t_f = stage_now();
+        std::vector<size_t> at[3];
+        for (auto &v : at) v.assign(n_ranges + 1, 0);
         WorkPool::instance().run(n_ranges, [&](size_t t) {
             const uint32_t a = (uint32_t)(t * per), b = (uint32_t)std::min<size_t>(ch.n, (t + 1) * per);
-            format(ch, a, b, bufs_[t]);
+            CountSink c[3];
+            format(ch, a, b, c[0], c[1], c[2]);
+            for (int f = 0; f < 3; ++f) at[f][t + 1] = c[f].n;
         });
-        // out: in parallel at the offsets the sizes give when the descriptor is a seekable file - memcpy into a
-        // shared mapping of the grown file (page faults of different threads proceed in parallel; pwrite to one
-        // file serialises on the inode lock), or pwrite (SHK_OUT=pwrite) - else in order
+        for (auto &v : at)
+            for (size_t t = 0; t < n_ranges; ++t) v[t + 1] += v[t];
         OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
+        char *dst[3] = {nullptr, nullptr, nullptr};  // where byte 0 of this chunk's share of output f goes
+        char *map_base[3] = {nullptr, nullptr, nullptr};
+        size_t map_len[3] = {0, 0, 0};
+        off_t file_end[3] = {0, 0, 0};
         for (int f = 0; f < 3; ++f) {
-            if (f == 1 && !has1_) continue;
-            if (f == 2 && !has2_) continue;
+            const size_t total = at[f][n_ranges];
+            if (!total || (f == 1 && !has1_) || (f == 2 && !has2_)) continue;
             OutBuf &ob = *outs[f];
-            size_t total = 0;
-            for (size_t t = 0; t < n_ranges; ++t) total += bufs_[t].s[f].size();
-            if (!total) continue;
-            bool done = false;
-            if (seekable_[f] && n_ranges > 1 && total >= (1u << 20)) {
+            if (mappable_[f] && total >= (1u << 16)) {
                 ob.flush();
                 const off_t base = lseek(ob.fd(), 0, SEEK_CUR);
-                std::vector<off_t> at(n_ranges + 1, base);
-                for (size_t t = 0; t < n_ranges; ++t) at[t + 1] = at[t] + (off_t)bufs_[t].s[f].size();
-                if (out_mode_ == 0 && base >= 0) {
-                    const off_t page = (off_t)sysconf(_SC_PAGESIZE), m0 = base / page * page;
-                    char *m = nullptr;
-                    if (ftruncate(ob.fd(), at[n_ranges]) == 0) {
-                        void *mm = mmap(nullptr, (size_t)(at[n_ranges] - m0), PROT_READ | PROT_WRITE, MAP_SHARED, ob.fd(), m0);
-                        if (mm != MAP_FAILED) m = (char *)mm;
+                const off_t page = (off_t)sysconf(_SC_PAGESIZE), m0 = base / page * page;
+                if (base >= 0 && ftruncate(ob.fd(), base + (off_t)total) == 0) {
+                    void *mm = mmap(nullptr, (size_t)(base - m0) + total, PROT_READ | PROT_WRITE, MAP_SHARED, ob.fd(), m0);
+                    if (mm != MAP_FAILED) {
+                        map_base[f] = (char *)mm;
+                        map_len[f] = (size_t)(base - m0) + total;
+                        dst[f] = map_base[f] + (base - m0);
+                        file_end[f] = base + (off_t)total;
                     }
-                    if (m) {
-                        WorkPool::instance().run(n_ranges, [&](size_t t) {
-                            const std::vector<char> &v = bufs_[t].s[f];
-                            if (!v.empty()) memcpy(m + (at[t] - m0), v.data(), v.size());
-                        });
-                        munmap(m, (size_t)(at[n_ranges] - m0));
-                        lseek(ob.fd(), at[n_ranges], SEEK_SET);
-                        done = true;
-                    }
-                }
-                if (!done && out_mode_ <= 1 && base >= 0) {
-                    WorkPool::instance().run(n_ranges, [&](size_t t) {
-                        const std::vector<char> &v = bufs_[t].s[f];
-                        size_t w_done = 0;
-                        while (w_done < v.size()) {
-                            const ssize_t w = pwrite(ob.fd(), v.data() + w_done, v.size() - w_done, at[t] + (off_t)w_done);
-                            if (w <= 0) {
-                                if (w < 0 && errno == EINTR) continue;
-                                return;  // like the reference, output errors are not reported
-                            }
-                            w_done += (size_t)w;
-                        }
-                    });
-                    lseek(ob.fd(), at[n_ranges], SEEK_SET);
-                    done = true;
                 }
             }
-            if (!done)
-                for (size_t t = 0; t < n_ranges; ++t) ob.put(bufs_[t].s[f].data(), bufs_[t].s[f].size());
+            if (!dst[f]) {
+                if (priv_[f].size() < total) priv_[f].resize(total);
+                dst[f] = priv_[f].data();
+            }
         }
+        WorkPool::instance().run(n_ranges, [&](size_t t) {
+            const uint32_t a = (uint32_t)(t * per), b = (uint32_t)std::min<size_t>(ch.n, (t + 1) * per);
+            WriteSink w[3];
+            for (int f = 0; f < 3; ++f) w[f].p = dst[f] ? dst[f] + at[f][t] : nullptr;
+            format(ch, a, b, w[0], w[1], w[2]);
+        });
+        const double t_o = stage_now();
+        stage_times().format += t_o - t_f;
+        for (int f = 0; f < 3; ++f) {
+            const size_t total = at[f][n_ranges];
+            if (!dst[f] || !total) continue;
+            if (map_base[f]) {
+                munmap(map_base[f], map_len[f]);
+                lseek(outs[f]->fd(), file_end[f], SEEK_SET);
+            } else {
+                outs[f]->put(dst[f], total);
+            }
+        }
+        stage_times().output += stage_now() - t_o;
         // the name ReadOutput's `previd` holds at the end of this chunk, for the first read of the next one
         update_carry(ch);
     }
 
 private:
-    struct RangeBufs {
-        std::vector<char> s[3];
+    struct CountSink {
+        size_t n = 0;
+        void put(const void *, size_t len) { n += len; }
+        void putc(char) { ++n; }
+    };
+    struct WriteSink {
+        char *p = nullptr;
+        void put(const void *src, size_t len)
+        {
+            memcpy(p, src, len);
+            p += len;
+        }
+        void putc(char c) { *p++ = c; }
     };
     struct Fields {
         const char *name1, *seq1, *qual1, *name2, *seq2, *qual2;
@@ -628,21 +671,15 @@ private:
         }
         return f;
     }
-    static void put(std::vector<char> &v, const void *p, size_t n)
-    {
-        const size_t at = v.size();
-        v.resize(at + n);
-        memcpy(v.data() + at, p, n);
-    }
     // start of the batch that read r belongs to, or -1 when that batch began in an earlier chunk
     static int64_t batch_begin(const Chunk<Alloc> &ch, uint32_t r)
     {
         auto it = std::upper_bound(ch.batch_start.begin(), ch.batch_start.end(), r);
         return it == ch.batch_start.begin() ? -1 : (int64_t) * (it - 1);
     }
-    void format(const Chunk<Alloc> &ch, uint32_t a, uint32_t b, RangeBufs &out) const
+    template <class Sink>
+    void format(const Chunk<Alloc> &ch, uint32_t a, uint32_t b, Sink &ssv, Sink &o1, Sink &o2) const
     {
-        for (auto &v : out.s) v.clear();
         // ReadOutput's previd (ReadOutput.hpp:41,44-48) entering this range: the name of the previous kept read of
         // the same batch - earlier in this chunk, or carried over from the previous chunk
         const char *previd = "";  // `string previd = ""`: an empty name at the start of a batch equals it
@@ -671,10 +708,10 @@ private:
             if (g16 == kGeneNone) continue;
             const Fields f = fields(ch, r, paired_);
             auto line = [&](uint32_t g) {
-                put(out.s[0], f.name1, f.nlen1);
-                out.s[0].push_back(' ');
-                if (g < legend_.size()) put(out.s[0], legend_[g].data(), legend_len_[g]);
-                out.s[0].push_back('\n');
+                ssv.put(f.name1, f.nlen1);
+                ssv.putc(' ');
+                if (g < legend_.size()) ssv.put(legend_[g].data(), legend_len_[g]);
+                ssv.putc('\n');
             };
             if (g16 != kGeneMulti) {
                 line(g16);
@@ -684,25 +721,22 @@ private:
             // FASTQ once per read unless its name equals the previous printed id (ReadOutput.hpp:44-48)
             const bool same = prevlen == f.nlen1 && memcmp(previd, f.name1, prevlen) == 0;
             if (!same) {
-                if (has1_) record(out.s[1], f.name1, f.nlen1, f.seq1, f.slen1, f.qual1, f.qlen1);
-                if (has2_) record(out.s[2], f.name2, f.nlen2, f.seq2, f.slen2, f.qual2, f.qlen2);
+                if (has1_) record(o1, f.name1, f.nlen1, f.seq1, f.slen1, f.qual1, f.qlen1);
+                if (has2_) record(o2, f.name2, f.nlen2, f.seq2, f.slen2, f.qual2, f.qlen2);
             }
             previd = f.name1, prevlen = f.nlen1;
         }
     }
-    static void record(std::vector<char> &v, const char *name, uint32_t nlen, const char *seq, uint32_t slen, const char *qual,
-                       uint32_t qlen)
+    template <class Sink>
+    static void record(Sink &o, const char *name, uint32_t nlen, const char *seq, uint32_t slen, const char *qual, uint32_t qlen)
     {
-        const size_t at = v.size();
-        v.resize(at + 1 + nlen + 1 + slen + 3 + qlen + 1);
-        char *d = v.data() + at;
-        *d++ = '@';
-        memcpy(d, name, nlen), d += nlen;
-        *d++ = '\n';
-        memcpy(d, seq, slen), d += slen;
-        memcpy(d, "\n+\n", 3), d += 3;
-        memcpy(d, qual, qlen), d += qlen;
-        *d = '\n';
+        o.putc('@');
+        o.put(name, nlen);
+        o.putc('\n');
+        o.put(seq, slen);
+        o.put("\n+\n", 3);
+        o.put(qual, qlen);
+        o.putc('\n');
     }
     void update_carry(const Chunk<Alloc> &ch)
     {
@@ -724,9 +758,8 @@ private:
     bool paired_;
     OutBuf ssv_, out1_, out2_;
     bool has1_, has2_;
-    bool seekable_[3] = {false, false, false};
-    int out_mode_ = 0;  // 0 mapping (then pwrite, then write as fallbacks), 1 pwrite, 2 write
-    std::vector<RangeBufs> bufs_;
+    bool mappable_[3] = {false, false, false};  // a regular file opened read-write (a shared mapping needs both)
+    std::vector<char> priv_[3];
     std::string carry_;
     bool carry_valid_ = false;
 };

@@ -19,6 +19,7 @@
 // the index build.
 #include <fcntl.h>
 #include <getopt.h>
+#include <malloc.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -283,6 +284,10 @@ private:
 
 int main(int argc, char *argv[])
 {
+    // the record arrays and staging buffers of the pipeline are megabytes each and are recycled chunk after chunk:
+    // keep them in the heap (fresh anonymous mappings would cost a page fault per 4 KiB every time)
+    mallopt(M_MMAP_THRESHOLD, 32 << 20);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
     const Options opt = parse_arguments(argc, argv);
 
     if (opt.verbose) {  // main.cpp:113-123
@@ -400,8 +405,8 @@ int main(int argc, char *argv[])
     std::vector<uint8_t>().swap(ref_bases);
 
     // ---- sample stage: scanners -> batcher thread -> (this thread: submit / collect) -> writer thread
-    const int fd1 = opt.out1_path.empty() ? -1 : open(opt.out1_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
-    const int fd2 = (!opt.paired || opt.out2_path.empty()) ? -1 : open(opt.out2_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    const int fd1 = opt.out1_path.empty() ? -1 : open(opt.out1_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
+    const int fd2 = (!opt.paired || opt.out2_path.empty()) ? -1 : open(opt.out2_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
     Writer writer(STDOUT_FILENO, fd1, fd2, legend_ID, opt.paired);
 
     std::thread writer_thread([&] {
@@ -423,11 +428,14 @@ int main(int argc, char *argv[])
     std::deque<InFlight> inflight;
     const size_t max_inflight = (size_t)opt.gpus * 2;
     uint64_t submitted = 0, total_reads = 0;
+    double t_submit = 0, t_collect = 0, t_wait = 0;
     auto drain_one = [&] {
         InFlight f = inflight.front();
         inflight.pop_front();
         shk_chunk_result res;
+        const double t0 = shkhost::stage_now();
         SHK_TRY(ctxs[f.gpu], shk_reads_collect(ctxs[f.gpu], f.slot, &res));
+        t_collect += shkhost::stage_now() - t0;
         // the slot's result buffers are reused by its next submit: the compact results travel with the chunk
         f.ch->gene16.assign(res.gene16, res.gene16 + res.n_reads);
         const shkhost::AssocPair *mu = reinterpret_cast<const shkhost::AssocPair *>(res.multi);
@@ -435,7 +443,9 @@ int main(int argc, char *argv[])
         write_q.push(f.ch);
     };
     for (bool done = false; !done;) {
+        const double t_w0 = shkhost::stage_now();
         Chunk *ch = ready_q.pop();
+        t_wait += shkhost::stage_now() - t_w0;
         done = ch->last;
         if (ch->n == 0) {
             ch->clear();
@@ -446,8 +456,10 @@ int main(int argc, char *argv[])
         if (inflight.size() == max_inflight) drain_one();
         const int gpu = (int)(submitted % (uint64_t)opt.gpus);
         const uint32_t slot = (uint32_t)((submitted / (uint64_t)opt.gpus) % 2);
+        const double t_s0 = shkhost::stage_now();
         SHK_TRY(ctxs[gpu], shk_reads_submit_packed(ctxs[gpu], slot, (const uint64_t *)ch->codes.p, (const uint32_t *)ch->valid.p,
                                                    ch->offsets(), ch->n));
+        t_submit += shkhost::stage_now() - t_s0;
         inflight.push_back({ch, gpu, slot});
         ++submitted;
         total_reads += ch->n;
@@ -460,8 +472,15 @@ int main(int argc, char *argv[])
     if (fd1 >= 0) close(fd1);
     if (fd2 >= 0) close(fd2);
     tstamp("output written");
-    if (g_timing) fprintf(stderr, "[shark-b200/timing] reads %llu in %llu chunks, %d host threads\n", (unsigned long long)total_reads,
-                          (unsigned long long)submitted, shkhost::host_threads());
+    if (g_timing) {
+        const shkhost::StageTimes &st = shkhost::stage_times();
+        fprintf(stderr, "[shark-b200/timing] reads %llu in %llu chunks, %d host threads\n", (unsigned long long)total_reads,
+                (unsigned long long)submitted, shkhost::host_threads());
+        fprintf(stderr, "[shark-b200/timing] batcher: waiting for the scanners %.0f ms, record arrays %.0f ms, offsets %.0f ms, packing %.0f ms, "
+                        "exact path %.0f ms; writer: formatting %.0f ms, output %.0f ms; main: submit %.0f ms, collect %.0f ms, waiting for chunks %.0f ms\n",
+                st.scan_wait * 1e3, st.flatten * 1e3, st.offsets * 1e3, st.pack * 1e3, st.exact * 1e3, st.format * 1e3, st.output * 1e3,
+                t_submit * 1e3, t_collect * 1e3, t_wait * 1e3);
+    }
     pelapsed("Sample completed");
     fflush(nullptr);
     // the process ends here: the context, the mappings and the staging memory go with it (tearing them down one

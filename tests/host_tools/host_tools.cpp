@@ -205,7 +205,7 @@ static int ingest_bench(const char *f1, const char *f2, bool with_qual)
     FILE *null = fopen("/dev/null", "w");
     const int fdn = fileno(null);
     const char *o1 = getenv("OUT1");
-    int fd1 = o1 ? open(o1, O_WRONLY | O_CREAT | O_TRUNC, 0666) : fdn;
+    int fd1 = o1 ? open(o1, O_RDWR | O_CREAT | O_TRUNC, 0666) : fdn;
     Writer<MallocAlloc> writer(fdn, fd1, f2 ? fdn : -1, legend, f2 != nullptr);
     Chunk<MallocAlloc> ch[2];
     uint64_t reads = 0, bytes = 0, bulk = 0;
@@ -242,8 +242,8 @@ static int pipe_check(const char *f1, const char *f2, int min_quality, unsigned 
     batcher.start();
     std::vector<std::string> legend{"gA", "gB"};
     const char *o1 = getenv("OUT1"), *o2 = getenv("OUT2");
-    const int fd1 = o1 ? open(o1, O_WRONLY | O_CREAT | O_TRUNC, 0666) : -1;
-    const int fd2 = (o2 && f2) ? open(o2, O_WRONLY | O_CREAT | O_TRUNC, 0666) : -1;
+    const int fd1 = o1 ? open(o1, O_RDWR | O_CREAT | O_TRUNC, 0666) : -1;
+    const int fd2 = (o2 && f2) ? open(o2, O_RDWR | O_CREAT | O_TRUNC, 0666) : -1;
     Writer<MallocAlloc> writer(STDOUT_FILENO, fd1, fd2, legend, f2 != nullptr);
     Chunk<MallocAlloc> ch;
     uint64_t global = 0;
