@@ -25,6 +25,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -544,14 +545,22 @@ public:
           has2_(fd_out2 >= 0 && paired)
     {
         for (const std::string &g : legend_) legend_len_.push_back((uint32_t)strlen(g.c_str()));
-        // regular files are written through mappings (SHK_OUT=write: always write(2), in order)
-        const bool want_map = !(getenv("SHK_OUT") && !strcmp(getenv("SHK_OUT"), "write"));
+        // Files on tmpfs are written through shared mappings: the threads of the pool fault pages in
+        // concurrently (7 GB/s on the B200 host), while write / pwrite to one file serialise on its inode lock
+        // (4-5 GB/s).  On disk-backed file systems write(2) into the page cache is the faster way (6.7 vs
+        // 3-4 GB/s there; profiles/iobench_r2.txt), so everything else is formatted into a private buffer and
+        // written in order.  SHK_OUT=map / write forces either.
+        const char *mode = getenv("SHK_OUT");
         const int fds[3] = {fd_ssv, has1_ ? fd_out1 : -1, has2_ ? fd_out2 : -1};
         for (int f = 0; f < 3; ++f) {
             struct stat st;
-            mappable_[f] = want_map && fds[f] >= 0 && fstat(fds[f], &st) == 0 && S_ISREG(st.st_mode) &&
-                           lseek(fds[f], 0, SEEK_CUR) >= 0 && (fcntl(fds[f], F_GETFL) & O_ACCMODE) == O_RDWR;
+            struct statfs sf;
+            const bool can = fds[f] >= 0 && fstat(fds[f], &st) == 0 && S_ISREG(st.st_mode) && lseek(fds[f], 0, SEEK_CUR) >= 0 &&
+                             (fcntl(fds[f], F_GETFL) & O_ACCMODE) == O_RDWR;
+            const bool tmpfs = can && fstatfs(fds[f], &sf) == 0 && (unsigned long)sf.f_type == 0x01021994ul;  // TMPFS_MAGIC
+            mappable_[f] = can && (mode ? !strcmp(mode, "map") : tmpfs);
         }
+        populate_ = getenv("SHK_OUT_POPULATE") && atoi(getenv("SHK_OUT_POPULATE")) != 0;
     }
     void flush()
     {
@@ -611,6 +620,15 @@ public:
             const uint32_t a = (uint32_t)(t * per), b = (uint32_t)std::min<size_t>(ch.n, (t + 1) * per);
             WriteSink w[3];
             for (int f = 0; f < 3; ++f) w[f].p = dst[f] ? dst[f] + at[f][t] : nullptr;
+#ifdef MADV_POPULATE_WRITE
+            if (populate_)  // allocate this range's pages of the file in one call instead of one fault per page
+                for (int f = 0; f < 3; ++f)
+                    if (map_base[f] && at[f][t + 1] > at[f][t]) {
+                        const uintptr_t pg = (uintptr_t)sysconf(_SC_PAGESIZE);
+                        const uintptr_t lo = (uintptr_t)(dst[f] + at[f][t]) / pg * pg, hi = (uintptr_t)(dst[f] + at[f][t + 1]);
+                        madvise((void *)lo, hi - lo, MADV_POPULATE_WRITE);
+                    }
+#endif
             format(ch, a, b, w[0], w[1], w[2]);
         });
         const double t_o = stage_now();
@@ -759,6 +777,7 @@ private:
     OutBuf ssv_, out1_, out2_;
     bool has1_, has2_;
     bool mappable_[3] = {false, false, false};  // a regular file opened read-write (a shared mapping needs both)
+    bool populate_ = false;
     std::vector<char> priv_[3];
     std::string carry_;
     bool carry_valid_ = false;

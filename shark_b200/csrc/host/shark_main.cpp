@@ -20,6 +20,8 @@
 #include <fcntl.h>
 #include <getopt.h>
 #include <malloc.h>
+#include <signal.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -282,7 +284,48 @@ private:
 
 }  // namespace
 
+// Detached tear-down.  When the last output byte has been written, what is left is the end of the process:
+// unmapping gigabytes of input, freeing the staging memory and - most of it - the driver taking the device
+// context apart, about half a second during which the results are already complete.  The work is therefore done
+// in a child process; the process the user started returns as soon as the child reports "output complete" and
+// leaves the child to finish on its own.  A child that fails, or ends without that report, has its exit status
+// passed on.  SHK_NO_DETACH=1 runs everything in the one process.
+int run(int argc, char *argv[], int done_fd);
+
 int main(int argc, char *argv[])
+{
+    if (getenv("SHK_NO_DETACH") && atoi(getenv("SHK_NO_DETACH")) != 0) return run(argc, argv, -1);
+    int fds[2];
+    if (pipe(fds) != 0) return run(argc, argv, -1);
+    fflush(nullptr);
+    const pid_t child = fork();
+    if (child < 0) {
+        close(fds[0]);
+        close(fds[1]);
+        return run(argc, argv, -1);
+    }
+    if (child == 0) {
+        close(fds[0]);
+        return run(argc, argv, fds[1]);
+    }
+    close(fds[1]);
+    char ok = 0;
+    ssize_t got;
+    do got = read(fds[0], &ok, 1);
+    while (got < 0 && errno == EINTR);
+    if (got == 1 && ok == 1) _exit(0);  // the outputs are complete; the child tidies up by itself
+    int status = 0;
+    while (waitpid(child, &status, 0) < 0 && errno == EINTR) {
+    }
+    if (WIFEXITED(status)) _exit(WEXITSTATUS(status));
+    if (WIFSIGNALED(status)) {  // die the way the child died, so that the caller sees the same thing
+        signal(WTERMSIG(status), SIG_DFL);
+        raise(WTERMSIG(status));
+    }
+    _exit(EXIT_FAILURE);
+}
+
+int run(int argc, char *argv[], int done_fd)
 {
     // the record arrays and staging buffers of the pipeline are megabytes each and are recycled chunk after chunk:
     // keep them in the heap (fresh anonymous mappings would cost a page fault per 4 KiB every time)
@@ -482,15 +525,17 @@ int main(int argc, char *argv[])
                 t_submit * 1e3, t_collect * 1e3, t_wait * 1e3);
     }
     pelapsed("Sample completed");
+    pelapsed("Association done");
     fflush(nullptr);
-    // the process ends here: the context, the mappings and the staging memory go with it (tearing them down one
-    // by one costs tens of milliseconds a user would wait for)
-    if (!getenv("SHK_CLEAN_EXIT")) {
-        pelapsed("Association done");
-        _exit(0);
+    if (done_fd >= 0) {  // everything a user waits for is done: the parent process returns now
+        const char ok = 1;
+        if (write(done_fd, &ok, 1) != 1) {
+        }
+        close(done_fd);
     }
+    // the process ends here: the context, the mappings and the staging memory go with it
+    if (!getenv("SHK_CLEAN_EXIT")) _exit(0);
     pool.clear();
     for (auto *c : ctxs) shk_destroy(c);
-    pelapsed("Association done");
     return 0;
 }
