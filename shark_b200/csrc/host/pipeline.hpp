@@ -564,9 +564,17 @@ public:
     }
     void flush()
     {
-        ssv_.flush();
-        out1_.flush();
-        out2_.flush();
+        OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
+        for (int f = 0; f < 3; ++f) {
+            outs[f]->flush();
+            if (win_[f].base) {  // the file was grown ahead of the data: cut it to what was written
+                if (ftruncate(outs[f]->fd(), win_[f].pos) != 0) {
+                }
+                lseek(outs[f]->fd(), win_[f].pos, SEEK_SET);
+                // the windows themselves are left to the end of the process (unmapping gigabytes of dirty pages
+                // costs tens of milliseconds that nobody needs to wait for)
+            }
+        }
     }
     void write(const Chunk<Alloc> &ch)
     {
@@ -590,27 +598,12 @@ public:
             for (size_t t = 0; t < n_ranges; ++t) v[t + 1] += v[t];
         OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
         char *dst[3] = {nullptr, nullptr, nullptr};  // where byte 0 of this chunk's share of output f goes
-        char *map_base[3] = {nullptr, nullptr, nullptr};
-        size_t map_len[3] = {0, 0, 0};
-        off_t file_end[3] = {0, 0, 0};
+        bool mapped[3] = {false, false, false};
         for (int f = 0; f < 3; ++f) {
             const size_t total = at[f][n_ranges];
             if (!total || (f == 1 && !has1_) || (f == 2 && !has2_)) continue;
-            OutBuf &ob = *outs[f];
-            if (mappable_[f] && total >= (1u << 16)) {
-                ob.flush();
-                const off_t base = lseek(ob.fd(), 0, SEEK_CUR);
-                const off_t page = (off_t)sysconf(_SC_PAGESIZE), m0 = base / page * page;
-                if (base >= 0 && ftruncate(ob.fd(), base + (off_t)total) == 0) {
-                    void *mm = mmap(nullptr, (size_t)(base - m0) + total, PROT_READ | PROT_WRITE, MAP_SHARED, ob.fd(), m0);
-                    if (mm != MAP_FAILED) {
-                        map_base[f] = (char *)mm;
-                        map_len[f] = (size_t)(base - m0) + total;
-                        dst[f] = map_base[f] + (base - m0);
-                        file_end[f] = base + (off_t)total;
-                    }
-                }
-            }
+            if (mappable_[f] && (total >= (1u << 16) || win_[f].base)) dst[f] = window(f, total);
+            mapped[f] = dst[f] != nullptr;
             if (!dst[f]) {
                 if (priv_[f].size() < total) priv_[f].resize(total);
                 dst[f] = priv_[f].data();
@@ -623,7 +616,7 @@ public:
 #ifdef MADV_POPULATE_WRITE
             if (populate_)  // allocate this range's pages of the file in one call instead of one fault per page
                 for (int f = 0; f < 3; ++f)
-                    if (map_base[f] && at[f][t + 1] > at[f][t]) {
+                    if (mapped[f] && at[f][t + 1] > at[f][t]) {
                         const uintptr_t pg = (uintptr_t)sysconf(_SC_PAGESIZE);
                         const uintptr_t lo = (uintptr_t)(dst[f] + at[f][t]) / pg * pg, hi = (uintptr_t)(dst[f] + at[f][t + 1]);
                         madvise((void *)lo, hi - lo, MADV_POPULATE_WRITE);
@@ -636,12 +629,8 @@ public:
         for (int f = 0; f < 3; ++f) {
             const size_t total = at[f][n_ranges];
             if (!dst[f] || !total) continue;
-            if (map_base[f]) {
-                munmap(map_base[f], map_len[f]);
-                lseek(outs[f]->fd(), file_end[f], SEEK_SET);
-            } else {
-                outs[f]->put(dst[f], total);
-            }
+            if (mapped[f]) win_[f].pos += (off_t)total;
+            else outs[f]->put(dst[f], total);
         }
         stage_times().output += stage_now() - t_o;
         // the name ReadOutput's `previd` holds at the end of this chunk, for the first read of the next one
@@ -776,6 +765,44 @@ private:
     bool paired_;
     OutBuf ssv_, out1_, out2_;
     bool has1_, has2_;
+    // Output through mappings: the file is grown a window (1 GiB) at a time and the window mapped once; chunks
+    // are formatted into it back to back.  -> address of the next `total` bytes of output f (nullptr: cannot map).
+    struct Window {
+        char *base = nullptr;  // mapping of [start, start + len)
+        off_t start = 0, len = 0, pos = 0;  // pos = file offset of the next output byte
+    };
+    char *window(int f, size_t total)
+    {
+        OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
+        Window &w = win_[f];
+        const int fd = outs[f]->fd();
+        if (!w.base) {
+            outs[f]->flush();
+            w.pos = lseek(fd, 0, SEEK_CUR);
+            if (w.pos < 0) return nullptr;
+        }
+        if (!w.base || w.pos + (off_t)total > w.start + w.len) {
+            const off_t page = (off_t)sysconf(_SC_PAGESIZE), start = w.pos / page * page;
+            const off_t len = std::max<off_t>((off_t)1 << 30, (w.pos - start) + (off_t)total);
+            if (ftruncate(fd, start + len) != 0) return w.base ? (abort_windows(f), nullptr) : nullptr;
+            void *mm = mmap(nullptr, (size_t)len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, start);
+            if (mm == MAP_FAILED) return w.base ? (abort_windows(f), nullptr) : nullptr;
+            w.base = (char *)mm;  // (the previous window stays mapped: see flush())
+            w.start = start;
+            w.len = len;
+        }
+        return w.base + (w.pos - w.start);
+    }
+    void abort_windows(int f)  // mapping failed mid-way: continue with write(2) at the current position
+    {
+        OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
+        if (ftruncate(outs[f]->fd(), win_[f].pos) != 0) {
+        }
+        lseek(outs[f]->fd(), win_[f].pos, SEEK_SET);
+        win_[f] = Window{};
+        mappable_[f] = false;
+    }
+    Window win_[3];
     bool mappable_[3] = {false, false, false};  // a regular file opened read-write (a shared mapping needs both)
     bool populate_ = false;
     std::vector<char> priv_[3];
