@@ -580,23 +580,24 @@ def run_workload(name, args, rank, world, local_rank, cores, dist, torch):
     leg_stats = {}
 
     def e2e_leg(mode):
+        # K steps = K passes over the rank's chunks as ONE stream through the slots (a step boundary does not drain
+        # the pipeline: a sample is a stream of chunks, not a sequence of separately flushed batches)
         if mode == "packed":
             sh.set_upload_mode(False)
-            run = lambda: sh.analyze_chunks(packed, copy=False, on_result=lambda r: None, packed=True)  # noqa: E731
+            run = lambda k: sh.analyze_chunks(packed * k, copy=False, on_result=lambda r: None, packed=True)  # noqa: E731
         else:
             sh.set_upload_mode(False if mode == "plain" else (True if mode == "split" else float(mode)))
-            run = lambda: sh.analyze_chunks(chunks, copy=False, on_result=lambda r: None)  # noqa: E731
-        for _ in range(args.warmup):
-            run()
+            run = lambda k: sh.analyze_chunks(chunks * k, copy=False, on_result=lambda r: None)  # noqa: E731
+        if args.warmup:
+            run(args.warmup)
         barrier()
         h0, dd0 = sh.h2d_bytes(), sh.d2h_bytes()
         t0 = time.perf_counter()
         sh.timer_start()
-        for _ in range(args.steps):
-            run()
+        run(args.steps)
         t_dev = sh.timer_stop() * 1e-3
         # the split upload packs on the host BEFORE a chunk's first device operation: the device stopwatch would
-        # miss the packing of the first chunk of a step, the host clock around the same region does not
+        # miss the packing of the first chunk, the host clock around the same region does not
         barrier()
         t_wall = time.perf_counter() - t0
         leg_stats[mode] = sh.upload_stats()

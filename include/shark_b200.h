@@ -73,6 +73,16 @@ typedef struct shk_params {
  * keep are NULL and shk_reads_collect does no per-read host work.  Without the flag shk_reads_collect expands
  * the compact form into assoc / keep on the calling thread (about 1 ms per million reads). */
 #define SHK_F_COMPACT_RESULTS 8u
+/* Lifts two limits of the reference - an opt-in extension, the default stays as the reference
+ * is: gene ids are 32 bits wide instead of the 16 of small_vector_t::push_back(uint16_t) / vector<uint16_t>
+ * (small_vector.hpp:46, bloomfilter.h:45), so that more than 65536 reference records can be indexed; and the
+ * id total is bounded by the 32 bits of the list offsets instead of the reference's `int tot_idx`
+ * (bloomfilter.h:130).  Without the flag such inputs fail with SHK_E_LIMIT.  With it the index keeps the
+ * reference's structures (filter + rank, per-bit entries, CSR with uint32 ids; shk_index_export_wide) but not
+ * the 16-bit accelerators built on top of them, every read is classified through the reference-shaped probe
+ * (warp per read), results arrive through the `multi` list, and the staged functor protocol
+ * (shk_bf_add_to_kmer) is not available. */
+#define SHK_F_WIDE_IDS 16u
 
 /* Compact per-read result words (shk_chunk_result.gene16). */
 #define SHK_GENE_NONE 0xFFFFu  /* no association: the read is not reported                                */
@@ -98,6 +108,8 @@ typedef struct shk_index_info {
     float build_wall_ms;   /* host clock around the same build, allocations included               */
     uint32_t n_shards;     /* 1 = built by shk_index_build; n = sharded build over n contexts;
                               0 = staged protocol / adopted                                         */
+    uint32_t id_bits;      /* width of a gene id in the CSR: 16, or 32 with SHK_F_WIDE_IDS            */
+    uint32_t reserved;
 } shk_index_info;
 
 /* One association = one line of the reference's stdout (ReadOutput.hpp:43): read `read_idx`
@@ -168,6 +180,9 @@ int shk_index_info_get(const shk_ctx *ctx, shk_index_info *info);
  * (offsets[r] = select(r)+1 over `_bv`, bloomfilter.h:142-148), ids[tot_ids] (`_index_kmer`).
  * Any pointer may be NULL. */
 int shk_index_export(shk_ctx *ctx, uint64_t *set_bit_pos, uint32_t *offsets, uint16_t *ids);
+/* The same with 32-bit ids: works for both id widths (ids of a 16-bit index are widened); shk_index_export
+ * returns SHK_E_STATE for an index built with SHK_F_WIDE_IDS when ids != NULL. */
+int shk_index_export_wide(shk_ctx *ctx, uint64_t *set_bit_pos, uint32_t *offsets, uint32_t *ids);
 
 /* Replication across GPUs (one context per GPU).  The arrays that define the
  * index are exposed as device buffers so that the host can move them with any transport

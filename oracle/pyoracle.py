@@ -53,6 +53,8 @@ def lib():
         L.shko_enumerate.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.shko_index_build.restype = C.c_void_p
         L.shko_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint64]
+        L.shko_index_build_wide.restype = C.c_void_p
+        L.shko_index_build_wide.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint64]
         L.shko_index_free.argtypes = [C.c_void_p]
         for f, t in (("n_set", C.c_uint64), ("tot_ids", C.c_uint64), ("n_genes", C.c_uint32)):
             getattr(L, "shko_index_" + f).restype = t
@@ -60,7 +62,8 @@ def lib():
         L.shko_index_pos.restype = u64p
         L.shko_index_off.restype = u32p
         L.shko_index_ids.restype = u16p
-        for f in ("pos", "off", "ids"):
+        L.shko_index_ids32.restype = u32p
+        for f in ("pos", "off", "ids", "ids32"):
             getattr(L, "shko_index_" + f).argtypes = [C.c_void_p]
         L.shko_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.shko_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
@@ -119,19 +122,22 @@ def concat_records(seqs):
 class Index:
     """Sparse restatement of class BF after switch_mode(2) (bloomfilter.h:36-203)."""
 
-    def __init__(self, bases, rec_off, k, bf_bits):
+    def __init__(self, bases, rec_off, k, bf_bits, wide=False):
+        """wide=True: the widened restatement (32-bit gene ids, SHK_F_WIDE_IDS / SURVEY.md 8f.4)."""
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
         self._keep = (bases, rec_off)
         self.k, self.bf_bits = k, bf_bits
-        self._h = lib().shko_index_build(_p(bases), _p(rec_off), len(rec_off) - 1, k, C.c_uint64(bf_bits))
         L = lib()
+        build = L.shko_index_build_wide if wide else L.shko_index_build
+        self._h = build(_p(bases), _p(rec_off), len(rec_off) - 1, k, C.c_uint64(bf_bits))
         self.n_set = L.shko_index_n_set(self._h)
         self.tot_ids = L.shko_index_tot_ids(self._h)
         self.n_genes = L.shko_index_n_genes(self._h)
         self.pos = np.ctypeslib.as_array(L.shko_index_pos(self._h), shape=(self.n_set + 1,))[: self.n_set]
         self.off = np.ctypeslib.as_array(L.shko_index_off(self._h), shape=(self.n_set + 1,))
         self.ids = np.ctypeslib.as_array(L.shko_index_ids(self._h), shape=(self.tot_ids + 1,))[: self.tot_ids]
+        self.ids32 = np.ctypeslib.as_array(L.shko_index_ids32(self._h), shape=(self.tot_ids + 1,))[: self.tot_ids]
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -150,6 +150,8 @@ typedef struct {
     uint64_t *pos;
     uint32_t *off;
     uint16_t *ids;
+    uint32_t *ids32;    /* the same ids untruncated: what SHK_F_WIDE_IDS indexes hold (see shko_index_build_wide) */
+    int wide;
 } shko_index;
 
 typedef struct { uint64_t pos; uint32_t gene; } occ_t;
@@ -167,10 +169,27 @@ static int cmp_occ(const void *a, const void *b)
  * (including the nidx rule: `continue` at main.cpp:166 skips `++nidx` at 186);
  * switch 1->2 = bloomfilter.h:126-184.  Gene ids are stored as uint16_t
  * (small_vector.hpp:46): callers must keep n_records <= 65536. */
+static shko_index *index_build(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_records, int k, uint64_t bf_bits,
+                               int wide);
 shko_index *shko_index_build(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_records, int k,
                              uint64_t bf_bits)
 {
+    return index_build(bases, rec_off, n_records, k, bf_bits, 0);
+}
+/* The same algorithm with the two widenings of SHK_F_WIDE_IDS: gene ids keep 32 bits where the
+ * reference's small_vector_t::push_back(uint16_t) / vector<uint16_t> (small_vector.hpp:46, bloomfilter.h:45) keep
+ * 16, and nothing is counted in an `int`.  This is the reference's algorithm with those two types changed - what
+ * the reference would compute if its id type were wide enough - not something the reference itself can run. */
+shko_index *shko_index_build_wide(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_records, int k,
+                                  uint64_t bf_bits)
+{
+    return index_build(bases, rec_off, n_records, k, bf_bits, 1);
+}
+static shko_index *index_build(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_records, int k, uint64_t bf_bits,
+                               int wide)
+{
     shko_index *ix = calloc(1, sizeof *ix);
+    ix->wide = wide;
     ix->k = k;
     ix->bf_bits = bf_bits;
     ix->n_records = n_records;
@@ -209,14 +228,17 @@ shko_index *shko_index_build(const uint8_t *bases, const uint64_t *rec_off, uint
     ix->pos = malloc((n_set + 1) * sizeof *ix->pos);
     ix->off = malloc((n_set + 1) * sizeof *ix->off);
     ix->ids = malloc((tot + 1) * sizeof *ix->ids);
+    ix->ids32 = malloc((tot + 1) * sizeof *ix->ids32);
     uint64_t r = 0, t = 0;
     for (uint64_t j = 0; j < n_occ; ++j) {
         if (j == 0 || occ[j].pos != occ[j - 1].pos) {
             ix->pos[r] = occ[j].pos;
             ix->off[r] = (uint32_t)t;
             ++r;
+            ix->ids32[t] = occ[j].gene;
             ix->ids[t++] = (uint16_t)occ[j].gene;
         } else if (occ[j].gene != occ[j - 1].gene) {
+            ix->ids32[t] = occ[j].gene;
             ix->ids[t++] = (uint16_t)occ[j].gene;
         }
     }
@@ -231,6 +253,7 @@ void shko_index_free(shko_index *ix)
     free(ix->pos);
     free(ix->off);
     free(ix->ids);
+    free(ix->ids32);
     free(ix);
 }
 
@@ -240,6 +263,7 @@ uint32_t shko_index_n_genes(const shko_index *ix) { return ix->n_genes; }
 const uint64_t *shko_index_pos(const shko_index *ix) { return ix->pos; }
 const uint32_t *shko_index_off(const shko_index *ix) { return ix->off; }
 const uint16_t *shko_index_ids(const shko_index *ix) { return ix->ids; }
+const uint32_t *shko_index_ids32(const shko_index *ix) { return ix->ids32; }
 
 /* rank of a set position, or -1 (bit clear).  bloomfilter.h:87-90: `_bf[bf_idx]` then
  * `_brank(bf_idx+1)` = r+1 for the r-th (0-based) set bit. */
@@ -343,7 +367,7 @@ uint64_t shko_analyze(const shko_index *ix, const uint8_t *seq, const uint8_t *q
                 int64_t r = find_rank(ix, shko_xxh64_u64(canon[j]) % ix->bf_bits);
                 if (r < 0) continue;
                 for (uint32_t t = ix->off[r]; t < ix->off[r + 1]; ++t) {
-                    gcov_t *g = map_get(&tab, &ntab, &captab, (int)ix->ids[t]);
+                    gcov_t *g = map_get(&tab, &ntab, &captab, ix->wide ? (int)ix->ids32[t] : (int)ix->ids[t]);
                     if (j == 0) {
                         /* ReadAnalyzer.hpp:57-61: pos is one past the window, unsigned math */
                         uint32_t pos = (uint32_t)(endpos[0] + 1);
@@ -417,7 +441,7 @@ int shko_read_table(const shko_index *ix, const uint8_t *text, int64_t n, int *g
             int64_t r = find_rank(ix, shko_xxh64_u64(canon[j]) % ix->bf_bits);
             if (r < 0) continue;
             for (uint32_t t = ix->off[r]; t < ix->off[r + 1]; ++t) {
-                gcov_t *g = map_get(&tab, &ntab, &captab, (int)ix->ids[t]);
+                gcov_t *g = map_get(&tab, &ntab, &captab, ix->wide ? (int)ix->ids32[t] : (int)ix->ids[t]);
                 uint32_t pos = (uint32_t)(j == 0 ? endpos[0] + 1 : endpos[j]);
                 uint32_t d = pos - g->last;
                 g->cov += k < d ? k : d;

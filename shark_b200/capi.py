@@ -25,7 +25,7 @@ EXPORTED = [
     "shk_set_options", "shk_shard_begin", "shk_shard_open", "shk_shard_close", "shk_shard_merge", "shk_shard_rank",
     "shk_shard_finish", "shk_shard_end", "shk_shard_cuts", "shk_index_build_sharded", "shk_index_save", "shk_index_load",
     "shk_host_pack", "shk_host_pack_info", "shk_h2d_bytes", "shk_d2h_bytes", "shk_set_upload_mode", "shk_upload_stats",
-    "shk_reads_submit_packed", "shk_reads_upload_packed", "shk_result_expand",
+    "shk_reads_submit_packed", "shk_reads_upload_packed", "shk_result_expand", "shk_index_export_wide",
 ]
 
 
@@ -42,7 +42,7 @@ class Params(C.Structure):
                 ("host_pack_permille", C.c_uint32), ("reserved", C.c_uint32 * 6)]
 
 
-F_EXTEND_ON, F_EXTEND_OFF, F_HOST_PACK, F_COMPACT_RESULTS = 1, 2, 4, 8
+F_EXTEND_ON, F_EXTEND_OFF, F_HOST_PACK, F_COMPACT_RESULTS, F_WIDE_IDS = 1, 2, 4, 8, 16
 GENE_NONE, GENE_MULTI = 0xFFFF, 0xFFFE
 
 
@@ -51,7 +51,7 @@ class IndexInfo(C.Structure):
                 ("n_windows", C.c_uint64), ("bf_bits", C.c_uint64), ("device_bytes", C.c_uint64), ("build_ms", C.c_float),
                 ("front_shift", C.c_uint32), ("front_entries", C.c_uint64), ("ref_bases", C.c_uint64),
                 ("extend", C.c_uint32), ("coarse_shift", C.c_uint32), ("build_wall_ms", C.c_float),
-                ("n_shards", C.c_uint32)]
+                ("n_shards", C.c_uint32), ("id_bits", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class ShardMem(C.Structure):
@@ -98,6 +98,7 @@ def load():
     L.shk_index_build.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(IndexInfo)]
     L.shk_index_info_get.argtypes = [vp, C.POINTER(IndexInfo)]
     L.shk_index_export.argtypes = [vp, vp, vp, vp]
+    L.shk_index_export_wide.argtypes = [vp, vp, vp, vp]
     L.shk_index_views_get.argtypes = [vp, C.POINTER(IndexViews)]
     L.shk_index_adopt.argtypes = [vp, C.POINTER(IndexInfo)]
     L.shk_index_finalize.argtypes = [vp]

@@ -7,7 +7,8 @@
 // shk_reads_collect.  Extensions (not in the reference): --gpus N, --chunk-reads N, --sharded-build
 // (with --gpus N: every GPU indexes one gene shard, filters OR-merged over NVLink, instead of build +
 // replicate), --save-index FILE / --load-index FILE (the reference rebuilds its index on every run;
-// the gene names still come from -r).
+// the gene names still come from -r), --wide-ids (32-bit gene ids: references of more than 65536 records, which
+// the reference's 16-bit ids cannot index - small_vector.hpp:46; without the flag such inputs end with an error).
 //
 // Pipeline (pipeline.hpp, fastpipe.hpp, ingest.hpp): plain input files are memory-mapped and scanned by
 // the host pool in parallel (compressed ones by a streaming scanner per file); a batcher thread turns runs
@@ -78,6 +79,7 @@ struct Options {
     int gpus = 1;                   // extension
     unsigned chunk_reads = 1000000; // extension
     bool sharded_build = false;     // extension
+    bool wide_ids = false;          // extension: more than 65536 reference records (SHK_F_WIDE_IDS)
     std::string save_index, load_index;  // extensions
 };
 
@@ -149,6 +151,7 @@ const OptionRow kOptions[] = {
     {1002, "sharded-build", false, [](Options &o, std::istringstream &) { o.sharded_build = true; }},
     {1003, "save-index", true, [](Options &o, std::istringstream &a) { a >> o.save_index; }},
     {1004, "load-index", true, [](Options &o, std::istringstream &a) { a >> o.load_index; }},
+    {1005, "wide-ids", false, [](Options &o, std::istringstream &) { o.wide_ids = true; }},
 };
 
 Options parse_arguments(int argc, char **argv)
@@ -415,7 +418,7 @@ int run(int argc, char *argv[], int done_fd)
         p.n_slots = 2;
         p.max_reads_per_chunk = chunk_reads;
         p.max_bytes_per_chunk = max_chunk_bytes;
-        p.flags = SHK_F_COMPACT_RESULTS;
+        p.flags = SHK_F_COMPACT_RESULTS | (opt.wide_ids ? SHK_F_WIDE_IDS : 0u);
         if (shk_create(&p, &ctxs[g]) != SHK_OK) die(std::string("shk_create: ") + shk_last_error(nullptr));
     }
     tstamp("contexts created");

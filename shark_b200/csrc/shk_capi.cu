@@ -225,6 +225,8 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     a.entries = ctx->index.entries;
     a.csr_off = ctx->index.csr_off;
     a.csr_ids = ctx->index.csr_ids;
+    a.csr_ids32 = ctx->index.csr_ids32;
+    a.wide = ctx->index.csr_ids32 != nullptr || ctx->index.info.id_bits == 32;
     a.geom = ctx->index.geom;
     a.front = ctx->index.front;
     a.fgeom = ctx->index.fgeom;
@@ -444,7 +446,7 @@ static int enqueue_upload_packed(shk_ctx *ctx, Slot &s, const uint64_t *codes, c
 
 using namespace shk;
 
-static_assert(sizeof(shk_index_info) == 88 && sizeof(shk_shard_mem) == 240 && sizeof(shk_chunk_result) == 112, "layouts mirrored in shark_b200/capi.py");
+static_assert(sizeof(shk_index_info) == 96 && sizeof(shk_shard_mem) == 240 && sizeof(shk_chunk_result) == 112, "layouts mirrored in shark_b200/capi.py");
 
 extern "C" {
 
@@ -461,8 +463,10 @@ int shk_create(const shk_params *p, shk_ctx **out)
     if (p->bf_bits < 64) return fail(nullptr, SHK_E_ARG, "bf_bits must be >= 64");
     if ((p->flags & SHK_F_EXTEND_ON) && (p->flags & SHK_F_EXTEND_OFF))
         return fail(nullptr, SHK_E_ARG, "SHK_F_EXTEND_ON and SHK_F_EXTEND_OFF are exclusive");
-    if (p->flags & ~(SHK_F_EXTEND_ON | SHK_F_EXTEND_OFF | SHK_F_HOST_PACK | SHK_F_COMPACT_RESULTS))
+    if (p->flags & ~(SHK_F_EXTEND_ON | SHK_F_EXTEND_OFF | SHK_F_HOST_PACK | SHK_F_COMPACT_RESULTS | SHK_F_WIDE_IDS))
         return fail(nullptr, SHK_E_ARG, "unknown flag bits");
+    if ((p->flags & SHK_F_WIDE_IDS) && (p->flags & SHK_F_EXTEND_ON))
+        return fail(nullptr, SHK_E_ARG, "SHK_F_WIDE_IDS has no extension structures (SHK_F_EXTEND_ON)");
     const uint64_t n_words = (p->bf_bits + 31) / 32;
     const uint64_t n_sectors = (n_words + kWordsPerSector - 1) / kWordsPerSector;
     if (n_sectors * 8 > 0xFFFFFFFFull)
@@ -482,6 +486,7 @@ int shk_create(const shk_params *p, shk_ctx **out)
     ctx->device = p->device;
     ctx->host_pack = (p->flags & SHK_F_HOST_PACK) != 0;
     ctx->compact_results = (p->flags & SHK_F_COMPACT_RESULTS) != 0;
+    ctx->wide_ids = (p->flags & SHK_F_WIDE_IDS) != 0;
     if (const char *ev = getenv("SHK_HOST_PACK")) ctx->host_pack = atoi(ev) != 0;  // tuning override
     int rc = SHK_OK;
     auto bail = [&](int code) {
@@ -552,6 +557,7 @@ void shk_destroy(shk_ctx *ctx)
     cudaFree(ctx->index.entries);
     cudaFree(ctx->index.csr_off);
     cudaFree(ctx->index.csr_ids);
+    cudaFree(ctx->index.csr_ids32);
     cudaFree(ctx->index.front);
     cudaFree(ctx->index.estream);
     cudaFree(ctx->index.ref2);
@@ -619,6 +625,7 @@ int shk_bf_switch_mode(shk_ctx *ctx, int new_mode, uint64_t *n_set_bits)
 int shk_bf_add_to_kmer(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int32_t input_idx)
 {
     if (!ctx || (n && !kmers)) return fail(ctx, SHK_E_ARG, "NULL argument");
+    if (ctx->wide_ids) return fail(ctx, SHK_E_STATE, "the staged protocol is the reference's (16-bit ids): not available with SHK_F_WIDE_IDS");
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
     return staged_add_to_kmer(ctx, kmers, n, input_idx);
 }
@@ -646,7 +653,15 @@ int shk_index_export(shk_ctx *ctx, uint64_t *set_bit_pos, uint32_t *offsets, uin
     if (!ctx) return SHK_E_ARG;
     if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index");
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
-    return index_export_device(ctx, set_bit_pos, offsets, ids);
+    return index_export_device(ctx, set_bit_pos, offsets, ids, nullptr);
+}
+
+int shk_index_export_wide(shk_ctx *ctx, uint64_t *set_bit_pos, uint32_t *offsets, uint32_t *ids)
+{
+    if (!ctx) return SHK_E_ARG;
+    if (!ctx->index.built) return fail(ctx, SHK_E_STATE, "no index");
+    SHK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return index_export_device(ctx, set_bit_pos, offsets, nullptr, ids);
 }
 
 int shk_index_views_get(shk_ctx *ctx, shk_index_views *v)
@@ -660,8 +675,9 @@ int shk_index_views_get(shk_ctx *ctx, shk_index_views *v)
     v->bytes[1] = (ix.info.n_set_bits + 1) * 8;
     v->dev_ptr[2] = ix.csr_off;
     v->bytes[2] = (ix.info.n_set_bits + 1) * 4;
-    v->dev_ptr[3] = ix.csr_ids;
-    v->bytes[3] = std::max<uint64_t>(ix.info.tot_ids, 1) * 2;
+    const bool wide = ix.info.id_bits == 32;
+    v->dev_ptr[3] = wide ? (void *)ix.csr_ids32 : (void *)ix.csr_ids;
+    v->bytes[3] = std::max<uint64_t>(ix.info.tot_ids, 1) * (wide ? 4 : 2);
     v->dev_ptr[4] = ix.front;
     v->bytes[4] = ix.fgeom.n_entries * 16 * ix.fgeom.stride;
     const bool ext = ix.egeom.enabled != 0;
@@ -682,15 +698,21 @@ int shk_index_adopt(shk_ctx *ctx, const shk_index_info *info)
         return fail(ctx, SHK_E_ARG, "bf_bits mismatch between source index and this context");
     SHK_CUDA(ctx, cudaSetDevice(ctx->device));
     DeviceIndex &ix = ctx->index;
+    if (info->id_bits != 16 && info->id_bits != 32) return fail(ctx, SHK_E_ARG, "index info: id_bits must be 16 or 32");
+    if ((info->id_bits == 32) != ctx->wide_ids)
+        return fail(ctx, SHK_E_ARG, "the index holds %u-bit gene ids, this context was created %s SHK_F_WIDE_IDS", info->id_bits,
+                    ctx->wide_ids ? "with" : "without");
     cudaFree(ix.entries);
     cudaFree(ix.csr_off);
     cudaFree(ix.csr_ids);
-    ix.entries = nullptr, ix.csr_off = nullptr, ix.csr_ids = nullptr;
+    cudaFree(ix.csr_ids32);
+    ix.entries = nullptr, ix.csr_off = nullptr, ix.csr_ids = nullptr, ix.csr_ids32 = nullptr;
     ix.built = false;
     ix.info = *info;
     SHK_CUDA(ctx, cudaMalloc((void **)&ix.entries, (info->n_set_bits + 1) * 8));
     SHK_CUDA(ctx, cudaMalloc((void **)&ix.csr_off, (info->n_set_bits + 1) * 4));
-    SHK_CUDA(ctx, cudaMalloc((void **)&ix.csr_ids, std::max<uint64_t>(info->tot_ids, 1) * 2));
+    if (info->id_bits == 32) SHK_CUDA(ctx, cudaMalloc((void **)&ix.csr_ids32, std::max<uint64_t>(info->tot_ids, 1) * 4));
+    else SHK_CUDA(ctx, cudaMalloc((void **)&ix.csr_ids, std::max<uint64_t>(info->tot_ids, 1) * 2));
     return index_alloc_front(ctx);
 }
 

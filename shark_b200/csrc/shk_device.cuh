@@ -172,6 +172,10 @@ __device__ __forceinline__ uint64_t make_entry(uint32_t id0, uint32_t len, uint3
 __device__ __forceinline__ uint32_t entry_id0(uint64_t e) { return (uint32_t)(e >> 48); }
 __device__ __forceinline__ uint32_t entry_len(uint64_t e) { return ((uint32_t)(e >> 32) & 0xFFFFu) + 1u; }
 __device__ __forceinline__ uint32_t entry_lo(uint64_t e) { return (uint32_t)e; }
+// SHK_F_WIDE_IDS (32-bit gene ids): bits 63..32 = list length - 1, bits 31..0 = the id of a one-id list, else the
+// CSR begin offset (the ids, first one included, are read from the 32-bit CSR).
+__device__ __forceinline__ uint64_t make_wide_entry(uint32_t len, uint32_t lo) { return ((uint64_t)(len - 1) << 32) | lo; }
+__device__ __forceinline__ uint32_t wide_entry_len(uint64_t e) { return (uint32_t)(e >> 32) + 1u; }
 
 // ---------------------------------------------------------------------------------------------
 // Front table: an exact, L2-sized accelerator in front of the bit vector.  The filter is sparse

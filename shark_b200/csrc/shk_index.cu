@@ -252,9 +252,10 @@ rank_count_kernel(uint64_t *win_pos, uint64_t total, const uint32_t *__restrict_
 
 // K4: second pass, filling.  Gene ids land unordered (and possibly repeated) in the slots that
 // the scan of cnt reserved for each set bit.
+template <class IdT>
 __global__ void __launch_bounds__(256)
 fill_kernel(const uint64_t *__restrict__ win_pos, uint64_t total, const uint64_t *__restrict__ rec_off, uint32_t n_rec,
-            const uint32_t *__restrict__ nidx, const uint32_t *__restrict__ tmp_off, uint32_t *fill, uint16_t *tmp_ids)
+            const uint32_t *__restrict__ nidx, const uint32_t *__restrict__ tmp_off, uint32_t *fill, IdT *tmp_ids)
 {
     uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= total) return;
@@ -263,7 +264,7 @@ fill_kernel(const uint64_t *__restrict__ win_pos, uint64_t total, const uint64_t
     uint32_t r = (uint32_t)v;
     uint32_t g = nidx[record_of(rec_off, n_rec, x)];
     uint32_t slot = tmp_off[r] + atomicAdd(&fill[r], 1u);
-    tmp_ids[slot] = (uint16_t)g;  // small_vector_t::push_back(uint16_t), small_vector.hpp:46
+    tmp_ids[slot] = (IdT)g;  // small_vector_t::push_back(uint16_t), small_vector.hpp:46 (uint32_t with SHK_F_WIDE_IDS)
 }
 
 // Sort + unique of each list (BF::add_to_kmer's `last() != input_idx` dedup with genes arriving
@@ -271,8 +272,9 @@ fill_kernel(const uint64_t *__restrict__ win_pos, uint64_t total, const uint64_t
 // per set bit for the common short lists; long lists are queued for the bitmap kernel.
 constexpr uint32_t kShortList = 48;
 
+template <class IdT>
 __global__ void __launch_bounds__(256)
-sort_unique_kernel(const uint32_t *__restrict__ tmp_off, uint32_t n_set, uint16_t *tmp_ids, uint32_t *len,
+sort_unique_kernel(const uint32_t *__restrict__ tmp_off, uint32_t n_set, IdT *tmp_ids, uint32_t *len,
                    uint32_t *long_list, uint32_t *n_long)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,9 +288,9 @@ sort_unique_kernel(const uint32_t *__restrict__ tmp_off, uint32_t n_set, uint16_
         long_list[atomicAdd(n_long, 1u)] = r;
         return;
     }
-    uint16_t *a = tmp_ids + b;
+    IdT *a = tmp_ids + b;
     for (uint32_t i = 1; i < n; ++i) {
-        uint16_t key = a[i];
+        IdT key = a[i];
         uint32_t j = i;
         while (j > 0 && a[j - 1] > key) {
             a[j] = a[j - 1];
@@ -339,22 +341,72 @@ sort_unique_long_kernel(const uint32_t *__restrict__ tmp_off, const uint32_t *__
     if (threadIdx.x == 255) len[r] = off;
 }
 
+// SHK_F_WIDE_IDS: the same for 32-bit ids.  The presence bitmap (one bit per gene index) lives in global memory,
+// one per CTA; a CTA takes long lists in turn: clear, mark, then compact the set bits in ascending order with a
+// block-wide scan over 256 bitmap words at a time.
+__global__ void __launch_bounds__(256)
+sort_unique_long_wide_kernel(const uint32_t *__restrict__ tmp_off, const uint32_t *__restrict__ long_list, uint32_t n_long,
+                             uint32_t *tmp_ids, uint32_t *len, uint32_t *bitmaps, uint32_t words)
+{
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t base_s;
+    uint32_t *bm = bitmaps + (uint64_t)blockIdx.x * words;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t li = blockIdx.x; li < n_long; li += gridDim.x) {
+        const uint32_t r = long_list[li];
+        const uint32_t b = tmp_off[r], n = tmp_off[r + 1] - b;
+        for (uint32_t i = threadIdx.x; i < words; i += 256) bm[i] = 0;
+        if (threadIdx.x == 0) base_s = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += 256) {
+            const uint32_t id = tmp_ids[b + i];
+            atomicOr(&bm[id >> 5], 1u << (id & 31));
+        }
+        __syncthreads();
+        for (uint32_t w0 = 0; w0 < words; w0 += 256) {
+            const uint32_t w = w0 + threadIdx.x;
+            uint32_t bits = w < words ? bm[w] : 0u;
+            const uint32_t c = __popc(bits);
+            const uint32_t incl = warp_incl_scan(c, lane);
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            uint32_t off = base_s + incl - c;
+            for (int ww = 0; ww < warp; ++ww) off += warp_tot[ww];
+            while (bits) {
+                const int bpos = __ffs(bits) - 1;
+                bits &= bits - 1;
+                tmp_ids[b + off++] = w * 32u + (uint32_t)bpos;
+            }
+            __syncthreads();
+            if (threadIdx.x == 255) base_s = off;  // thread 255 ends at base + all counts of this round
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) len[r] = base_s;
+        __syncthreads();
+    }
+}
+
 // Final layout (BF::switch_mode(2), bloomfilter.h:126-168): ids concatenated in rank order
 // (`_index_kmer`), offsets (= select over `_bv`), and the 8-byte entry per set bit.
+template <class IdT>
 __global__ void __launch_bounds__(256)
-finalize_lists_kernel(const uint32_t *__restrict__ tmp_off, const uint16_t *__restrict__ tmp_ids,
-                      const uint32_t *__restrict__ csr_off, uint32_t n_set, uint16_t *csr_ids, uint64_t *entries)
+finalize_lists_kernel(const uint32_t *__restrict__ tmp_off, const IdT *__restrict__ tmp_ids,
+                      const uint32_t *__restrict__ csr_off, uint32_t n_set, IdT *csr_ids, uint64_t *entries)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_set) return;
     uint32_t o = csr_off[r], m = csr_off[r + 1] - o;
-    const uint16_t *src = tmp_ids + tmp_off[r];
+    const IdT *src = tmp_ids + tmp_off[r];
     if (m == 0) {
         entries[r] = 0;
         return;
     }
     for (uint32_t t = 0; t < m; ++t) csr_ids[o + t] = src[t];
     uint32_t id0 = src[0];
+    if (sizeof(IdT) == 4) {  // wide entries: {length - 1, the id of a one-id list | CSR begin}
+        entries[r] = make_wide_entry(m, m == 1 ? id0 : o);
+        return;
+    }
     uint32_t lo = m == 1 ? 0u : (m == 2 ? (uint32_t)src[1] : o);
     entries[r] = make_entry(id0, m, lo);
 }
@@ -660,6 +712,7 @@ static void free_index_arrays(DeviceIndex &ix)
     if (ix.entries) cudaFree(ix.entries);
     if (ix.csr_off) cudaFree(ix.csr_off);
     if (ix.csr_ids) cudaFree(ix.csr_ids);
+    if (ix.csr_ids32) cudaFree(ix.csr_ids32);
     if (ix.front) cudaFree(ix.front);
     if (ix.estream) cudaFree(ix.estream);
     if (ix.ref2) cudaFree(ix.ref2);
@@ -668,6 +721,7 @@ static void free_index_arrays(DeviceIndex &ix)
     ix.entries = nullptr;
     ix.csr_off = nullptr;
     ix.csr_ids = nullptr;
+    ix.csr_ids32 = nullptr;
     ix.estream = nullptr;
     ix.ref2 = nullptr;
     ix.coarse = nullptr;
@@ -735,6 +789,10 @@ int index_alloc_front(shk_ctx *ctx)
     ix.front = nullptr;
     ix.estream = nullptr, ix.ref2 = nullptr, ix.coarse = nullptr;
     ix.egeom = ExtGeom{};
+    if (ix.info.id_bits == 32) {  // SHK_F_WIDE_IDS: no front table
+        ix.fgeom = FrontGeom{};
+        return SHK_OK;
+    }
     ix.fgeom.shift = ix.info.front_shift;
     ix.fgeom.off_mask = (1u << ix.fgeom.shift) - 1u;
     ix.fgeom.n_buckets = (ix.geom.bf_bits + (1ull << ix.fgeom.shift) - 1) >> ix.fgeom.shift;
@@ -843,21 +901,33 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
 // Second half of the list build, shared by the one-call build and the staged protocol: lists that
 // sit unordered (and repeated) at tmp_ids[tmp_off[r] ..] become the sorted unique CSR + entries.
 // d_len (n_set + 1 words) receives the final lengths, d_long / d_n_long queue the long lists.
-static int finish_lists(shk_ctx *ctx, cudaStream_t st, uint32_t n_set, const uint32_t *d_tmp_off, uint16_t *d_tmp_ids,
+template <class IdT>
+static int finish_lists(shk_ctx *ctx, cudaStream_t st, uint32_t n_set, const uint32_t *d_tmp_off, IdT *d_tmp_ids,
                         uint32_t *d_len, uint32_t *d_long, uint32_t *d_n_long, uint32_t *d_tiles, DevBuf<uint32_t> &d_csr_off,
-                        DevBuf<uint16_t> &d_csr_ids, DevBuf<uint64_t> &d_entries, uint64_t &tot_ids, SegTimer *tm = nullptr)
+                        DevBuf<IdT> &d_csr_ids, DevBuf<uint64_t> &d_entries, uint64_t &tot_ids, SegTimer *tm = nullptr,
+                        uint32_t n_genes = 0)
 {
     const unsigned blocks_r = (unsigned)(((uint64_t)n_set + 255) / 256);
     SHK_CUDA(ctx, cudaMemsetAsync(d_n_long, 0, 4, st));
-    sort_unique_kernel<<<blocks_r, 256, 0, st>>>(d_tmp_off, n_set, d_tmp_ids, d_len, d_long, d_n_long);
+    sort_unique_kernel<IdT><<<blocks_r, 256, 0, st>>>(d_tmp_off, n_set, d_tmp_ids, d_len, d_long, d_n_long);
     ctx->launches += 1;
     uint32_t h_long = 0;
     SHK_CUDA(ctx, cudaMemcpyAsync(&h_long, d_n_long, 4, cudaMemcpyDeviceToHost, st));
     seg_stop(tm, st);
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
     seg_start(tm, st);
+    DevBuf<uint32_t> d_bitmaps;
     if (h_long > 0) {
-        sort_unique_long_kernel<<<h_long, 256, 0, st>>>(d_tmp_off, d_long, d_tmp_ids, d_len);
+        if constexpr (sizeof(IdT) == 2) {
+            sort_unique_long_kernel<<<h_long, 256, 0, st>>>(d_tmp_off, d_long, d_tmp_ids, d_len);
+        } else {
+            const uint32_t words = (std::max<uint32_t>(n_genes, 1) + 31) / 32;
+            const uint32_t ctas = std::min<uint32_t>(h_long, 296);
+            seg_stop(tm, st);
+            SHK_CUDA(ctx, d_bitmaps.alloc((uint64_t)ctas * words));
+            seg_start(tm, st);
+            sort_unique_long_wide_kernel<<<ctas, 256, 0, st>>>(d_tmp_off, d_long, h_long, d_tmp_ids, d_len, d_bitmaps.p, words);
+        }
         ctx->launches += 1;
     }
     int rc = exclusive_scan(ctx, st, U32In{d_len}, U32Out{d_csr_off.p}, (uint64_t)n_set, d_tiles, d_csr_off.p + n_set);
@@ -867,11 +937,12 @@ static int finish_lists(shk_ctx *ctx, cudaStream_t st, uint32_t n_set, const uin
     seg_stop(tm, st);
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
     tot_ids = h_tot;
-    if (tot_ids >= 0x7FFFFFFFull)
+    // the reference counts ids in an int (bloomfilter.h:130); SHK_F_WIDE_IDS lifts that to the 32 bits of our offsets
+    if (tot_ids >= (sizeof(IdT) == 2 ? 0x7FFFFFFFull : 0xFFFFFFFFull))
         return fail(ctx, SHK_E_LIMIT, "total id count overflows the reference's int (bloomfilter.h:130)");
     SHK_CUDA(ctx, d_csr_ids.alloc(tot_ids));
     seg_start(tm, st);
-    finalize_lists_kernel<<<blocks_r, 256, 0, st>>>(d_tmp_off, d_tmp_ids, d_csr_off.p, n_set, d_csr_ids.p, d_entries.p);
+    finalize_lists_kernel<IdT><<<blocks_r, 256, 0, st>>>(d_tmp_off, d_tmp_ids, d_csr_off.p, n_set, d_csr_ids.p, d_entries.p);
     ctx->launches += 1;
     SHK_CUDA(ctx, cudaGetLastError());
     return SHK_OK;
@@ -971,10 +1042,10 @@ static int build_rank(shk_ctx *ctx, BuildState &bs)
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
     bs.n_genes = h_scalars[0];
     bs.n_set = h_scalars[1];
-    if (bs.n_genes > 65536)
+    if (bs.n_genes > 65536 && !ctx->wide_ids)
         return fail(ctx, SHK_E_LIMIT,
-                    "%u gene indices: the reference stores gene ids in 16 bits (small_vector.hpp:46), "
-                    "more than 65536 is not supported",
+                    "%u gene indices: the reference stores gene ids in 16 bits (small_vector.hpp:46), more than 65536 "
+                    "need SHK_F_WIDE_IDS (shark-b200 --wide-ids)",
                     bs.n_genes);
     if (bs.n_set >= 0x7FFFFFFFu || bs.n_windows >= 0xFFFFFFFFull)
         return fail(ctx, SHK_E_LIMIT, "too many set bits / windows");
@@ -1013,17 +1084,19 @@ count_ranks_kernel(const uint64_t *__restrict__ win, uint64_t total, uint32_t *c
 
 // Pass 2 (main.cpp:154-189 -> BF::add_to_kmer), BF::switch_mode(2), front table, info.
 // win_is_rank: the window array already holds ranks (sharded build, gathered from all shards).
-static int build_lists(shk_ctx *ctx, BuildState &bs, bool win_is_rank)
+template <class IdT>
+static int build_lists_t(shk_ctx *ctx, BuildState &bs, bool win_is_rank)
 {
+    constexpr bool kWide = sizeof(IdT) == 4;
     DeviceIndex &ix = ctx->index;
     cudaStream_t st = ctx->build_stream;
     const uint64_t total = bs.total;
     const uint32_t n_set = bs.n_set;
     int rc;
     DevBuf<uint32_t> d_cnt, d_fill, d_tmp_off, d_long;
-    DevBuf<uint16_t> d_tmp_ids;
+    DevBuf<IdT> d_tmp_ids;
     DevBuf<uint32_t> d_csr_off;
-    DevBuf<uint16_t> d_csr_ids;
+    DevBuf<IdT> d_csr_ids;
     DevBuf<uint64_t> d_entries;
     SHK_CUDA(ctx, d_cnt.alloc((uint64_t)n_set + 1));
     SHK_CUDA(ctx, d_fill.alloc((uint64_t)n_set + 1));
@@ -1049,11 +1122,11 @@ static int build_lists(shk_ctx *ctx, BuildState &bs, bool win_is_rank)
         ctx->launches += 1;
         rc = exclusive_scan(ctx, st, U32In{d_cnt.p}, U32Out{d_tmp_off.p}, (uint64_t)n_set, bs.tiles.p, d_tmp_off.p + n_set);
         if (rc) return rc;
-        fill_kernel<<<blocks_x, 256, 0, st>>>(bs.win.p, total, bs.rec_off.p, bs.n_rec, bs.nidx.p, d_tmp_off.p, d_fill.p,
-                                              d_tmp_ids.p);
+        fill_kernel<IdT><<<blocks_x, 256, 0, st>>>(bs.win.p, total, bs.rec_off.p, bs.n_rec, bs.nidx.p, d_tmp_off.p, d_fill.p,
+                                                   d_tmp_ids.p);
         ctx->launches += 1;
-        rc = finish_lists(ctx, st, n_set, d_tmp_off.p, d_tmp_ids.p, d_fill.p, d_long.p, bs.scalars.p + 4, bs.tiles.p, d_csr_off,
-                          d_csr_ids, d_entries, tot_ids, &bs.tm);
+        rc = finish_lists<IdT>(ctx, st, n_set, d_tmp_off.p, d_tmp_ids.p, d_fill.p, d_long.p, bs.scalars.p + 4, bs.tiles.p,
+                               d_csr_off, d_csr_ids, d_entries, tot_ids, &bs.tm, bs.n_genes);
         if (rc) return rc;
     } else {
         SHK_CUDA(ctx, cudaMemsetAsync(d_csr_off.p, 0, 4, st));
@@ -1061,13 +1134,18 @@ static int build_lists(shk_ctx *ctx, BuildState &bs, bool win_is_rank)
         SHK_CUDA(ctx, d_csr_ids.alloc(1));
     }
     bs.tm.stop(st);
-    // front table over the finished entries
+    // front table over the finished entries (16-bit ids only: with SHK_F_WIDE_IDS every read takes the
+    // reference-shaped path filter word -> sector rank -> entry -> CSR)
     ix.info.n_set_bits = n_set;
-    {
+    if constexpr (kWide) {
+        ix.fgeom = FrontGeom{};
+        ix.egeom = ExtGeom{};
+        ix.info.front_shift = 0, ix.info.front_entries = 0, ix.info.extend = 0, ix.info.ref_bases = total, ix.info.coarse_shift = 0;
+    } else {
         uint64_t need_tiles = (((ix.geom.bf_bits + 31) >> 5) + kScanTile - 1) / kScanTile + 2;
         DevBuf<uint32_t> d_tiles2;
         SHK_CUDA(ctx, d_tiles2.alloc(need_tiles));
-        rc = build_front(ctx, st, d_entries.p, d_csr_ids.p, d_tiles2.p, bs.scalars.p + 5,
+        rc = build_front(ctx, st, d_entries.p, reinterpret_cast<const uint16_t *>(d_csr_ids.p), d_tiles2.p, bs.scalars.p + 5,
                          ExtBuildInputs{bs.bases.p, bs.win.p, total}, &bs.tm);
         if (rc) return rc;
     }
@@ -1077,20 +1155,27 @@ static int build_lists(shk_ctx *ctx, BuildState &bs, bool win_is_rank)
 
     ix.entries = d_entries.release();
     ix.csr_off = d_csr_off.release();
-    ix.csr_ids = d_csr_ids.release();
+    if constexpr (kWide) ix.csr_ids32 = reinterpret_cast<uint32_t *>(d_csr_ids.release());
+    else ix.csr_ids = reinterpret_cast<uint16_t *>(d_csr_ids.release());
+    ix.info.id_bits = kWide ? 32u : 16u;
     ix.info.n_records = bs.n_rec;
     ix.info.n_genes = bs.n_genes;
     ix.info.n_set_bits = n_set;
     ix.info.tot_ids = tot_ids;
     ix.info.n_windows = bs.n_windows;
     ix.info.bf_bits = ix.geom.bf_bits;
-    ix.info.device_bytes = ix.geom.n_sectors * 32 + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * 2 +
+    ix.info.device_bytes = ix.geom.n_sectors * 32 + ((uint64_t)n_set + 1) * (8 + 4) + tot_ids * sizeof(IdT) +
                            ix.fgeom.n_entries * 16 * ix.fgeom.stride +
                            (ix.egeom.enabled ? ix.egeom.estream_words * 8 + ix.egeom.ref2_words * 8 + ix.egeom.coarse_words * 4 : 0);
     ix.info.build_ms = bs.tm.total();
     ix.info.build_wall_ms = (float)(wall_ms() - bs.t_wall0);
     ix.built = true;
     return SHK_OK;
+}
+
+static int build_lists(shk_ctx *ctx, BuildState &bs, bool win_is_rank)
+{
+    return ctx->wide_ids ? build_lists_t<uint32_t>(ctx, bs, win_is_rank) : build_lists_t<uint16_t>(ctx, bs, win_is_rank);
 }
 
 int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_rec)
@@ -1366,7 +1451,13 @@ int shard_finish(shk_ctx *ctx, const shk_shard_mem *all)
     return SHK_OK;
 }
 
-int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *ids)
+__global__ void __launch_bounds__(256) widen_ids_kernel(const uint16_t *__restrict__ in, uint64_t n, uint32_t *out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *ids, uint32_t *ids32)
 {
     DeviceIndex &ix = ctx->index;
     cudaStream_t st = ctx->build_stream;
@@ -1382,8 +1473,23 @@ int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *id
         SHK_CUDA(ctx, cudaStreamSynchronize(st));
     }
     if (off) SHK_CUDA(ctx, cudaMemcpyAsync(off, ix.csr_off, (n_set + 1) * 4, cudaMemcpyDeviceToHost, st));
-    if (ids && ix.info.tot_ids)
+    if (ids && ix.info.tot_ids) {
+        if (!ix.csr_ids) return fail(ctx, SHK_E_STATE, "the index holds 32-bit ids (SHK_F_WIDE_IDS): use shk_index_export_wide");
         SHK_CUDA(ctx, cudaMemcpyAsync(ids, ix.csr_ids, ix.info.tot_ids * 2, cudaMemcpyDeviceToHost, st));
+    }
+    if (ids32 && ix.info.tot_ids) {
+        if (ix.csr_ids32) {
+            SHK_CUDA(ctx, cudaMemcpyAsync(ids32, ix.csr_ids32, ix.info.tot_ids * 4, cudaMemcpyDeviceToHost, st));
+        } else {
+            DevBuf<uint32_t> d_w;
+            SHK_CUDA(ctx, d_w.alloc(ix.info.tot_ids));
+            widen_ids_kernel<<<(unsigned)((ix.info.tot_ids + 255) / 256), 256, 0, st>>>(ix.csr_ids, ix.info.tot_ids, d_w.p);
+            ctx->launches += 1;
+            SHK_CUDA(ctx, cudaGetLastError());
+            SHK_CUDA(ctx, cudaMemcpyAsync(ids32, d_w.p, ix.info.tot_ids * 4, cudaMemcpyDeviceToHost, st));
+            SHK_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+    }
     SHK_CUDA(ctx, cudaStreamSynchronize(st));
     return SHK_OK;
 }
@@ -1863,8 +1969,8 @@ int staged_switch_mode(shk_ctx *ctx, int new_mode, uint64_t *n_set_bits)
                                                                                         d_tmp_off.p, d_fill.p, d_tmp_ids.p);
                 ctx->launches += 1;
             }
-            rc = finish_lists(ctx, st, n_set, d_tmp_off.p, d_tmp_ids.p, d_fill.p, d_long.p, d_scalars.p + 4, d_tiles.p,
-                              d_csr_off, d_csr_ids, d_entries, tot_ids);
+            rc = finish_lists<uint16_t>(ctx, st, n_set, d_tmp_off.p, d_tmp_ids.p, d_fill.p, d_long.p, d_scalars.p + 4, d_tiles.p,
+                                        d_csr_off, d_csr_ids, d_entries, tot_ids);
             if (rc) return rc;
         } else {
             SHK_CUDA(ctx, cudaMemsetAsync(d_csr_off.p, 0, 4, st));
@@ -1872,6 +1978,7 @@ int staged_switch_mode(shk_ctx *ctx, int new_mode, uint64_t *n_set_bits)
         }
         ix.info = shk_index_info{};
         ix.info.n_set_bits = n_set;
+        ix.info.id_bits = 16;
         {
             const uint64_t need_tiles = (((ix.geom.bf_bits + 31) >> 5) + kScanTile - 1) / kScanTile + 2;
             DevBuf<uint32_t> d_tiles2;

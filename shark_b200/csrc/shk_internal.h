@@ -20,6 +20,7 @@ struct DeviceIndex {
     uint64_t *entries = nullptr;  // one per set bit
     uint32_t *csr_off = nullptr;  // n_set + 1
     uint16_t *csr_ids = nullptr;  // tot_ids
+    uint32_t *csr_ids32 = nullptr;  // tot_ids, instead of csr_ids with SHK_F_WIDE_IDS
     uint4 *front = nullptr;       // front table, fgeom.n_entries x 16 bytes (x 32 with anchors)
     FrontGeom fgeom{};
     // anchor-and-extend structures (only when info.extend; layouts in shk_device.cuh)
@@ -64,6 +65,8 @@ struct ReadKernelArgs {
     const uint64_t *entries;
     const uint32_t *csr_off;
     const uint16_t *csr_ids;
+    const uint32_t *csr_ids32;  // SHK_F_WIDE_IDS: 32-bit ids, wide entries, no front table (wide != 0)
+    uint32_t wide;
     FilterGeom geom;
     const uint4 *front;
     FrontGeom fgeom;
@@ -195,6 +198,7 @@ struct shk_ctx {
     std::atomic<uint64_t> d2h_bytes{0};    // result bytes copied back
     std::atomic<double> multi_per_read{-1.0};  // last chunk's multi entries per read: sizes the early read-back
     bool compact_results = false;          // SHK_F_COMPACT_RESULTS
+    bool wide_ids = false;                 // SHK_F_WIDE_IDS
     shk::PackControl pack;                 // split upload: feedback state of the packed share
     char err[512] = {0};
 };
@@ -215,7 +219,7 @@ int fail(shk_ctx *ctx, int code, const char *fmt, ...);
 // shk_index.cu
 int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_records);
 int index_alloc_front(shk_ctx *ctx);  // sizes fgeom from info and allocates the table
-int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *ids);
+int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *ids, uint32_t *ids32);
 int probe_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int64_t *rank, uint32_t *begin, uint32_t *len);
 int probe_bench_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, uint32_t reps, float *ms, uint64_t *hits);
 int random_sector_bench_device(shk_ctx *ctx, uint64_t n_loads, uint64_t span_bytes, uint64_t seed, float *ms);

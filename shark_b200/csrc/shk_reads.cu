@@ -20,9 +20,24 @@ namespace shk {
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 // Does a read's result fit the compact per-read form (one 16-bit word), or does it go to the `multi` list?
-__device__ __forceinline__ uint32_t multi_entries(uint32_t count, uint32_t payload)
+// (With 32-bit gene ids - SHK_F_WIDE_IDS - every reported read goes to the list.)
+__device__ __forceinline__ uint32_t multi_entries(uint32_t count, uint32_t payload, uint32_t wide = 0u)
 {
-    return (count >= 2u || (count == 1u && payload >= SHK_GENE_MULTI)) ? count : 0u;
+    return (count >= 2u || (count == 1u && (payload >= SHK_GENE_MULTI || wide))) ? count : 0u;
+}
+
+// Ids of a per-bit entry, for the warp-per-read kernels: list length and id number t (shk_device.cuh).
+template <bool WIDE>
+__device__ __forceinline__ uint32_t list_len(uint64_t e)
+{
+    return WIDE ? wide_entry_len(e) : entry_len(e);
+}
+template <bool WIDE>
+__device__ __forceinline__ uint32_t list_id(const ReadKernelArgs &a, uint64_t e, uint32_t ln, uint32_t t)
+{
+    if (WIDE) return ln == 1 ? entry_lo(e) : a.csr_ids32[entry_lo(e) + t];
+    if (t == 0) return entry_id0(e);
+    return ln == 2 ? entry_lo(e) : (uint32_t)a.csr_ids[entry_lo(e) + t];
 }
 
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
@@ -590,7 +605,7 @@ analyze_reads_kernel(const ReadKernelArgs a)
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kMidSlots = 128, kMidMaxGenes = 95, kMidWarps = 4;
 
-template <bool HAS_QUAL, int MOD>
+template <bool HAS_QUAL, int MOD, bool WIDE>
 __global__ void __launch_bounds__(kMidWarps * 32) analyze_mid_kernel(const ReadKernelArgs a)
 {
     __shared__ uint4 tables[kMidWarps][kMidSlots];  // {gene (0xFFFFFFFF = free), cov, hits, last}
@@ -635,7 +650,7 @@ __global__ void __launch_bounds__(kMidWarps * 32) analyze_mid_kernel(const ReadK
                 H &= H - 1;
                 const uint64_t el = shfl64(e, src);
                 const uint32_t epos = (uint32_t)c * 32u + (uint32_t)src;
-                const uint32_t ln = entry_len(el);
+                const uint32_t ln = list_len<WIDE>(el);
                 for (uint32_t t0 = 0; t0 < ln; t0 += 32) {
                     if (n_used > kMidMaxGenes) {  // at most 32 inserts follow: the table never fills up
                         overflow = true;
@@ -644,10 +659,7 @@ __global__ void __launch_bounds__(kMidWarps * 32) analyze_mid_kernel(const ReadK
                     const uint32_t t = t0 + (uint32_t)lane;
                     bool inserted = false;
                     if (t < ln) {
-                        uint32_t g;
-                        if (t == 0) g = entry_id0(el);
-                        else if (ln == 2) g = entry_lo(el);
-                        else g = a.csr_ids[entry_lo(el) + t];
+                        const uint32_t g = list_id<WIDE>(a, el, ln, t);
                         uint32_t s = (g * 0x9E3779B1u) >> 25;  // 7 bits
                         for (;;) {
                             uint32_t key = keys[4 * s];
@@ -727,7 +739,7 @@ __global__ void __launch_bounds__(kMidWarps * 32) analyze_mid_kernel(const ReadK
         }
         if (lane == 0) {
             a.rec[r] = make_uint2(count, payload);
-            if (multi_entries(count, payload)) atomicAdd(&a.tile_sums[r / kReadsPerTile], count);
+            if (multi_entries(count, payload, a.wide)) atomicAdd(&a.tile_sums[r / kReadsPerTile], count);
             assoc_total += count;
             kept_total += count ? 1u : 0u;
         }
@@ -747,7 +759,7 @@ __global__ void __launch_bounds__(kMidWarps * 32) analyze_mid_kernel(const ReadK
 // updated window by window in read order exactly as ReadAnalyzer.hpp:56-62,79-86 does, the
 // lanes sharing the (distinct) ids of one list.  Stamps make clearing unnecessary.
 // ---------------------------------------------------------------------------------------------
-template <bool HAS_QUAL, int MOD>
+template <bool HAS_QUAL, int MOD, bool WIDE>
 __global__ void __launch_bounds__(128) analyze_slow_kernel(const ReadKernelArgs a)
 {
     const int lane = threadIdx.x & 31;
@@ -793,12 +805,9 @@ __global__ void __launch_bounds__(128) analyze_slow_kernel(const ReadKernelArgs 
                 H &= H - 1;
                 const uint64_t el = shfl64(e, src);
                 const uint32_t epos = (uint32_t)c * 32u + (uint32_t)src;
-                const uint32_t ln = entry_len(el);
+                const uint32_t ln = list_len<WIDE>(el);
                 for (uint32_t t = lane; t < ln; t += 32) {
-                    uint32_t g;
-                    if (t == 0) g = entry_id0(el);
-                    else if (ln == 2) g = entry_lo(el);
-                    else g = a.csr_ids[entry_lo(el) + t];
+                    const uint32_t g = list_id<WIDE>(a, el, ln, t);
                     uint4 ent = table[g];
                     if (ent.x != stamp) {
                         // fresh map entry: `pos - 0` >= k for every window, so cov = k
@@ -860,7 +869,7 @@ __global__ void __launch_bounds__(128) analyze_slow_kernel(const ReadKernelArgs 
         }
         if (lane == 0) {
             a.rec[r] = make_uint2(count, payload);
-            if (multi_entries(count, payload)) atomicAdd(&a.tile_sums[r / kReadsPerTile], count);
+            if (multi_entries(count, payload, a.wide)) atomicAdd(&a.tile_sums[r / kReadsPerTile], count);
             assoc_total += count;
             kept_total += count ? 1u : 0u;
         }
@@ -890,7 +899,7 @@ scatter_assoc_kernel(const ReadKernelArgs a, uint64_t multi_cap, const uint32_t 
     const uint32_t r = blockIdx.x * kReadsPerTile + threadIdx.x;
     uint2 rc = make_uint2(0u, 0u);
     if (r < a.n_reads) rc = a.rec[r];
-    const uint32_t m = multi_entries(rc.x, rc.y);
+    const uint32_t m = multi_entries(rc.x, rc.y, a.wide);
     const uint32_t incl = warp_incl_scan(m, lane);
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
@@ -909,12 +918,30 @@ scatter_assoc_kernel(const ReadKernelArgs a, uint64_t multi_cap, const uint32_t 
     if (blockIdx.x == 0 && threadIdx.x == 0) a.counters->n_multi = *total;
 }
 
+// SHK_F_WIDE_IDS: there is no front table, every read goes to the middle path.
+__global__ void __launch_bounds__(256) all_reads_slow_kernel(const ReadKernelArgs a)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < a.n_reads) {
+        a.slow_list[r] = r;
+        a.rec[r] = make_uint2(0u, 0u);
+    }
+    if (r == 0) a.counters->n_slow = a.n_reads;
+}
+
 template <bool HAS_QUAL, int MOD>
 static void launch_typed(const ReadKernelArgs &a0, cudaStream_t st, unsigned tiles, unsigned slow_blocks, cudaEvent_t ev_ka)
 {
     // middle path: a grid-stride loop over the slow list (its length is only known on the device)
     const unsigned mid_blocks = std::min<unsigned>((tiles * kReadsPerTile + kMidWarps - 1) / kMidWarps, 148u * 8u);
     ReadKernelArgs a = a0;
+    if (a.wide) {
+        all_reads_slow_kernel<<<(a.n_reads + 255) / 256, 256, 0, st>>>(a);
+        if (ev_ka) cudaEventRecord(ev_ka, st);
+        analyze_mid_kernel<HAS_QUAL, MOD, true><<<mid_blocks, kMidWarps * 32, 0, st>>>(a);
+        analyze_slow_kernel<HAS_QUAL, MOD, true><<<slow_blocks, 128, 0, st>>>(a);
+        return;
+    }
     const uint32_t split = std::min(a.pack_first, a.n_reads);
     if (split > 0) {  // text part
         a.r0 = 0;
@@ -931,8 +958,8 @@ static void launch_typed(const ReadKernelArgs &a0, cudaStream_t st, unsigned til
         else analyze_reads_kernel<false, MOD, false, true><<<blocks, kFastThreads, 0, st>>>(a);
     }
     if (ev_ka) cudaEventRecord(ev_ka, st);
-    analyze_mid_kernel<HAS_QUAL, MOD><<<mid_blocks, kMidWarps * 32, 0, st>>>(a);
-    analyze_slow_kernel<HAS_QUAL, MOD><<<slow_blocks, 128, 0, st>>>(a);
+    analyze_mid_kernel<HAS_QUAL, MOD, false><<<mid_blocks, kMidWarps * 32, 0, st>>>(a);
+    analyze_slow_kernel<HAS_QUAL, MOD, false><<<slow_blocks, 128, 0, st>>>(a);
 }
 
 int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t multi_cap, cudaStream_t st, cudaEvent_t ev_k0,
@@ -955,7 +982,7 @@ int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t multi_ca
         scan_tile_sums_kernel<<<1, 1024, 0, st>>>(a.tile_base, tiles, a.tile_base + tiles);
         scatter_assoc_kernel<<<tiles, kReadsPerTile, 0, st>>>(a, multi_cap, a.tile_base + tiles);
         const uint32_t split = std::min(a.pack_first, a.n_reads);
-        launched = 4 + (split > 0 ? 1 : 0) + (split < a.n_reads ? 1 : 0);
+        launched = a.wide ? 5 : 4 + (split > 0 ? 1 : 0) + (split < a.n_reads ? 1 : 0);
         ctx->launches += launched;
     }
     else if (ev_ka) cudaEventRecord(ev_ka, st);

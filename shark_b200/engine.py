@@ -15,7 +15,8 @@ from . import capi
 
 class Shark:
     def __init__(self, k=17, c=0.6, bf_bits=1 << 33, min_quality=0, single=False, device=0, n_slots=2,
-                 max_reads_per_chunk=1 << 20, max_bytes_per_chunk=0, extend=None, host_pack=False, compact=False):
+                 max_reads_per_chunk=1 << 20, max_bytes_per_chunk=0, extend=None, host_pack=False, compact=False,
+                 wide_ids=False):
         """extend: None = automatic (anchor-and-extend when the front table is DRAM-sized), True /
         False = force it on / off (results are identical; tests run both).  compact: results stay in the
         compact form (gene16 / multi), shk_reads_collect does no per-read host work."""
@@ -23,7 +24,10 @@ class Shark:
         flags = 0 if extend is None else (capi.F_EXTEND_ON if extend else capi.F_EXTEND_OFF)
         if compact:
             flags |= capi.F_COMPACT_RESULTS
+        if wide_ids:  # 32-bit gene ids (more than 65536 reference records), an opt-in extension
+            flags |= capi.F_WIDE_IDS
         self.compact = bool(compact)
+        self.wide_ids = bool(wide_ids)
         permille = 0
         if host_pack:  # split upload: part of every chunk is packed to 3 bits per base by the host cores
             flags |= capi.F_HOST_PACK
@@ -184,14 +188,16 @@ class Shark:
         self._check(self.lib.shk_set_options(self.ctx, k, c, q, int(s)))
         self.k, self.c, self.min_quality, self.single = k, c, q, s
 
-    def export_index(self):
-        """-> (set_bit_pos uint64[n_set], offsets uint32[n_set+1], ids uint16[tot_ids])"""
+    def export_index(self, wide=None):
+        """-> (set_bit_pos uint64[n_set], offsets uint32[n_set+1], ids uint16[tot_ids]); ids uint32 through
+        shk_index_export_wide when wide (default: what the index holds)"""
         n, t = self.info.n_set_bits, self.info.tot_ids
+        wide = (self.info.id_bits == 32) if wide is None else wide
         pos = np.zeros(n, np.uint64)
         off = np.zeros(n + 1, np.uint32)
-        ids = np.zeros(t, np.uint16)
-        self._check(self.lib.shk_index_export(self.ctx, capi.ptr(pos) if n else None, capi.ptr(off),
-                                              capi.ptr(ids) if t else None))
+        ids = np.zeros(t, np.uint32 if wide else np.uint16)
+        fn = self.lib.shk_index_export_wide if wide else self.lib.shk_index_export
+        self._check(fn(self.ctx, capi.ptr(pos) if n else None, capi.ptr(off), capi.ptr(ids) if t else None))
         return pos, off, ids
 
     def index_views(self):

@@ -40,10 +40,10 @@ def test_struct_sizes():
     from shark_b200 import capi
     # must match the C layouts in include/shark_b200.h (x86-64 SysV)
     assert ctypes.sizeof(capi.Params) == 88
-    assert ctypes.sizeof(capi.IndexInfo) == 88
+    assert ctypes.sizeof(capi.IndexInfo) == 96
     assert ctypes.sizeof(capi.Assoc) == 8
     assert ctypes.sizeof(capi.ChunkResult) == 112
-    assert ctypes.sizeof(capi.IndexViews) == 64 + 64 + 88
+    assert ctypes.sizeof(capi.IndexViews) == 64 + 64 + 96
     assert ctypes.sizeof(capi.ShardMem) == 24 + 192 + 8 + 16
 
 
