@@ -436,7 +436,7 @@ def cli_leg(wl, wd, cores, n_total):
             return ka == kb and len(ka) > 0
 
         steady = None
-        if "first chunk packed" in stamps and "output written" in stamps and "index ready" in stamps:
+        if "output written" in stamps and "index ready" in stamps:
             # reads/s of the sample stage once the index exists and the pipeline runs (start-up excluded)
             span = stamps["output written"] - stamps["index ready"]
             steady = n_total / (span * 1e-3) if span > 0 else None

@@ -31,6 +31,8 @@
 #include <algorithm>
 #include <cerrno>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -71,9 +73,21 @@ template <class Alloc>
 struct Staging {
     uint8_t *p = nullptr;
     size_t cap = 0;
+    bool external = false;  // the bytes belong to someone else (a slot of the memory shared with the device process)
+    void use(void *mem, size_t bytes)
+    {
+        if (p && !external) Alloc::free(p);
+        p = (uint8_t *)mem;
+        cap = bytes;
+        external = true;
+    }
     void reserve(size_t n, size_t keep_bytes)
     {
         if (n <= cap) return;
+        if (external) {  // sized for the largest chunk by whoever provided it
+            fprintf(stderr, "shark: internal error: a chunk outgrew its shared buffer (%zu > %zu bytes)\n", n, cap);
+            abort();
+        }
         size_t want = cap ? cap : (1u << 20);
         while (want < n) want *= 2;
         uint8_t *q = (uint8_t *)Alloc::alloc(want);
@@ -86,7 +100,7 @@ struct Staging {
     }
     ~Staging()
     {
-        if (p) Alloc::free(p);
+        if (p && !external) Alloc::free(p);
     }
 };
 
@@ -109,9 +123,20 @@ struct Chunk {
     std::vector<ReadMeta> meta;
     std::vector<uint32_t> batch_start;  // read indices where a 50 000-read batch begins
     std::vector<std::shared_ptr<Block>> keep;
-    // results, copied out of the slot before the slot is reused (compact form)
-    std::vector<uint16_t> gene16;
-    std::vector<AssocPair> multi;
+    // results in the compact form: views (into the memory shared with the device process, or into the vectors
+    // below), valid until the chunk is recycled
+    const uint16_t *gene16 = nullptr;
+    const AssocPair *multi = nullptr;
+    size_t n_multi = 0;
+    std::vector<uint16_t> gene16_v;
+    std::vector<AssocPair> multi_v;
+    void results_from_vectors()
+    {
+        gene16 = gene16_v.data();
+        multi = multi_v.data();
+        n_multi = multi_v.size();
+    }
+    int slot = -1;  // shared slot this chunk's buffers live in (two-process CLI)
     uint32_t n = 0;
     uint64_t bytes = 0;
     bool last = false;
@@ -123,8 +148,9 @@ struct Chunk {
         meta.clear();
         batch_start.clear();
         keep.clear();
-        gene16.clear();
-        multi.clear();
+        gene16_v.clear();
+        multi_v.clear();
+        gene16 = nullptr, multi = nullptr, n_multi = 0;
         bulk = false;
         n = 0;
         bytes = 0;
@@ -704,8 +730,8 @@ private:
             }
         }
         size_t next_batch = (size_t)(std::upper_bound(ch.batch_start.begin(), ch.batch_start.end(), a) - ch.batch_start.begin());
-        auto m_it = std::lower_bound(ch.multi.begin(), ch.multi.end(), a,
-                                     [](const AssocPair &p, uint32_t r) { return p.read_idx < r; });
+        const AssocPair *m_end = ch.multi + ch.n_multi;
+        const AssocPair *m_it = std::lower_bound(ch.multi, m_end, a, [](const AssocPair &p, uint32_t r) { return p.read_idx < r; });
         for (uint32_t r = a; r < b; ++r) {
             if (next_batch < ch.batch_start.size() && ch.batch_start[next_batch] == r) {
                 previd = "", prevlen = 0;  // `string previd = ""` per ReadOutput call = per batch
@@ -723,7 +749,7 @@ private:
             if (g16 != kGeneMulti) {
                 line(g16);
             } else {
-                for (; m_it != ch.multi.end() && m_it->read_idx == r; ++m_it) line(m_it->gene_idx);
+                for (; m_it != m_end && m_it->read_idx == r; ++m_it) line(m_it->gene_idx);
             }
             // FASTQ once per read unless its name equals the previous printed id (ReadOutput.hpp:44-48)
             const bool same = prevlen == f.nlen1 && memcmp(previd, f.name1, prevlen) == 0;

@@ -22,10 +22,12 @@
 #include <getopt.h>
 #include <malloc.h>
 #include <signal.h>
+#include <sys/mman.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
@@ -287,48 +289,236 @@ private:
 
 }  // namespace
 
-// Detached tear-down.  When the last output byte has been written, what is left is the end of the process:
-// unmapping gigabytes of input, freeing the staging memory and - most of it - the driver taking the device
-// context apart, about half a second during which the results are already complete.  The work is therefore done
-// in a child process; the process the user started returns as soon as the child reports "output complete" and
-// leaves the child to finish on its own.  A child that fails, or ends without that report, has its exit status
-// passed on.  SHK_NO_DETACH=1 runs everything in the one process.
-int run(int argc, char *argv[], int done_fd);
+// ---------------------------------------------------------------------------------------------------------
+// Two processes.  The process the user starts is the HOST process: it scans the sample files, builds the packed
+// chunks, formats and writes the output.  Before it creates a single thread it forks the DEVICE process, which
+// owns everything CUDA: device contexts, index build, shk_reads_submit_packed / shk_reads_collect.  Why two:
+//   * CUDA start-up (0.4 - 2 s on these boxes) reserves and maps address space for most of that time with the
+//     process's memory-map lock held, and every page fault of every other thread of the SAME process waits for
+//     it - measured: not one chunk of the sample was packed before the context was up, although the packing
+//     threads had the cores to themselves.  In its own process the host pipeline runs at full speed meanwhile.
+//   * When the last output byte is written the host process returns; what is left - unmapping, freeing and the
+//     driver taking the device context apart, about half a second - is the device process's business, which
+//     finishes on its own ("detached tear-down").
+// The two share one anonymous mapping created before the fork: per chunk buffer a slot with the packed chunk
+// (offsets, code words, validity words; host -> device) and the compact results (one 16-bit word per read + the
+// list for ties; device -> host).  Two pipes carry the small messages.  SHK_ONE_PROCESS=1 runs the device side as
+// a thread of the host process instead (same protocol; for debuggers and sanitizers).
+// ---------------------------------------------------------------------------------------------------------
+struct SlotView {
+    uint32_t *off;
+    uint64_t *codes;
+    uint32_t *valid;
+    uint16_t *gene16;
+    shkhost::AssocPair *multi;
+};
+struct SharedLayout {
+    char *base = nullptr;
+    size_t n_slots = 0, slot_bytes = 0;
+    size_t off_bytes = 0, codes_bytes = 0, valid_bytes = 0, gene_bytes = 0, multi_cap = 0;
+    static size_t round(size_t n) { return (n + 4095) / 4096 * 4096; }
+    void plan(size_t slots, size_t max_reads, uint64_t max_bytes)
+    {
+        n_slots = slots;
+        const size_t groups = (size_t)((max_bytes + 31) / 32) + 2;
+        off_bytes = round((max_reads + 2) * 4);
+        codes_bytes = round(groups * 8 + 64);
+        valid_bytes = round(groups * 4 + 64);
+        gene_bytes = round((max_reads + 64) * 2);
+        multi_cap = max_reads;  // entries; a chunk with more ties than reads sends the rest through the pipe
+        slot_bytes = off_bytes + codes_bytes + valid_bytes + gene_bytes + round(multi_cap * sizeof(shkhost::AssocPair));
+    }
+    bool map()
+    {
+        void *m = mmap(nullptr, n_slots * slot_bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (m == MAP_FAILED) return false;
+        base = (char *)m;
+        return true;
+    }
+    SlotView slot(size_t i) const
+    {
+        char *p = base + i * slot_bytes;
+        SlotView v;
+        v.off = (uint32_t *)p;
+        v.codes = (uint64_t *)(p + off_bytes);
+        v.valid = (uint32_t *)(p + off_bytes + codes_bytes);
+        v.gene16 = (uint16_t *)(p + off_bytes + codes_bytes + valid_bytes);
+        v.multi = (shkhost::AssocPair *)(p + off_bytes + codes_bytes + valid_bytes + gene_bytes);
+        return v;
+    }
+};
 
-int main(int argc, char *argv[])
+enum : uint32_t { kMsgChunk = 1, kMsgEnd = 2, kMsgReady = 3, kMsgResult = 4, kMsgDone = 5 };
+struct Msg {  // both directions; well below PIPE_BUF, so a write is atomic
+    uint32_t kind = 0, slot = 0;
+    uint32_t n_reads = 0, n_genes = 0;
+    uint64_t n_bytes = 0, n_multi = 0, tail = 0;  // tail: multi entries that follow on the pipe (beyond the slot's capacity)
+};
+
+bool write_all(int fd, const void *p, size_t n)
 {
-    if (getenv("SHK_NO_DETACH") && atoi(getenv("SHK_NO_DETACH")) != 0) return run(argc, argv, -1);
-    int fds[2];
-    if (pipe(fds) != 0) return run(argc, argv, -1);
-    fflush(nullptr);
-    const pid_t child = fork();
-    if (child < 0) {
-        close(fds[0]);
-        close(fds[1]);
-        return run(argc, argv, -1);
+    const char *c = (const char *)p;
+    while (n) {
+        const ssize_t w = write(fd, c, n);
+        if (w <= 0) {
+            if (w < 0 && errno == EINTR) continue;
+            return false;
+        }
+        c += w;
+        n -= (size_t)w;
     }
-    if (child == 0) {
-        close(fds[0]);
-        return run(argc, argv, fds[1]);
+    return true;
+}
+bool read_all(int fd, void *p, size_t n)
+{
+    char *c = (char *)p;
+    while (n) {
+        const ssize_t r = read(fd, c, n);
+        if (r <= 0) {
+            if (r < 0 && errno == EINTR) continue;
+            return false;
+        }
+        c += r;
+        n -= (size_t)r;
     }
-    close(fds[1]);
-    char ok = 0;
-    ssize_t got;
-    do got = read(fds[0], &ok, 1);
-    while (got < 0 && errno == EINTR);
-    if (got == 1 && ok == 1) _exit(0);  // the outputs are complete; the child tidies up by itself
-    int status = 0;
-    while (waitpid(child, &status, 0) < 0 && errno == EINTR) {
-    }
-    if (WIFEXITED(status)) _exit(WEXITSTATUS(status));
-    if (WIFSIGNALED(status)) {  // die the way the child died, so that the caller sees the same thing
-        signal(WTERMSIG(status), SIG_DFL);
-        raise(WTERMSIG(status));
-    }
-    _exit(EXIT_FAILURE);
+    return true;
 }
 
-int run(int argc, char *argv[], int done_fd)
+// ---- the device side -----------------------------------------------------------------------------------------
+// Reference -> index on every GPU; then chunks as they are announced on `in`, results announced on `out`.
+void device_main(const Options &opt, const SharedLayout &shm, unsigned chunk_reads, uint64_t max_chunk_bytes, int in, int out)
+{
+    const int32_t min_quality = (int32_t)(unsigned char)opt.min_quality;
+    // the driver initialises every visible device: name only the ones this run uses (a second per GPU saved on
+    // an 8-GPU box); a CUDA_VISIBLE_DEVICES set by the user stands
+    {
+        std::string vis;
+        for (int g = 0; g < opt.gpus; ++g) vis += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
+    }
+    // FastaSplitter (FastaSplitter.hpp:42-54) -> concatenated records, parsed while the contexts come up.
+    // Unlike the reference (which ignores open failures and later segfaults) we fail cleanly.
+    std::vector<uint8_t> ref_bases;
+    std::vector<uint64_t> rec_off{0};
+    uint32_t n_records = 0;
+    std::thread ref_thread([&] {
+        shkhost::RecordSource ref(opt.fasta_path.c_str());
+        if (!ref.ok()) die("cannot open reference " + opt.fasta_path);
+        ref.start();
+        for (;;) {
+            const shkhost::Rec r = ref.peek();
+            if (r.status < 0) break;  // `while ((seq_len = kseq_read(seq)) >= 0)`, FastaSplitter.hpp:46
+            const void *zs = memchr(r.seq, 0, r.seq_len);  // `seq->seq.s` as a C string (FastaSplitter.hpp:49)
+            const size_t l = zs ? (size_t)((const char *)zs - r.seq) : r.seq_len;
+            ref_bases.insert(ref_bases.end(), r.seq, r.seq + l);
+            rec_off.push_back(ref_bases.size());
+            ++n_records;
+            ref.consume();
+        }
+        tstamp("reference parsed");
+    });
+    std::vector<shk_ctx *> ctxs((size_t)opt.gpus, nullptr);
+    for (int g = 0; g < opt.gpus; ++g) {
+        shk_params p;
+        memset(&p, 0, sizeof p);
+        p.k = opt.k;
+        p.c = opt.c;
+        p.bf_bits = opt.bf_size;
+        p.min_quality = min_quality;
+        p.single = opt.single ? 1 : 0;
+        p.device = g;
+        p.n_slots = 2;
+        p.max_reads_per_chunk = chunk_reads;
+        p.max_bytes_per_chunk = max_chunk_bytes;
+        p.flags = SHK_F_COMPACT_RESULTS | (opt.wide_ids ? SHK_F_WIDE_IDS : 0u);
+        if (shk_create(&p, &ctxs[g]) != SHK_OK) die(std::string("shk_create: ") + shk_last_error(nullptr));
+    }
+    tstamp("contexts created");
+    ref_thread.join();
+    shk_index_info info;
+    bool replicated = false;
+    if (!opt.load_index.empty()) {
+        SHK_TRY(ctxs[0], shk_index_load(ctxs[0], opt.load_index.c_str(), &info));
+        if (info.n_records != n_records)
+            die("index " + opt.load_index + " was built from " + std::to_string(info.n_records) + " records, " +
+                opt.fasta_path + " has " + std::to_string(n_records));
+    } else if (opt.sharded_build && opt.gpus > 1) {
+        SHK_TRY(ctxs[0], shk_index_build_sharded(ctxs.data(), (uint32_t)opt.gpus, ref_bases.data(), rec_off.data(), n_records, &info));
+        replicated = true;
+    } else {
+        SHK_TRY(ctxs[0], shk_index_build(ctxs[0], ref_bases.data(), rec_off.data(), n_records, &info));
+    }
+    tstamp("index built");
+    if (!opt.save_index.empty()) {
+        SHK_TRY(ctxs[0], shk_index_save(ctxs[0], opt.save_index.c_str()));
+        tstamp("index saved");
+    }
+    if (!replicated)
+        for (int g = 1; g < opt.gpus; ++g) SHK_TRY(ctxs[g], shk_index_replicate(ctxs[0], ctxs[g]));
+    tstamp("index ready");
+    std::vector<uint8_t>().swap(ref_bases);
+    Msg ready;
+    ready.kind = kMsgReady;
+    ready.n_genes = info.n_genes;
+    if (!write_all(out, &ready, sizeof ready)) _exit(EXIT_FAILURE);
+
+    struct InFlight {
+        uint32_t shm_slot;
+        int gpu;
+        uint32_t slot;
+    };
+    std::deque<InFlight> inflight;
+    const size_t max_inflight = (size_t)opt.gpus * 2;
+    uint64_t submitted = 0;
+    double t_submit = 0, t_collect = 0;
+    auto drain_one = [&] {
+        const InFlight f = inflight.front();
+        inflight.pop_front();
+        shk_chunk_result res;
+        const double t0 = shkhost::stage_now();
+        SHK_TRY(ctxs[f.gpu], shk_reads_collect(ctxs[f.gpu], f.slot, &res));
+        t_collect += shkhost::stage_now() - t0;
+        // the slot's result buffers are reused by its next submit: the compact results go to the shared slot
+        const SlotView v = shm.slot(f.shm_slot);
+        memcpy(v.gene16, res.gene16, (size_t)res.n_reads * 2);
+        const uint64_t in_slot = std::min<uint64_t>(res.n_multi, shm.multi_cap);
+        if (in_slot) memcpy(v.multi, res.multi, in_slot * sizeof(shk_assoc));
+        Msg m;
+        m.kind = kMsgResult;
+        m.slot = f.shm_slot;
+        m.n_reads = res.n_reads;
+        m.n_multi = res.n_multi;
+        m.tail = res.n_multi - in_slot;
+        if (!write_all(out, &m, sizeof m) || (m.tail && !write_all(out, res.multi + in_slot, m.tail * sizeof(shk_assoc)))) _exit(EXIT_FAILURE);
+    };
+    for (;;) {
+        Msg c;
+        if (!read_all(in, &c, sizeof c)) _exit(EXIT_FAILURE);  // the host process is gone
+        if (c.kind == kMsgEnd) break;
+        if (submitted == 0) tstamp("first chunk submitted");
+        if (inflight.size() == max_inflight) drain_one();
+        const int gpu = (int)(submitted % (uint64_t)opt.gpus);
+        const uint32_t slot = (uint32_t)((submitted / (uint64_t)opt.gpus) % 2);
+        const SlotView v = shm.slot(c.slot);
+        const double t0 = shkhost::stage_now();
+        SHK_TRY(ctxs[gpu], shk_reads_submit_packed(ctxs[gpu], slot, v.codes, v.valid, v.off, c.n_reads));
+        t_submit += shkhost::stage_now() - t0;
+        inflight.push_back({c.slot, gpu, slot});
+        ++submitted;
+    }
+    while (!inflight.empty()) drain_one();
+    tstamp("last chunk collected");
+    if (g_timing) fprintf(stderr, "[shark-b200/timing] device side: %llu chunks, submit %.0f ms, collect %.0f ms\n",
+                          (unsigned long long)submitted, t_submit * 1e3, t_collect * 1e3);
+    Msg d;
+    d.kind = kMsgDone;
+    write_all(out, &d, sizeof d);
+    if (getenv("SHK_CLEAN_EXIT")) {
+        for (auto *c : ctxs) shk_destroy(c);
+    }
+}
+
+int main(int argc, char *argv[])
 {
     // the record arrays and staging buffers of the pipeline are megabytes each and are recycled chunk after chunk:
     // keep them in the heap (fresh anonymous mappings would cost a page fault per 4 KiB every time)
@@ -347,114 +537,113 @@ int run(int argc, char *argv[], int done_fd)
         std::cerr << std::endl;
     }
     if (opt.n_threads > 1) shkhost::set_ingest_threads(opt.n_threads);  // -t: inflate threads for blocked-gzip samples
-    // the driver initialises every visible device: name only the ones this run uses (a second per GPU saved on
-    // an 8-GPU box); a CUDA_VISIBLE_DEVICES set by the user stands
-    {
-        std::string vis;
-        for (int g = 0; g < opt.gpus; ++g) vis += (g ? "," : "") + std::to_string(g);
-        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
-    }
-
-    // The sample files are scanned ahead from the start (into a bounded queue while the index is being built).
-    const int32_t min_quality = (int32_t)(unsigned char)opt.min_quality;
-    Batcher batcher(opt.sample1_path.c_str(), opt.paired ? opt.sample2_path.c_str() : nullptr, min_quality, pack_piece);
-    if (batcher.files_ok()) batcher.start();
-    else die("cannot open sample file(s)");
     const unsigned chunk_reads = std::max(1000u, opt.chunk_reads);
     // slot buffers are sized by this; a chunk is closed early when its text would not fit
     const uint64_t max_chunk_bytes = std::min<uint64_t>(0xF0000000ull, std::max<uint64_t>((uint64_t)chunk_reads * 640, 64ull << 20));
     const size_t n_bufs = (size_t)opt.gpus * 2 + 3;
+    // the sample files are opened (and mapped) before the device process exists, so that a missing file ends the
+    // run here; no thread runs yet
+    const int32_t min_quality = (int32_t)(unsigned char)opt.min_quality;
+    Batcher batcher(opt.sample1_path.c_str(), opt.paired ? opt.sample2_path.c_str() : nullptr, min_quality, pack_piece);
+    if (!batcher.files_ok()) die("cannot open sample file(s)");
+    SharedLayout shm;
+    shm.plan(n_bufs, chunk_reads, max_chunk_bytes);
+    if (!shm.map()) die("cannot map the chunk buffers");
+    int h2d[2], d2h[2];
+    if (pipe(h2d) != 0 || pipe(d2h) != 0) die("cannot create pipes");
+    signal(SIGPIPE, SIG_IGN);
+    fflush(nullptr);
+    const bool one_process = getenv("SHK_ONE_PROCESS") && atoi(getenv("SHK_ONE_PROCESS")) != 0;
+    pid_t child = -1;
+    std::thread device_thread;
+    if (one_process) {
+        device_thread = std::thread([&] { device_main(opt, shm, chunk_reads, max_chunk_bytes, h2d[0], d2h[1]); });
+    } else {
+        child = fork();  // before this process has any thread
+        if (child < 0) die("cannot fork the device process");
+        if (child == 0) {
+            close(h2d[1]);
+            close(d2h[0]);
+            device_main(opt, shm, chunk_reads, max_chunk_bytes, h2d[0], d2h[1]);
+            fflush(nullptr);
+            _exit(0);  // tear-down of the device context happens here, after the host process has returned
+        }
+        close(h2d[0]);
+        close(d2h[1]);
+    }
+    // the device process ended without finishing its job: pass its fate on
+    auto device_failed = [&]() -> int {
+        if (child > 0) {
+            int status = 0;
+            while (waitpid(child, &status, 0) < 0 && errno == EINTR) {
+            }
+            if (WIFEXITED(status) && WEXITSTATUS(status) != 0) return WEXITSTATUS(status);
+            if (WIFSIGNALED(status)) {
+                signal(WTERMSIG(status), SIG_DFL);
+                raise(WTERMSIG(status));
+            }
+        }
+        return EXIT_FAILURE;
+    };
+
+    // ---- host side: scanners -> batcher thread -> (device process) -> writer thread
+    batcher.start();
     std::vector<std::unique_ptr<Chunk>> pool;
-    Channel<Chunk *> free_q, ready_q, write_q;
+    Channel<Chunk *> free_q, write_q;
     for (size_t i = 0; i < n_bufs; ++i) {
         pool.emplace_back(new Chunk);
-        free_q.push(pool.back().get());
+        Chunk &c = *pool.back();
+        const SlotView v = shm.slot(i);
+        c.slot = (int)i;
+        c.off.use(v.off, shm.off_bytes);
+        c.codes.use(v.codes, shm.codes_bytes);
+        c.valid.use(v.valid, shm.valid_bytes);
+        free_q.push(&c);
     }
-    std::thread parser([&] {  // builds chunks while the device context and the index are being set up
-        uint64_t idx = 0;
+    std::atomic<uint64_t> chunks_sent{0};
+    std::atomic<bool> input_done{false};
+    std::thread parser([&] {  // builds chunks and announces them to the device process
         for (;;) {
             Chunk *ch = free_q.pop();
             const bool more = batcher.fill(*ch, chunk_reads, max_chunk_bytes);
             if (batcher.error()) die(batcher.error());
-            ch->index = idx++;
-            ch->last = !more;
-            ready_q.push(ch);
+            if (ch->n) {
+                Msg m;
+                m.kind = kMsgChunk;
+                m.slot = (uint32_t)ch->slot;
+                m.n_reads = ch->n;
+                m.n_bytes = ch->bytes;
+                chunks_sent.fetch_add(1);
+                if (!write_all(h2d[1], &m, sizeof m)) break;  // the device process is gone: the reader below reports it
+            } else {
+                ch->clear();
+                free_q.push(ch);
+            }
             if (!more) break;
         }
+        input_done.store(true);
+        Msg e;
+        e.kind = kMsgEnd;
+        write_all(h2d[1], &e, sizeof e);
+        tstamp("all chunks packed");
     });
 
-    // ---- reference: FastaSplitter (FastaSplitter.hpp:42-54) -> legend_ID + concatenated records.
-    // Unlike the reference (which ignores open failures and later segfaults) we fail cleanly.
+    // legend_ID (FastaSplitter.hpp:48): every record's name, in file order
     std::vector<std::string> legend_ID;
-    std::vector<uint8_t> ref_bases;
-    std::vector<uint64_t> rec_off{0};
     {
         shkhost::RecordSource ref(opt.fasta_path.c_str());
-        if (!ref.ok()) die("cannot open reference " + opt.fasta_path);
-        ref.start();
-        for (;;) {
+        if (ref.ok()) ref.start();  // (a reference that cannot be opened: the device process says so and ends the run)
+        for (; ref.ok();) {
             const shkhost::Rec r = ref.peek();
-            if (r.status < 0) break;  // `while ((seq_len = kseq_read(seq)) >= 0)`, FastaSplitter.hpp:46
-            // `seq->name.s` / `seq->seq.s` as C strings (FastaSplitter.hpp:48-49)
-            const void *zn = memchr(r.name, 0, r.name_len), *zs = memchr(r.seq, 0, r.seq_len);
+            if (r.status < 0) break;
+            const void *zn = memchr(r.name, 0, r.name_len);  // `seq->name.s` as a C string
             legend_ID.emplace_back(r.name, zn ? (size_t)((const char *)zn - r.name) : r.name_len);
-            const size_t l = zs ? (size_t)((const char *)zs - r.seq) : r.seq_len;
-            ref_bases.insert(ref_bases.end(), r.seq, r.seq + l);
-            rec_off.push_back(ref_bases.size());
             ref.consume();
         }
     }
-    tstamp("reference parsed");
-    std::vector<shk_ctx *> ctxs((size_t)opt.gpus, nullptr);
-    for (int g = 0; g < opt.gpus; ++g) {
-        shk_params p;
-        memset(&p, 0, sizeof p);
-        p.k = opt.k;
-        p.c = opt.c;
-        p.bf_bits = opt.bf_size;
-        p.min_quality = min_quality;
-        p.single = opt.single ? 1 : 0;
-        p.device = g;
-        p.n_slots = 2;
-        p.max_reads_per_chunk = chunk_reads;
-        p.max_bytes_per_chunk = max_chunk_bytes;
-        p.flags = SHK_F_COMPACT_RESULTS | (opt.wide_ids ? SHK_F_WIDE_IDS : 0u);
-        if (shk_create(&p, &ctxs[g]) != SHK_OK) die(std::string("shk_create: ") + shk_last_error(nullptr));
-    }
-    tstamp("contexts created");
-    shk_index_info info;
-    bool replicated = false;
-    if (!opt.load_index.empty()) {
-        SHK_TRY(ctxs[0], shk_index_load(ctxs[0], opt.load_index.c_str(), &info));
-        if (info.n_records != legend_ID.size())
-            die("index " + opt.load_index + " was built from " + std::to_string(info.n_records) + " records, " +
-                opt.fasta_path + " has " + std::to_string(legend_ID.size()));
-    } else if (opt.sharded_build && opt.gpus > 1) {
-        SHK_TRY(ctxs[0], shk_index_build_sharded(ctxs.data(), (uint32_t)opt.gpus, ref_bases.data(), rec_off.data(),
-                                                 (uint32_t)legend_ID.size(), &info));
-        replicated = true;
-    } else {
-        SHK_TRY(ctxs[0], shk_index_build(ctxs[0], ref_bases.data(), rec_off.data(), (uint32_t)legend_ID.size(), &info));
-    }
-    tstamp("index built");
-    if (!opt.save_index.empty()) {
-        SHK_TRY(ctxs[0], shk_index_save(ctxs[0], opt.save_index.c_str()));
-        tstamp("index saved");
-    }
-    pelapsed("Transcript file processed");
-    pelapsed("First switch performed");
-    pelapsed("BF created from transcripts (" + std::to_string(info.n_genes) + " genes)");
-    if (!replicated)
-        for (int g = 1; g < opt.gpus; ++g) SHK_TRY(ctxs[g], shk_index_replicate(ctxs[0], ctxs[g]));
-    pelapsed("Second switch performed");
-    tstamp("index ready");
-    std::vector<uint8_t>().swap(ref_bases);
-
-    // ---- sample stage: scanners -> batcher thread -> (this thread: submit / collect) -> writer thread
     const int fd1 = opt.out1_path.empty() ? -1 : open(opt.out1_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
     const int fd2 = (!opt.paired || opt.out2_path.empty()) ? -1 : open(opt.out2_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
     Writer writer(STDOUT_FILENO, fd1, fd2, legend_ID, opt.paired);
-
     std::thread writer_thread([&] {
         for (;;) {
             Chunk *ch = write_q.pop();
@@ -466,52 +655,46 @@ int run(int argc, char *argv[], int done_fd)
         writer.flush();
     });
 
-    struct InFlight {
-        Chunk *ch;
-        int gpu;
-        uint32_t slot;
-    };
-    std::deque<InFlight> inflight;
-    const size_t max_inflight = (size_t)opt.gpus * 2;
-    uint64_t submitted = 0, total_reads = 0;
-    double t_submit = 0, t_collect = 0, t_wait = 0;
-    auto drain_one = [&] {
-        InFlight f = inflight.front();
-        inflight.pop_front();
-        shk_chunk_result res;
-        const double t0 = shkhost::stage_now();
-        SHK_TRY(ctxs[f.gpu], shk_reads_collect(ctxs[f.gpu], f.slot, &res));
-        t_collect += shkhost::stage_now() - t0;
-        // the slot's result buffers are reused by its next submit: the compact results travel with the chunk
-        f.ch->gene16.assign(res.gene16, res.gene16 + res.n_reads);
-        const shkhost::AssocPair *mu = reinterpret_cast<const shkhost::AssocPair *>(res.multi);
-        f.ch->multi.assign(mu, mu + res.n_multi);
-        write_q.push(f.ch);
-    };
-    for (bool done = false; !done;) {
-        const double t_w0 = shkhost::stage_now();
-        Chunk *ch = ready_q.pop();
-        t_wait += shkhost::stage_now() - t_w0;
-        done = ch->last;
-        if (ch->n == 0) {
-            ch->clear();
-            free_q.push(ch);
+    // results, in the order the chunks were sent
+    uint64_t total_reads = 0, chunks_done = 0;
+    bool got_ready = false, got_done = false;
+    for (;;) {
+        Msg m;
+        if (!read_all(d2h[0], &m, sizeof m)) break;
+        if (m.kind == kMsgReady) {
+            got_ready = true;
+            pelapsed("Transcript file processed");
+            pelapsed("First switch performed");
+            pelapsed("BF created from transcripts (" + std::to_string(m.n_genes) + " genes)");
+            pelapsed("Second switch performed");
             continue;
         }
-        if (submitted == 0) tstamp("first chunk packed");
-        if (inflight.size() == max_inflight) drain_one();
-        const int gpu = (int)(submitted % (uint64_t)opt.gpus);
-        const uint32_t slot = (uint32_t)((submitted / (uint64_t)opt.gpus) % 2);
-        const double t_s0 = shkhost::stage_now();
-        SHK_TRY(ctxs[gpu], shk_reads_submit_packed(ctxs[gpu], slot, (const uint64_t *)ch->codes.p, (const uint32_t *)ch->valid.p,
-                                                   ch->offsets(), ch->n));
-        t_submit += shkhost::stage_now() - t_s0;
-        inflight.push_back({ch, gpu, slot});
-        ++submitted;
+        if (m.kind == kMsgDone) {
+            got_done = true;
+            break;
+        }
+        if (m.kind != kMsgResult || m.slot >= n_bufs) break;
+        Chunk *ch = pool[m.slot].get();
+        const SlotView v = shm.slot(m.slot);
+        ch->gene16 = v.gene16;
+        if (m.tail) {  // more ties than the slot holds: the whole list, slot part + pipe part, in the chunk's own vector
+            ch->multi_v.resize((size_t)m.n_multi);
+            memcpy(ch->multi_v.data(), v.multi, (size_t)(m.n_multi - m.tail) * sizeof(shkhost::AssocPair));
+            if (!read_all(d2h[0], ch->multi_v.data() + (m.n_multi - m.tail), (size_t)m.tail * sizeof(shkhost::AssocPair))) break;
+            ch->multi = ch->multi_v.data();
+        } else {
+            ch->multi = v.multi;
+        }
+        ch->n_multi = (size_t)m.n_multi;
         total_reads += ch->n;
+        ++chunks_done;
+        write_q.push(ch);
     }
-    while (!inflight.empty()) drain_one();
-    tstamp("last chunk collected");
+    if (!got_ready || !got_done) {
+        fflush(nullptr);
+        _exit(device_failed());
+    }
+    tstamp("last results received");
     parser.join();
     write_q.push(nullptr);
     writer_thread.join();
@@ -521,24 +704,21 @@ int run(int argc, char *argv[], int done_fd)
     if (g_timing) {
         const shkhost::StageTimes &st = shkhost::stage_times();
         fprintf(stderr, "[shark-b200/timing] reads %llu in %llu chunks, %d host threads\n", (unsigned long long)total_reads,
-                (unsigned long long)submitted, shkhost::host_threads());
+                (unsigned long long)chunks_done, shkhost::host_threads());
         fprintf(stderr, "[shark-b200/timing] batcher: waiting for the scanners %.0f ms, record arrays %.0f ms, offsets %.0f ms, packing %.0f ms, "
-                        "exact path %.0f ms; writer: formatting %.0f ms, output %.0f ms; main: submit %.0f ms, collect %.0f ms, waiting for chunks %.0f ms\n",
-                st.scan_wait * 1e3, st.flatten * 1e3, st.offsets * 1e3, st.pack * 1e3, st.exact * 1e3, st.format * 1e3, st.output * 1e3,
-                t_submit * 1e3, t_collect * 1e3, t_wait * 1e3);
+                        "exact path %.0f ms; writer: formatting %.0f ms, output %.0f ms\n",
+                st.scan_wait * 1e3, st.flatten * 1e3, st.offsets * 1e3, st.pack * 1e3, st.exact * 1e3, st.format * 1e3, st.output * 1e3);
     }
     pelapsed("Sample completed");
     pelapsed("Association done");
     fflush(nullptr);
-    if (done_fd >= 0) {  // everything a user waits for is done: the parent process returns now
-        const char ok = 1;
-        if (write(done_fd, &ok, 1) != 1) {
+    if (one_process) {
+        device_thread.join();
+        if (getenv("SHK_CLEAN_EXIT")) {
+            pool.clear();
+            return 0;
         }
-        close(done_fd);
     }
-    // the process ends here: the context, the mappings and the staging memory go with it
-    if (!getenv("SHK_CLEAN_EXIT")) _exit(0);
-    pool.clear();
-    for (auto *c : ctxs) shk_destroy(c);
-    return 0;
+    // the process ends here: its mappings and staging memory go with it; the device process tidies up by itself
+    _exit(0);
 }

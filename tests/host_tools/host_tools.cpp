@@ -215,7 +215,8 @@ static int ingest_bench(const char *f1, const char *f2, bool with_qual)
         const bool more = batcher.fill(ch[i], 1000000, 640000000ull);
         double b = now();
         t_fill += b - a;
-        ch[i].gene16.assign(ch[i].n, 0);
+        ch[i].gene16_v.assign(ch[i].n, 0);
+        ch[i].results_from_vectors();
         a = now();
         writer.write(ch[i]);
         t_write += now() - a;
@@ -253,15 +254,16 @@ static int pipe_check(const char *f1, const char *f2, int min_quality, unsigned 
             fprintf(stderr, "ERROR %s\n", batcher.error());
             return 3;
         }
-        ch.gene16.assign(ch.n, 0);
+        ch.gene16_v.assign(ch.n, 0);
         for (uint32_t r = 0; r < ch.n; ++r, ++global) {
-            if (global % 7 == 3) ch.gene16[r] = kGeneNone;
+            if (global % 7 == 3) ch.gene16_v[r] = kGeneNone;
             else if (global % 5 == 1) {
-                ch.gene16[r] = kGeneMulti;
-                ch.multi.push_back(AssocPair{r, 0});
-                ch.multi.push_back(AssocPair{r, 1});
+                ch.gene16_v[r] = kGeneMulti;
+                ch.multi_v.push_back(AssocPair{r, 0});
+                ch.multi_v.push_back(AssocPair{r, 1});
             }
         }
+        ch.results_from_vectors();
         if (ch.n) {
             uint64_t h = 0xCBF29CE484222325ull;
             auto eat = [&](const void *p, size_t n) {
