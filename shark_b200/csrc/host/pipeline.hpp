@@ -588,8 +588,49 @@ public:
         }
         populate_ = getenv("SHK_OUT_POPULATE") && atoi(getenv("SHK_OUT_POPULATE")) != 0;
     }
+    // Pre-faulting.  Writing a fresh file on tmpfs costs a page allocation per 4 KiB, at most ~7 GB/s on the B200
+    // host however many threads fault - the writer's whole budget.  The device needs a second or so to come up,
+    // during which nothing can be written yet: `expect[f]` > 0 (an upper bound of output f's size - the filtered
+    // FASTQ is never longer than its input) makes a few threads allocate that many bytes of the file ahead of the
+    // writer, so that the writer's own stores find the pages in place.  A touch is an atomic `or 0` on one byte
+    // per page: it allocates the page and can never change what the writer has already stored there.  The file is
+    // cut to its real length at the end (flush()).  Only for mapped outputs, and only if the file system has
+    // room for twice the bound.
+    void start_prefault(const uint64_t expect[3], int n_threads)
+    {
+        OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
+        for (int f = 0; f < 3; ++f) {
+            if (!expect[f] || !mappable_[f] || n_threads < 1) continue;
+            struct statfs sf;
+            if (fstatfs(outs[f]->fd(), &sf) != 0 || (uint64_t)sf.f_bavail * (uint64_t)sf.f_bsize < 2 * expect[f]) continue;
+            char *p = window(f, (size_t)expect[f]);  // grows the file and maps [pos, pos + expect)
+            if (!p) continue;
+            pre_[f].base = p;
+            pre_[f].len = expect[f];
+            for (int t = 0; t < n_threads; ++t)
+                pre_threads_.emplace_back([this, f] {
+                    constexpr uint64_t kStep = 4u << 20;
+                    const long page = sysconf(_SC_PAGESIZE);
+                    for (;;) {
+                        const uint64_t a = pre_[f].cursor.fetch_add(kStep);
+                        if (a >= pre_[f].len || pre_stop_.load()) return;
+                        const uint64_t b = std::min(pre_[f].len, a + kStep);
+                        if ((off_t)b <= win_[f].pos - win_[f].start0) continue;  // the writer is past this piece already
+                        for (uint64_t o = a; o < b; o += (uint64_t)page)
+                            __atomic_fetch_or((unsigned char *)pre_[f].base + o, 0, __ATOMIC_RELAXED);
+                    }
+                });
+        }
+    }
+    void stop_prefault()
+    {
+        pre_stop_.store(true);
+        for (auto &t : pre_threads_) t.join();
+        pre_threads_.clear();
+    }
     void flush()
     {
+        stop_prefault();
         OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
         for (int f = 0; f < 3; ++f) {
             outs[f]->flush();
@@ -796,7 +837,16 @@ private:
     struct Window {
         char *base = nullptr;  // mapping of [start, start + len)
         off_t start = 0, len = 0, pos = 0;  // pos = file offset of the next output byte
+        off_t start0 = 0;                   // file offset where the first window's data began (pre-faulting)
     };
+    struct Prefault {
+        char *base = nullptr;
+        uint64_t len = 0;
+        std::atomic<uint64_t> cursor{0};
+    };
+    Prefault pre_[3];
+    std::vector<std::thread> pre_threads_;
+    std::atomic<bool> pre_stop_{false};
     char *window(int f, size_t total)
     {
         OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
@@ -806,6 +856,7 @@ private:
             outs[f]->flush();
             w.pos = lseek(fd, 0, SEEK_CUR);
             if (w.pos < 0) return nullptr;
+            w.start0 = w.pos;
         }
         if (!w.base || w.pos + (off_t)total > w.start + w.len) {
             const off_t page = (off_t)sysconf(_SC_PAGESIZE), start = w.pos / page * page;

@@ -644,6 +644,15 @@ int main(int argc, char *argv[])
     const int fd1 = opt.out1_path.empty() ? -1 : open(opt.out1_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
     const int fd2 = (!opt.paired || opt.out2_path.empty()) ? -1 : open(opt.out2_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
     Writer writer(STDOUT_FILENO, fd1, fd2, legend_ID, opt.paired);
+    if (!(getenv("SHK_PREFAULT") && atoi(getenv("SHK_PREFAULT")) == 0)) {
+        // the filtered FASTQ of a FASTQ sample is never longer than the sample (pipeline.hpp, Writer::start_prefault)
+        auto plain_size = [](const std::string &path) -> uint64_t {
+            shkhost::MappedFile m(path.c_str());  // maps only plain regular files
+            return m.ok() && m.size() > 0 && m.data()[0] == '@' ? (uint64_t)m.size() : 0;
+        };
+        const uint64_t expect[3] = {0, fd1 >= 0 ? plain_size(opt.sample1_path) : 0, fd2 >= 0 ? plain_size(opt.sample2_path) : 0};
+        writer.start_prefault(expect, std::max(1, shkhost::host_threads() / (opt.paired ? 8 : 4)));
+    }
     std::thread writer_thread([&] {
         for (;;) {
             Chunk *ch = write_q.pop();

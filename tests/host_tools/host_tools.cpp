@@ -246,6 +246,14 @@ static int pipe_check(const char *f1, const char *f2, int min_quality, unsigned 
     const int fd1 = o1 ? open(o1, O_RDWR | O_CREAT | O_TRUNC, 0666) : -1;
     const int fd2 = (o2 && f2) ? open(o2, O_RDWR | O_CREAT | O_TRUNC, 0666) : -1;
     Writer<MallocAlloc> writer(STDOUT_FILENO, fd1, fd2, legend, f2 != nullptr);
+    if (getenv("PREFAULT")) {  // the CLI's pre-faulting of mapped outputs, with the input sizes as bounds (+ slack: FASTA records grow)
+        auto size_of = [](const char *p) -> uint64_t {
+            struct stat st;
+            return p && stat(p, &st) == 0 ? (uint64_t)st.st_size * 2 + 4096 : 0;
+        };
+        const uint64_t expect[3] = {0, fd1 >= 0 ? size_of(f1) : 0, fd2 >= 0 ? size_of(f2) : 0};
+        writer.start_prefault(expect, 3);
+    }
     Chunk<MallocAlloc> ch;
     uint64_t global = 0;
     for (;;) {

@@ -473,7 +473,7 @@ def test_pipeline_bulk_chunks_batches_and_dedup(tool, tmp_path, paired, q):
     if paired:
         _write_fastq(f2, rng, 120000, name_run=2, seed_names=10 ** 6)
     for chunk, max_bytes, env in ((1000000, 10 ** 9, {}), (30000, 10 ** 9, {"SHK_HOST_THREADS": "4"}), (50000, 10 ** 9, {"SHK_HOST_THREADS": "1"}),
-                                  (17777, 700000, {"SHK_HOST_THREADS": "3", "SHK_OUT": "map"}), (40000, 10 ** 9, {"SHK_NO_BULK": "1", "SHK_OUT": "write"})):
+                                  (17777, 700000, {"SHK_HOST_THREADS": "3", "SHK_OUT": "map", "PREFAULT": "1"}), (40000, 10 ** 9, {"SHK_NO_BULK": "1", "SHK_OUT": "write"})):
         chunks = _check_pipe(tool, tmp_path, f1, f2, q, chunk, max_bytes, env, want_bulk="SHK_NO_BULK" not in env)
         assert len(chunks) >= 120000 // chunk
 
@@ -511,7 +511,7 @@ def test_pipeline_hostile_inputs(tool, tmp_path, seed):
     open(f1, "wb").write(d1.encode("latin-1"))
     open(f2, "wb").write(d2.encode("latin-1"))
     for q in (0, 20):
-        _check_pipe(tool, tmp_path, f1, None, q, 700, env_extra={"SHK_SCAN_SEGMENT": "4096", "SHK_HOST_THREADS": "4", "SHK_OUT": "map"})
+        _check_pipe(tool, tmp_path, f1, None, q, 700, env_extra={"SHK_SCAN_SEGMENT": "4096", "SHK_HOST_THREADS": "4", "SHK_OUT": "map", "PREFAULT": "1"})
         _check_pipe(tool, tmp_path, f1, f2, q, 1000, env_extra={"SHK_SCAN_SEGMENT": "1000", "SHK_HOST_THREADS": "3"})
 
 
