@@ -854,7 +854,13 @@ static int build_front(shk_ctx *ctx, cudaStream_t st, const uint64_t *d_entries,
         ix.egeom.enabled = 1;
         uint32_t lg = 0;
         while (lg < 63 && (1ull << lg) < ix.geom.bf_bits) ++lg;
-        ix.egeom.coarse_shift = std::min<uint32_t>(lg > 28 ? lg - 28 : 0, ix.fgeom.shift);
+        // coarse filter: 2^28 bits (32 MB, L2-resident) unless the filter is smaller; SHK_COARSE_LOG2 (tuning) overrides
+        uint32_t coarse_log2 = 28;
+        if (const char *ev = getenv("SHK_COARSE_LOG2")) {
+            const int v = atoi(ev);
+            if (v >= 20 && v <= 32) coarse_log2 = (uint32_t)v;
+        }
+        ix.egeom.coarse_shift = std::min<uint32_t>(lg > coarse_log2 ? lg - coarse_log2 : 0, ix.fgeom.shift);
         ext_geometry(ix, xin.total);
         int rc = ext_alloc(ctx);
         if (rc) return rc;
