@@ -540,7 +540,13 @@ int main(int argc, char *argv[])
     const unsigned chunk_reads = std::max(1000u, opt.chunk_reads);
     // slot buffers are sized by this; a chunk is closed early when its text would not fit
     const uint64_t max_chunk_bytes = std::min<uint64_t>(0xF0000000ull, std::max<uint64_t>((uint64_t)chunk_reads * 640, 64ull << 20));
-    const size_t n_bufs = (size_t)opt.gpus * 2 + 3;
+    // chunk buffers: what the GPUs have in flight (2 each) + the writer's + enough for the host side to keep packing
+    // while the device process is still starting up (the device side drains them in a few milliseconds each)
+    size_t n_bufs = std::max<size_t>((size_t)opt.gpus * 2 + 3, 16);
+    if (const char *ev = getenv("SHK_CHUNK_BUFFERS")) {
+        const long v = atol(ev);
+        if (v >= (long)opt.gpus * 2 + 2 && v <= 256) n_bufs = (size_t)v;
+    }
     // the sample files are opened (and mapped) before the device process exists, so that a missing file ends the
     // run here; no thread runs yet
     const int32_t min_quality = (int32_t)(unsigned char)opt.min_quality;
