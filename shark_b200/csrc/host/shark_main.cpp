@@ -593,6 +593,14 @@ int main(int argc, char *argv[])
     };
 
     // ---- host side: scanners -> batcher thread -> (device process) -> writer thread
+    // The device process's start-up is the critical path of a run and is mostly one thread deep; the host side
+    // has a dozen threads that would happily take every core.  They run at a lower priority (threads created
+    // from here on inherit it), so that the scheduler serves the device process first.
+    if (!one_process && !(getenv("SHK_HOST_NICE") && atoi(getenv("SHK_HOST_NICE")) == 0)) {
+        errno = 0;
+        if (nice(getenv("SHK_HOST_NICE") ? atoi(getenv("SHK_HOST_NICE")) : 10) == -1 && errno != 0) {
+        }
+    }
     batcher.start();
     std::vector<std::unique_ptr<Chunk>> pool;
     Channel<Chunk *> free_q, write_q;
