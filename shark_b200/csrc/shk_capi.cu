@@ -340,21 +340,33 @@ static double now_secs()
 static double pack_fraction(shk_ctx *ctx, bool has_qual, uint64_t n)
 {
     if (ctx->params.host_pack_permille) return std::min(1.0, ctx->params.host_pack_permille / 1000.0);
-    static const double B = [] {
+    static const double B_max = [] {
         const char *ev = getenv("SHK_PCIE_GBS");
         const double v = ev ? atof(ev) : 0;
         return (v > 1 ? v : 53.0) * 1e9;
     }();
     PackControl &pc = ctx->pack;
+    if (pc.link <= 0) pc.link = B_max;
     const double t = now_secs();
     if (pc.last_submit > 0) {
         const double cycle = t - pc.last_submit;
         const double h = cycle - pc.last_pack_secs - pc.blocked_secs;
         if (cycle < 1.0 && h >= 0) pc.h0 = 0.7 * pc.h0 + 0.3 * std::min(h, 5e-3);  // (a long pause is not a cycle)
+        // The link rate is not a constant of the machine: GPUs behind one PCIe switch share an uplink, all ranks of
+        // a host share its memory system (measured: 53 GB/s for one rank alone, 20 GB/s per rank with eight).  The
+        // submitting thread sees which resource binds: blocked in shk_reads_collect for a good part of the cycle =
+        // the device side (the link) is behind -> the link is slower than assumed, pack more; hardly ever blocked =
+        // the host is behind -> assume a faster link, pack less.
+        if (cycle < 1.0 && cycle > 0) {
+            const double blocked = pc.blocked_secs / cycle;
+            if (blocked > 0.25) pc.link = std::max(4e9, pc.link * 0.92);
+            else if (blocked < 0.08) pc.link = std::min(B_max, pc.link * 1.04);
+        }
     }
     pc.last_submit = t;
     pc.blocked_secs = 0;
     pc.last_pack_secs = 0;
+    const double B = pc.link;
     const double b = has_qual ? 2.0 : 1.0;
     const double P = pc.rate > 0 ? pc.rate : 3e9 * host_pack_threads() / b;  // first chunk: a guess
     const double nn = (double)n;

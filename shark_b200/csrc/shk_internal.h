@@ -173,6 +173,7 @@ struct PackControl {
     double last_submit = 0;     // host clock of the previous packed submit
     double last_pack_secs = 0;  // packing time of that submit
     double blocked_secs = 0;    // time blocked on the device in shk_reads_collect since then
+    double link = 0;            // current estimate of this context's share of the host-to-device link, bytes/s
 };
 }
 
