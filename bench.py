@@ -780,7 +780,7 @@ def main():
                          "in (0, 1]")
     ap.add_argument("--value-form", default="packed", choices=["text", "packed"],
                     help="form in which the reads are resident in HBM for `value` (both are measured: value_by_form)")
-    ap.add_argument("--e2e-slots", type=int, default=3, help="chunks in flight in the e2e legs")
+    ap.add_argument("--e2e-slots", type=int, default=5, help="chunks in flight in the e2e legs")
     ap.add_argument("--index", default="", choices=["", "broadcast", "sharded", "both"],
                     help="N > 1: build on rank 0 + NCCL broadcast, the sharded P2P OR-merge build, or both (default) with an "
                          "equality check on every rank")

@@ -631,6 +631,7 @@ public:
     void flush()
     {
         stop_prefault();
+        stop_async();
         OutBuf *outs[3] = {&ssv_, &out1_, &out2_};
         for (int f = 0; f < 3; ++f) {
             outs[f]->flush();
@@ -672,8 +673,13 @@ public:
             if (mappable_[f] && (total >= (1u << 16) || win_[f].base)) dst[f] = window(f, total);
             mapped[f] = dst[f] != nullptr;
             if (!dst[f]) {
-                if (priv_[f].size() < total) priv_[f].resize(total);
-                dst[f] = priv_[f].data();
+                // private buffer, written out in order - by the background thread when the descriptor is never mapped
+                // (a pipe, a file opened write-only by the shell: the ssv on stdout), so that write(2) of this chunk
+                // overlaps the formatting of the next; two buffers per output take turns
+                std::vector<char> &buf = priv_[f][priv_turn_[f]];
+                wait_async(priv_job_[f][priv_turn_[f]]);
+                if (buf.size() < total) buf.resize(total);
+                dst[f] = buf.data();
             }
         }
         WorkPool::instance().run(n_ranges, [&](size_t t) {
@@ -696,8 +702,14 @@ public:
         for (int f = 0; f < 3; ++f) {
             const size_t total = at[f][n_ranges];
             if (!dst[f] || !total) continue;
-            if (mapped[f]) win_[f].pos += (off_t)total;
-            else outs[f]->put(dst[f], total);
+            if (mapped[f]) {
+                win_[f].pos += (off_t)total;
+            } else if (!mappable_[f]) {
+                priv_job_[f][priv_turn_[f]] = submit_async(outs[f], dst[f], total);
+                priv_turn_[f] ^= 1;
+            } else {
+                outs[f]->put(dst[f], total);
+            }
         }
         stage_times().output += stage_now() - t_o;
         // the name ReadOutput's `previd` holds at the end of this chunk, for the first read of the next one
@@ -882,7 +894,61 @@ private:
     Window win_[3];
     bool mappable_[3] = {false, false, false};  // a regular file opened read-write (a shared mapping needs both)
     bool populate_ = false;
-    std::vector<char> priv_[3];
+    std::vector<char> priv_[3][2];
+    int priv_turn_[3] = {0, 0, 0};
+    uint64_t priv_job_[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    // background write(2) of private buffers, in submission order
+    struct AsyncJob {
+        OutBuf *ob;
+        const char *p;
+        size_t n;
+    };
+    std::thread async_thread_;
+    std::mutex async_mu_;
+    std::condition_variable async_cv_;
+    std::deque<AsyncJob> async_q_;
+    uint64_t async_submitted_ = 0, async_done_ = 0;
+    bool async_stop_ = false;
+    uint64_t submit_async(OutBuf *ob, const char *p, size_t n)
+    {
+        std::unique_lock<std::mutex> lk(async_mu_);
+        if (!async_thread_.joinable())
+            async_thread_ = std::thread([this] {
+                std::unique_lock<std::mutex> lk2(async_mu_);
+                for (;;) {
+                    async_cv_.wait(lk2, [&] { return async_stop_ || !async_q_.empty(); });
+                    if (async_q_.empty()) return;
+                    const AsyncJob j = async_q_.front();
+                    async_q_.pop_front();
+                    lk2.unlock();
+                    j.ob->put(j.p, j.n);
+                    lk2.lock();
+                    ++async_done_;
+                    async_cv_.notify_all();
+                }
+            });
+        async_q_.push_back(AsyncJob{ob, p, n});
+        const uint64_t id = ++async_submitted_;
+        async_cv_.notify_all();
+        return id;
+    }
+    void wait_async(uint64_t id)
+    {
+        if (!id) return;
+        std::unique_lock<std::mutex> lk(async_mu_);
+        async_cv_.wait(lk, [&] { return async_done_ >= id; });
+    }
+    void stop_async()
+    {
+        {
+            std::unique_lock<std::mutex> lk(async_mu_);
+            async_cv_.wait(lk, [&] { return async_done_ >= async_submitted_; });
+            async_stop_ = true;
+            async_cv_.notify_all();
+        }
+        if (async_thread_.joinable()) async_thread_.join();
+        async_stop_ = false;
+    }
     std::string carry_;
     bool carry_valid_ = false;
 };
