@@ -588,6 +588,11 @@ public:
         }
         populate_ = getenv("SHK_OUT_POPULATE") && atoi(getenv("SHK_OUT_POPULATE")) != 0;
     }
+    ~Writer()
+    {
+        stop_prefault();
+        stop_async();
+    }
     // Pre-faulting.  Writing a fresh file on tmpfs costs a page allocation per 4 KiB, at most ~7 GB/s on the B200
     // host however many threads fault - the writer's whole budget.  The device needs a second or so to come up,
     // during which nothing can be written yet: `expect[f]` > 0 (an upper bound of output f's size - the filtered
