@@ -679,6 +679,14 @@ def run_workload(name, args, rank, world, local_rank, cores, dist, torch):
 
     h2d_step, d2h_step = sums.tolist()[3] / world, sums.tolist()[4] / world
     u = unit_of(wl)
+    # aggregate host-to-device rate of every e2e leg: beyond one GPU per host they converge on the host's ceiling
+    agg = {"text_split": h2d_step * world / (t_e2e / args.steps) / 1e9,
+           "text_plain": legs["plain"]["h2d"] * world / (t_plain / args.steps) / 1e9,
+           "packed": legs["packed"]["h2d"] * world / (t_e2e_packed / args.steps) / 1e9}
+    host_limit = {"h2d_gbs_all_gpus_by_leg": agg, "max_gbs": max(agg.values()), "ranks_on_host": world, "cores_per_rank": cores,
+                  "note": "every e2e leg moves its bytes out of ONE host's memory: past one GPU the legs converge on the same "
+                          "aggregate rate whatever the form of the reads - the host's ceiling, not the GPUs' and not NVLink's; "
+                          "fewer bytes per read (packed: 0.375 B per base) is what moves more reads through it"}
     rec = {
         "metric": "reads/sec", "value": total / t_value, "unit": u, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_value / args.steps * 1e3,
@@ -703,6 +711,7 @@ def run_workload(name, args, rank, world, local_rank, cores, dist, torch):
                        "d2h_bytes_per_step": int(legs["packed"]["d2h"]), "ms_per_step": t_e2e_packed / args.steps * 1e3,
                        "input": "pinned host buffers already in the packed form the CLI's batcher emits (packing NOT in "
                                 "the timed region): shk_reads_submit_packed"},
+        "host_limit": host_limit,
         "gpu_launches": int(res_v["launches"]), "roofline": roofline,
         "roofline_text": roofline_of(res_text, pm_text, "text") if value_form == "packed" else None,
         "probe": probe, "cpu_baseline": cpu_baseline, "parity_ranks": parity_ranks, "cli": cli, "clocks": clocks,

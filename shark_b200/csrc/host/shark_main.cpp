@@ -219,35 +219,20 @@ void tstamp(const char *what)
 
 using shkhost::kBatch;
 
-// Staging memory of the chunks (offsets and packed reads: 0.375 bytes per base).  CUDA start-up takes about a
-// second on these boxes: the chunks live in ordinary memory, so that scanning and packing run from the first
-// millisecond, concurrently with the creation of the device context and the index build (SHK_PINNED=1 switches
-// to the library's pinned allocator).
-struct PinnedAlloc {
-    static bool pinned()
-    {
-        static const bool p = getenv("SHK_PINNED") != nullptr;
-        return p;
-    }
+// Staging memory of the exact-path chunks (text, qualities); the packed chunks themselves live in the memory shared
+// with the device process.  Ordinary memory: the host process never calls into CUDA.
+struct HostAlloc {
     static void *alloc(size_t n)
     {
         void *q = nullptr;
-        if (pinned()) {
-            if (shk_alloc_pinned(&q, n) != SHK_OK) die(std::string("cannot allocate pinned memory: ") + shk_last_error(nullptr));
-        } else if (posix_memalign(&q, 4096, n) != 0) {
-            die("out of memory");
-        }
+        if (posix_memalign(&q, 4096, n) != 0) die("out of memory");
         return q;
     }
-    static void free(void *p)
-    {
-        if (pinned()) shk_free_pinned(p);
-        else ::free(p);
-    }
+    static void free(void *p) { ::free(p); }
 };
-using Chunk = shkhost::Chunk<PinnedAlloc>;
-using Batcher = shkhost::Batcher<PinnedAlloc>;
-using Writer = shkhost::Writer<PinnedAlloc>;
+using Chunk = shkhost::Chunk<HostAlloc>;
+using Batcher = shkhost::Batcher<HostAlloc>;
+using Writer = shkhost::Writer<HostAlloc>;
 static_assert(sizeof(shkhost::AssocPair) == sizeof(shk_assoc), "AssocPair mirrors shk_assoc");
 static_assert(shkhost::kGeneNone == SHK_GENE_NONE && shkhost::kGeneMulti == SHK_GENE_MULTI, "compact result markers");
 
