@@ -589,18 +589,25 @@ def run_workload(name, args, rank, world, local_rank, cores, dist, torch):
     def e2e_leg(mode):
         # K steps = K passes over the rank's chunks as ONE stream through the slots (a step boundary does not drain
         # the pipeline: a sample is a stream of chunks, not a sequence of separately flushed batches)
+        kms = [0.0, 0]
+
+        def seen(r):  # device time of the classification kernels of this chunk, while the copies of the next ones run
+            kms[0] += r["analyze_ms"]
+            kms[1] += 1
+
         if mode == "packed":
             sh.set_upload_mode(False)
-            run = lambda k: sh.analyze_chunks(packed * k, copy=False, on_result=lambda r: None, packed=True)  # noqa: E731
+            run = lambda k: sh.analyze_chunks(packed * k, copy=False, on_result=seen, packed=True)  # noqa: E731
         else:
             sh.set_upload_mode(False if mode == "plain" else (True if mode == "split" else float(mode)))
-            run = lambda k: sh.analyze_chunks(chunks * k, copy=False, on_result=lambda r: None)  # noqa: E731
+            run = lambda k: sh.analyze_chunks(chunks * k, copy=False, on_result=seen)  # noqa: E731
         if args.warmup:
             run(args.warmup)
         barrier()
         h0, dd0 = sh.h2d_bytes(), sh.d2h_bytes()
         t0 = time.perf_counter()
         sh.timer_start()
+        kms[0], kms[1] = 0.0, 0
         run(args.steps)
         t_dev = sh.timer_stop() * 1e-3
         # the split upload packs on the host BEFORE a chunk's first device operation: the device stopwatch would
@@ -610,7 +617,7 @@ def run_workload(name, args, rank, world, local_rank, cores, dist, torch):
         leg_stats[mode] = sh.upload_stats()
         t = max(t_dev, t_wall) if mode not in ("plain", "packed") else t_dev
         return dict(t=t, t_dev=t_dev, t_wall=t_wall, h2d=(sh.h2d_bytes() - h0) // max(args.steps, 1),
-                    d2h=(sh.d2h_bytes() - dd0) // max(args.steps, 1))
+                    d2h=(sh.d2h_bytes() - dd0) // max(args.steps, 1), kernels_ms_per_chunk=kms[0] / max(kms[1], 1))
 
     legs = {}
     for mode in ("plain", "packed", args.upload):
@@ -702,6 +709,7 @@ def run_workload(name, args, rank, world, local_rank, cores, dist, torch):
                 "upload": args.upload, "slots": sh.n_slots, "packed_share": leg_stats[args.upload][0],
                 "pack_gbases_per_s": leg_stats[args.upload][1], "ms_per_step": t_e2e / args.steps * 1e3,
                 "wall_ms_per_step": t_e2e_wall / args.steps * 1e3, "pack": "%s, %d threads" % capi_pack_info(),
+                "kernels_ms_per_chunk_while_copying": legs[args.upload]["kernels_ms_per_chunk"],
                 "h2d_gbs_per_gpu": h2d_step / (t_e2e / args.steps) / 1e9, "d2h_gbs_per_gpu": d2h_step / (t_e2e / args.steps) / 1e9,
                 "h2d_gbs_all_gpus": h2d_step * world / (t_e2e / args.steps) / 1e9,
                 "input": "read text (and qualities with -q) in pinned host memory"},
@@ -709,6 +717,7 @@ def run_workload(name, args, rank, world, local_rank, cores, dist, torch):
                       "ms_per_step": t_plain / args.steps * 1e3, "input": "read text in pinned host memory, no host packing"},
         "e2e_packed": {"value": total / t_e2e_packed, "unit": u, "h2d_bytes_per_step": int(legs["packed"]["h2d"]),
                        "d2h_bytes_per_step": int(legs["packed"]["d2h"]), "ms_per_step": t_e2e_packed / args.steps * 1e3,
+                       "kernels_ms_per_chunk_while_copying": legs["packed"]["kernels_ms_per_chunk"],
                        "input": "pinned host buffers already in the packed form the CLI's batcher emits (packing NOT in "
                                 "the timed region): shk_reads_submit_packed"},
         "host_limit": host_limit,
