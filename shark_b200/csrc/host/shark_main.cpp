@@ -537,6 +537,11 @@ int main(int argc, char *argv[])
     const int32_t min_quality = (int32_t)(unsigned char)opt.min_quality;
     Batcher batcher(opt.sample1_path.c_str(), opt.paired ? opt.sample2_path.c_str() : nullptr, min_quality, pack_piece);
     if (!batcher.files_ok()) die("cannot open sample file(s)");
+    {  // unlike the reference (which ignores open failures and later segfaults) a missing reference ends the run here
+        const int fd = open(opt.fasta_path.c_str(), O_RDONLY);
+        if (fd < 0) die("cannot open reference " + opt.fasta_path);
+        close(fd);
+    }
     SharedLayout shm;
     shm.plan(n_bufs, chunk_reads, max_chunk_bytes);
     if (!shm.map()) die("cannot map the chunk buffers");
