@@ -19,6 +19,12 @@
  * The restatement is written from the algorithm's description; data
  * structures differ from the reference on purpose (sparse sorted bit positions instead of
  * a 1 GiB sdsl bit vector; CSR instead of small_vector + select) - only semantics match.
+ *
+ * shko_index_build_wide is NOT a restatement of something the reference computes: it is this
+ * restatement with the reference's two narrow types widened (16-bit gene ids, `int` id total),
+ * the checker of the opt-in extension SHK_F_WIDE_IDS.  Inside the reference's
+ * limits it equals shko_index_build (tests/test_gpu_wide.py checks that too); beyond them its
+ * parity is "unpinned" by construction - the reference has no defined behaviour there.
  */
 #include <stdint.h>
 #include <stdlib.h>
