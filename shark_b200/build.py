@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libshark_b200.so")
 CLI = os.path.join(HERE, "shark-b200")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["shk_capi.cu", "shk_index.cu", "shk_reads.cu"]
+CU_SOURCES = ["shk_capi.cu", "shk_index.cu", "shk_reads.cu", "shk_bulk.cu"]
 CPP_SOURCES = ["shk_hostpack.cpp"]  # host code of the library (g++): read packing for the H2D link
 HOST_SOURCES = ["host/shark_main.cpp"]
 

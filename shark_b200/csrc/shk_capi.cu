@@ -233,6 +233,9 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     a.estream = ctx->index.estream;
     a.ref2 = ctx->index.ref2;
     a.coarse = ctx->index.coarse;
+    a.refr = ctx->index.refr;
+    a.ebits = ctx->index.ebits;
+    a.ref_total = ctx->index.egeom.total;
     a.coarse_rel = ctx->index.egeom.enabled ? ctx->index.fgeom.shift - ctx->index.egeom.coarse_shift : 0;
     a.coarse_key_shift = kFrontKeyShift + ctx->index.egeom.coarse_shift;
     a.n_genes = ctx->index.info.n_genes;
@@ -263,6 +266,7 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
 // one set per slot because the slots' kernels run concurrently.
 static int ensure_slow_table(shk_ctx *ctx)
 {
+    if (int rc = index_derive_bulk(ctx)) return rc;  // every path to a ready index ends here
     const uint64_t ng = std::max<uint32_t>(ctx->index.info.n_genes, 1);
     // as many concurrent exact-path warps as 128 MiB of tables allow, at most 4 per SM
     uint64_t slabs = std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (128ull << 20) / (ng * sizeof(uint4)));
@@ -574,6 +578,8 @@ void shk_destroy(shk_ctx *ctx)
     cudaFree(ctx->index.estream);
     cudaFree(ctx->index.ref2);
     cudaFree(ctx->index.coarse);
+    cudaFree(ctx->index.refr);
+    cudaFree(ctx->index.ebits);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);

@@ -717,6 +717,10 @@ static void free_index_arrays(DeviceIndex &ix)
     if (ix.estream) cudaFree(ix.estream);
     if (ix.ref2) cudaFree(ix.ref2);
     if (ix.coarse) cudaFree(ix.coarse);
+    if (ix.refr) cudaFree(ix.refr);
+    if (ix.ebits) cudaFree(ix.ebits);
+    ix.refr = nullptr;
+    ix.ebits = nullptr;
     ix.front = nullptr;
     ix.entries = nullptr;
     ix.csr_off = nullptr;
@@ -786,6 +790,9 @@ int index_alloc_front(shk_ctx *ctx)
     if (ix.estream) cudaFree(ix.estream);
     if (ix.ref2) cudaFree(ix.ref2);
     if (ix.coarse) cudaFree(ix.coarse);
+    if (ix.refr) cudaFree(ix.refr);
+    if (ix.ebits) cudaFree(ix.ebits);
+    ix.refr = nullptr, ix.ebits = nullptr;
     ix.front = nullptr;
     ix.estream = nullptr, ix.ref2 = nullptr, ix.coarse = nullptr;
     ix.egeom = ExtGeom{};
@@ -808,6 +815,52 @@ int index_alloc_front(shk_ctx *ctx)
         ext_geometry(ix, ix.info.ref_bases);
         return ext_alloc(ctx);
     }
+    return SHK_OK;
+}
+
+// refr / ebits: the reference and the E flags in the form the bulk classification kernel reads them (shk_bulk.cu) -
+// 32 positions per word like the packed reads, zero words on both sides.  Derived from estream, so every way an
+// index becomes ready (build, staged protocol, adopt + finalize, load, replicate, sharded build) gets them.
+__global__ void __launch_bounds__(256)
+derive_bulk_kernel(const uint64_t *__restrict__ estream, uint64_t total, uint64_t *refr, uint32_t *ebits)
+{
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // positions 32w .. 32w+31
+    if (w * 32 >= total) return;
+    uint64_t codes = 0;
+    uint32_t e = 0;
+    for (uint32_t h = 0; h < 2; ++h) {
+        const uint64_t t0 = w * 32 + h * 16;
+        if (t0 >= total) break;
+        const uint64_t word = estream[(t0 >> 4) + 1];
+        for (uint32_t i = 0; i < 16; ++i) {
+            const uint32_t nib = (uint32_t)(word >> (4 * i)) & 15u;
+            const uint32_t code = nib & 3u, raw = code ^ (code >> 1);  // A0 C1 G2 T3 -> A0 C1 T2 G3
+            codes |= (uint64_t)raw << (2 * (h * 16 + i));
+            e |= ((nib >> 2) & 1u) << (h * 16 + i);
+        }
+    }
+    refr[w + kDerivedPad] = codes;
+    ebits[w + kDerivedPad] = e;
+}
+
+int index_derive_bulk(shk_ctx *ctx)
+{
+    DeviceIndex &ix = ctx->index;
+    if (ix.refr) cudaFree(ix.refr);
+    if (ix.ebits) cudaFree(ix.ebits);
+    ix.refr = nullptr, ix.ebits = nullptr;
+    if (!ix.egeom.enabled || !ix.estream) return SHK_OK;
+    const uint64_t words = ix.egeom.total / 32 + 1 + kDerivedPad + kDerivedTail;
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.refr, words * 8));
+    SHK_CUDA(ctx, cudaMalloc((void **)&ix.ebits, words * 4));
+    cudaStream_t st = ctx->build_stream;
+    SHK_CUDA(ctx, cudaMemsetAsync(ix.refr, 0, words * 8, st));
+    SHK_CUDA(ctx, cudaMemsetAsync(ix.ebits, 0, words * 4, st));
+    const uint64_t n = (ix.egeom.total + 31) / 32;
+    if (n) derive_bulk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ix.estream, ix.egeom.total, ix.refr, ix.ebits);
+    SHK_CUDA(ctx, cudaGetLastError());
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->launches += 1;
     return SHK_OK;
 }
 

@@ -27,6 +27,11 @@ struct DeviceIndex {
     uint64_t *estream = nullptr;  // 4 bits per reference position: base code + two extension flags
     uint64_t *ref2 = nullptr;     // 2-bit packed reference, 32 bases per word (anchor verification)
     uint32_t *coarse = nullptr;   // coarse miss filter: one bit per 2^coarse_shift filter positions
+    // derived from estream whenever an index becomes ready (index_derive_bulk): the inputs of the bulk
+    // classification kernel (shk_bulk.cu).  Never serialised, broadcast or exported.
+    uint64_t *refr = nullptr;     // reference in the layout of the packed reads (base t at bits 2*(t&31) of word
+                                  // (t>>5)+kDerivedPad, codes A0 C1 T2 G3), zero words on both sides
+    uint32_t *ebits = nullptr;    // E[t] (shk_device.cuh) at bit t&31 of word (t>>5)+kDerivedPad
     ExtGeom egeom{};
     shk_index_info info{};
     bool built = false;
@@ -73,6 +78,9 @@ struct ReadKernelArgs {
     const uint64_t *estream;
     const uint64_t *ref2;
     const uint32_t *coarse;
+    const uint64_t *refr;       // bulk kernel: see DeviceIndex
+    const uint32_t *ebits;
+    uint64_t ref_total;         // reference bases
     uint32_t coarse_rel;        // fgeom.shift - coarse_shift: coarse index = bucket << rel | offset >> coarse_shift
     uint32_t coarse_key_shift;  // kFrontKeyShift + coarse_shift (the offset sits in the key)
     uint32_t n_genes;
@@ -103,6 +111,8 @@ struct ReadKernelArgs {
 };
 
 constexpr uint32_t kReadsPerTile = 128;  // one CTA of the fast kernel: 128 threads = 128 reads
+constexpr uint32_t kDerivedPad = 2;     // zero words in front of refr / ebits (a read may overhang the reference)
+constexpr uint32_t kDerivedTail = 4;    // and behind
 constexpr uint32_t kMaxFastLen = 1024;  // longer reads take the exact path (32 chunks x 32)
 
 struct Slot {
@@ -220,6 +230,7 @@ int fail(shk_ctx *ctx, int code, const char *fmt, ...);
 // shk_index.cu
 int index_build_device(shk_ctx *ctx, const uint8_t *ref_bases, const uint64_t *rec_off, uint32_t n_records);
 int index_alloc_front(shk_ctx *ctx);  // sizes fgeom from info and allocates the table
+int index_derive_bulk(shk_ctx *ctx);  // refr / ebits from estream (no-op without the extension structures)
 int index_export_device(shk_ctx *ctx, uint64_t *pos, uint32_t *off, uint16_t *ids, uint32_t *ids32);
 int probe_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, int64_t *rank, uint32_t *begin, uint32_t *len);
 int probe_bench_device(shk_ctx *ctx, const uint64_t *kmers, uint64_t n, uint32_t reps, float *ms, uint64_t *hits);
@@ -247,6 +258,9 @@ void shard_cuts_host(const uint64_t *rec_off, uint32_t n_rec, uint32_t n_shards,
 int launch_read_kernels(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st, cudaEvent_t ev_k0,
                         cudaEvent_t ev_ka, cudaEvent_t ev_k1);
 int launch_scatter(shk_ctx *ctx, const ReadKernelArgs &a, uint64_t assoc_cap, cudaStream_t st);
+// shk_bulk.cu: the bulk classification kernel for packed reads over the extension structures
+bool bulk_enabled();
+void launch_bulk_kernel(const ReadKernelArgs &a, cudaStream_t st, unsigned blocks);
 int fetch_cache_policies(shk_ctx *ctx);
 
 }  // namespace shk

@@ -11,20 +11,12 @@
 //   scatter_assoc_kernel   ordered (read_idx, gene_idx) list + keep flags
 #include "shk_internal.h"
 #include "shk_scan.cuh"
+#include "shk_reads.cuh"
 
 #include <algorithm>
 #include <cstdlib>
 
 namespace shk {
-
-constexpr uint32_t kFull = 0xFFFFFFFFu;
-
-// Does a read's result fit the compact per-read form (one 16-bit word), or does it go to the `multi` list?
-// (With 32-bit gene ids - SHK_F_WIDE_IDS - every reported read goes to the list.)
-__device__ __forceinline__ uint32_t multi_entries(uint32_t count, uint32_t payload, uint32_t wide = 0u)
-{
-    return (count >= 2u || (count == 1u && (payload >= SHK_GENE_MULTI || wide))) ? count : 0u;
-}
 
 // Ids of a per-bit entry, for the warp-per-read kernels: list length and id number t (shk_device.cuh).
 template <bool WIDE>
@@ -201,56 +193,6 @@ __device__ __forceinline__ void codes4(uint32_t w, uint32_t &code4, uint32_t &x)
     code4 = c4 ^ ((c4 >> 1) & 0x01010101u);
 }
 
-struct Mru4 {
-    uint32_t g0, c0, h0, l0, g1, c1, h1, l1, g2, c2, h2, l2, g3, c3, h3, l3;
-    uint32_t n;
-    bool overflow;
-    __device__ __forceinline__ void init()
-    {
-        g0 = g1 = g2 = g3 = 0xFFFFFFFFu;
-        c0 = c1 = c2 = c3 = h0 = h1 = h2 = h3 = l0 = l1 = l2 = l3 = 0u;
-        n = 0;
-        overflow = false;
-    }
-    // ReadAnalyzer.hpp:57-61 / 80-85.  A fresh std::map entry has last == 0 and `pos - 0 >= k`
-    // for every window, so its coverage starts at k.
-    __device__ __forceinline__ void hit(uint32_t g, uint32_t pos, uint32_t k)
-    {
-        if (g == g0) {
-            c0 += min(k, pos - l0);
-            h0 += 1;
-            l0 = pos;
-        } else if (g == g1) {
-            c1 += min(k, pos - l1);
-            h1 += 1;
-            l1 = pos;
-        } else {
-            other(g, pos, k);
-        }
-    }
-    __device__ __forceinline__ void other(uint32_t g, uint32_t pos, uint32_t k)
-    {
-        uint32_t c = k, h = 1;
-        if (g == g2) {
-            c = c2 + min(k, pos - l2);
-            h = h2 + 1;
-        } else if (g == g3) {
-            c = c3 + min(k, pos - l3);
-            h = h3 + 1;
-            g3 = g2, c3 = c2, h3 = h2, l3 = l2;
-        } else {
-            if (n == 4) {
-                overflow = true;
-                return;
-            }
-            ++n;
-            g3 = g2, c3 = c2, h3 = h2, l3 = l2;  // slot 3 was free
-        }
-        g2 = g1, c2 = c1, h2 = h1, l2 = l1;
-        g1 = g0, c1 = c0, h1 = h0, l1 = l0;
-        g0 = g, c0 = c, h0 = h, l0 = pos;
-    }
-};
 
 // ---------------------------------------------------------------------------------------------
 // Fast path, version 5 = version 4 with a branch-free common case for the table update.  The v4
@@ -526,48 +468,13 @@ analyze_reads_kernel(const ReadKernelArgs a)
             if (tab.overflow) {
                 slow = true;
             } else {
-                // argmax with ties (ReadAnalyzer.hpp:90-102), threshold and -s (ReadAnalyzer.hpp:104)
-                const uint32_t tg[4] = {tab.g0, tab.g1, tab.g2, tab.g3}, tc[4] = {tab.c0, tab.c1, tab.c2, tab.c3},
-                               th[4] = {tab.h0, tab.h1, tab.h2, tab.h3};
-                uint32_t maxc = 0, maxh = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if ((uint32_t)i < tab.n && (tc[i] > maxc || (tc[i] == maxc && th[i] > maxh))) {
-                        maxc = tc[i];
-                        maxh = th[i];
-                    }
-                }
-                uint32_t wg[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const bool is = (uint32_t)i < tab.n && tc[i] == maxc && th[i] == maxh;
-                    wg[i] = is ? tg[i] : 0xFFFFFFFFu;
-                    count += is ? 1u : 0u;
-                }
-                const bool pass = count > 0 && (double)maxc >= __dmul_rn(a.c, (double)len) && (!a.single || count == 1);
-                if (!pass) count = 0;
-                if (count == 1) {
-                    payload = min(min(wg[0], wg[1]), min(wg[2], wg[3]));
-                } else if (count >= 2) {
-                    // ascending gene order = std::map order: sort the (at most 4) winners
-#define SHK_CSWAP(x, y) { const uint32_t lo_ = min(wg[x], wg[y]), hi_ = max(wg[x], wg[y]); wg[x] = lo_; wg[y] = hi_; }
-                    SHK_CSWAP(0, 1) SHK_CSWAP(2, 3) SHK_CSWAP(0, 2) SHK_CSWAP(1, 3) SHK_CSWAP(1, 2)
-#undef SHK_CSWAP
-                    payload = atomicAdd(&a.counters->pool_used, count);
-                    if ((uint64_t)payload + count > a.pool_cap) {
-                        a.counters->pool_overflow = 1;
-                        payload = 0xFFFFFFFFu;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if ((uint32_t)i < count) a.pool[payload + i] = wg[i];
-                    }
-                }
+                finish_read(a, tab, len, count, payload);
             }
         }
         if (slow) {
             count = 0;
             payload = 0;
+            my_probes = 0, my_hits = 0;  // counted by the kernel that classifies the read
             a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
         }
         a.rec[r] = make_uint2(count, payload);
@@ -954,7 +861,8 @@ static void launch_typed(const ReadKernelArgs &a0, cudaStream_t st, unsigned til
         a.r0 = split;
         a.r1 = a.n_reads;
         const unsigned blocks = (a.n_reads - split + kReadsPerTile - 1) / kReadsPerTile;
-        if (a.estream) analyze_reads_kernel<false, MOD, true, true><<<blocks, kFastThreads, 0, st>>>(a);
+        if (a.estream && a.refr && bulk_enabled()) launch_bulk_kernel(a, st, blocks);
+        else if (a.estream) analyze_reads_kernel<false, MOD, true, true><<<blocks, kFastThreads, 0, st>>>(a);
         else analyze_reads_kernel<false, MOD, false, true><<<blocks, kFastThreads, 0, st>>>(a);
     }
     if (ev_ka) cudaEventRecord(ev_ka, st);
