@@ -38,14 +38,12 @@
 namespace shk {
 
 #ifndef SHK_BULK_MIN_BLOCKS
-#define SHK_BULK_MIN_BLOCKS 4
-#endif
-#ifndef SHK_BULK_ILP
-#define SHK_BULK_ILP 4
+#define SHK_BULK_MIN_BLOCKS 6
 #endif
 constexpr int kBulkWarps = 4;
 constexpr uint32_t kBulkComplex = 0xFFFFFFFEu;  // "ids of the previous window": a list of more than 2 ids
 constexpr int kBulkThreads = kBulkWarps * 32;
+constexpr uint32_t kBulkQueue = 64;  // ring: fewer than 32 entries wait while up to 32 are pushed
 static_assert(kBulkThreads == (int)kReadsPerTile, "one CTA of the bulk kernel = one scan tile");
 
 struct BulkWarp {
@@ -57,6 +55,90 @@ struct BulkWarp {
     uint32_t hit[32];              // per lane: looked-up windows that are set in the filter (plain lists)
     uint32_t res[32][33];          // [lane][pos in word]: ids of a hit, A | B << 16 (B == A: one id)
     uint32_t cplx[32];             // per lane: hits whose list has more than 2 ids (the owner walks the bucket itself)
+    // queue of table loads (windows that passed the coarse filter): bucket, key, owner lane | position << 8
+    uint32_t fq_bucket[kBulkQueue], fq_key[kBulkQueue];
+    uint16_t fq_who[kBulkQueue];
+    // owner state that is idle while the warp does lookups (registers there are resident CTAs)
+    uint32_t prev_a[32], prev_b[32], last_ev[32];  // ids and end of the last window with ids
+    uint32_t n_len[32], n_probes[32], n_hits[32], n_ext[32];
+};
+
+// The per-gene table of the owner (Mru4, shk_reads.cuh) with its two older genes in shared memory: they are touched only
+// when the read changes genes, and eight registers more per thread are one more resident CTA per SM.
+struct BulkCold {
+    uint32_t v[8][kBulkThreads];  // g2 c2 h2 l2 g3 c3 h3 l3, one column per thread
+};
+struct BulkTab {
+    uint32_t g0, c0, h0, l0, g1, c1, h1, l1;
+    uint32_t n;
+    bool overflow;
+    __device__ __forceinline__ void init(BulkCold &cold)
+    {
+        g0 = g1 = 0xFFFFFFFFu;
+        c0 = c1 = h0 = h1 = l0 = l1 = 0u;
+        n = 0;
+        overflow = false;
+        cold.v[0][threadIdx.x] = 0xFFFFFFFFu;
+        cold.v[4][threadIdx.x] = 0xFFFFFFFFu;
+    }
+    __device__ __forceinline__ void hit(BulkCold &cold, uint32_t g, uint32_t pos, uint32_t k)
+    {
+        if (g == g0) {
+            c0 += min(k, pos - l0);
+            h0 += 1;
+            l0 = pos;
+        } else if (g == g1) {
+            c1 += min(k, pos - l1);
+            h1 += 1;
+            l1 = pos;
+        } else {
+            other(cold, g, pos, k);
+        }
+    }
+    __device__ __forceinline__ void more(uint32_t g, uint32_t d)
+    {
+        if (g == g0) {
+            c0 += d, h0 += d, l0 += d;
+        } else {
+            c1 += d, h1 += d, l1 += d;
+        }
+    }
+    // Mru4::other with slots 2 and 3 in shared memory
+    __device__ __noinline__ void other(BulkCold &cold, uint32_t g, uint32_t pos, uint32_t k)
+    {
+        const uint32_t t = threadIdx.x;
+        uint32_t c = k, h = 1;
+        const uint32_t g2 = cold.v[0][t], c2 = cold.v[1][t], h2 = cold.v[2][t], l2 = cold.v[3][t];
+        if (g == g2) {
+            c = c2 + min(k, pos - l2);
+            h = h2 + 1;
+        } else {
+            if (g == cold.v[4][t]) {
+                c = cold.v[5][t] + min(k, pos - cold.v[7][t]);
+                h = cold.v[6][t] + 1;
+            } else {
+                if (n == 4) {
+                    overflow = true;
+                    return;
+                }
+                ++n;
+            }
+            cold.v[4][t] = g2, cold.v[5][t] = c2, cold.v[6][t] = h2, cold.v[7][t] = l2;
+        }
+        cold.v[0][t] = g1, cold.v[1][t] = c1, cold.v[2][t] = h1, cold.v[3][t] = l1;
+        g1 = g0, c1 = c0, h1 = h0, l1 = l0;
+        g0 = g, c0 = c, h0 = h, l0 = pos;
+    }
+    __device__ __forceinline__ Mru4 full(const BulkCold &cold) const
+    {
+        const uint32_t t = threadIdx.x;
+        Mru4 m;
+        m.g0 = g0, m.c0 = c0, m.h0 = h0, m.l0 = l0, m.g1 = g1, m.c1 = c1, m.h1 = h1, m.l1 = l1;
+        m.g2 = cold.v[0][t], m.c2 = cold.v[1][t], m.h2 = cold.v[2][t], m.l2 = cold.v[3][t];
+        m.g3 = cold.v[4][t], m.c3 = cold.v[5][t], m.h3 = cold.v[6][t], m.l3 = cold.v[7][t];
+        m.n = n, m.overflow = overflow;
+        return m;
+    }
 };
 
 // reverse the order of the 32 2-bit groups of a word
@@ -93,21 +175,6 @@ __device__ __forceinline__ uint32_t runs_ge(uint32_t prev, uint32_t cur, uint32_
     if (k > have) r &= r << (k - have);  // k - have <= have: the two runs overlap or touch
     return (uint32_t)(r >> 32);
 }
-// 32 positions t0 .. t0 + 31 of the derived reference arrays (t0 >= -32 * kDerivedPad)
-__device__ __forceinline__ uint64_t ref_codes(const uint64_t *refr, int64_t t0, uint64_t pol)
-{
-    const uint64_t u = (uint64_t)(t0 + 32 * (int64_t)kDerivedPad);
-    const uint32_t sh = 2u * ((uint32_t)u & 31u);
-    const uint64_t lo = ld_u64_hint(refr + (u >> 5), pol), hi = ld_u64_hint(refr + (u >> 5) + 1, pol);
-    return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
-}
-__device__ __forceinline__ uint32_t ref_flags(const uint32_t *ebits, int64_t t0, uint64_t pol)
-{
-    const uint64_t u = (uint64_t)(t0 + 32 * (int64_t)kDerivedPad);
-    const uint32_t lo = ld_u32_hint(ebits + (u >> 5), pol), hi = ld_u32_hint(ebits + (u >> 5) + 1, pol);
-    return __funnelshift_r(lo, hi, (uint32_t)u & 31u);
-}
-
 // A read's diagonal: read position q <-> reference position base + q (forward) or base - q (reverse strand).
 struct Diagonal {
     int64_t base;
@@ -115,26 +182,119 @@ struct Diagonal {
     bool on;
 };
 
+// The words of refr / ebits that cover word w of a read under a diagonal, as loaded (the shifts wait until the values
+// are used, so that the loads of the NEXT round can be issued before the lookups of this one).
+struct RefRaw {
+    uint64_t lo, hi;
+    uint32_t elo, ehi;
+};
+__device__ __forceinline__ bool diag_t0(const ReadKernelArgs &a, const Diagonal &dg, uint32_t w, int64_t &t0)
+{
+    t0 = dg.dir ? dg.base - 32 * (int64_t)w - 31 : dg.base + 32 * (int64_t)w;
+    // outside: the arrays have zero words around them, nothing there can match
+    return dg.on && t0 >= -32 * (int64_t)kDerivedPad && t0 <= (int64_t)a.ref_total;
+}
+__device__ __forceinline__ void ref_fetch(const ReadKernelArgs &a, const Diagonal &dg, uint32_t w, uint32_t k, uint64_t pol,
+                                          RefRaw &rw)
+{
+    int64_t t0;
+    if (!diag_t0(a, dg, w, t0)) return;
+    const uint64_t u = (uint64_t)(t0 + 32 * (int64_t)kDerivedPad), ue = dg.dir ? u + k : u;
+    rw.lo = ld_u64_hint(a.refr + (u >> 5), pol);
+    rw.hi = ld_u64_hint(a.refr + (u >> 5) + 1, pol);
+    rw.elo = ld_u32_hint(a.ebits + (ue >> 5), pol);
+    rw.ehi = ld_u32_hint(a.ebits + (ue >> 5) + 1, pol);
+}
 // Word w of a read under a diagonal: M = positions whose base is valid and equals the reference base (its complement
 // on the reverse strand), E = the same-list flag of the window ENDING at each position (shk_device.cuh: forward E[e];
 // reverse strand: the read window ending at q is the reference window ending at e = base - q + k - 1 and the window
 // before it ends at e + 1, so the flag is E[e + 1]).
 __device__ __forceinline__ void match_word(const ReadKernelArgs &a, const Diagonal &dg, uint32_t w, uint64_t C, uint32_t V,
-                                           uint32_t k, uint64_t pol, uint32_t &M, uint32_t &E)
+                                           uint32_t k, const RefRaw &rw, uint32_t &M, uint32_t &E)
 {
     M = 0u;
     E = 0u;
-    if (!dg.on || V == 0u) return;
-    const int64_t t0 = dg.dir ? dg.base - 32 * (int64_t)w - 31 : dg.base + 32 * (int64_t)w;
-    if (t0 < -32 * (int64_t)kDerivedPad || t0 > (int64_t)a.ref_total) return;  // the arrays have zero words around them
-    uint64_t R = ref_codes(a.refr, t0, pol);
+    int64_t t0;
+    if (!diag_t0(a, dg, w, t0) || V == 0u) return;
+    const uint64_t u = (uint64_t)(t0 + 32 * (int64_t)kDerivedPad);
+    const uint32_t sh = 2u * ((uint32_t)u & 31u);
+    uint64_t R = sh ? (rw.lo >> sh) | (rw.hi << (64u - sh)) : rw.lo;
     if (dg.dir) {
         R = pair_reverse(R) ^ 0xAAAAAAAAAAAAAAAAULL;  // complement of A0 C1 T2 G3 = code ^ 2
-        E = __brev(ref_flags(a.ebits, t0 + (int64_t)k, pol));
+        E = __brev(__funnelshift_r(rw.elo, rw.ehi, ((uint32_t)u + k) & 31u));
     } else {
-        E = ref_flags(a.ebits, t0, pol);
+        E = __funnelshift_r(rw.elo, rw.ehi, (uint32_t)u & 31u);
     }
     M = V & ~nonzero_pairs(C ^ R);
+}
+
+// slots and anchors of a front-table entry (one 32-byte sector) in one load
+__device__ __forceinline__ void ld_front_pair(const uint4 *p, uint64_t pol, uint4 &slots, uint4 &anchors)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(slots.x), "=r"(slots.y), "=r"(slots.z), "=r"(slots.w), "=r"(anchors.x), "=r"(anchors.y),
+                   "=r"(anchors.z), "=r"(anchors.w)
+                 : "l"(p), "l"(pol));
+}
+
+// The k-mer of the window ENDING at position p of the current word (previous word : current word, LSB first), in the
+// reference's code (A0 C1 G2 T3, kmer_utils.hpp:29-41): forward with the first base in the most significant group
+// (kmer_utils.hpp:73-75) and its reverse complement (kmer_utils.hpp:47-55).
+__device__ __forceinline__ void window_kmers(uint64_t lo, uint64_t hi, uint32_t p, uint32_t k, uint64_t kmask2, uint64_t &fwd,
+                                             uint64_t &rcm)
+{
+    const uint32_t s2 = 2u * (33u + p - k);  // >= 4
+    uint64_t X = s2 < 64u ? (lo >> s2) | (hi << (64u - s2)) : hi >> (s2 - 64u);
+    X &= kmask2;
+    X ^= (X >> 1) & 0x5555555555555555ULL;  // A0 C1 T2 G3 -> A0 C1 G2 T3
+    rcm = ~X & kmask2;                       // LSB-first complement = the reverse complement, first base on top
+    fwd = pair_reverse(X) >> (64u - 2u * k);
+}
+
+// One queued table load per lane: the position's ids go back to the owner of the window; a plain hit of an owner that
+// is looking for a diagonal is verified against the reference (the slot's anchor names a reference window with the
+// same filter bit; it gives a diagonal only if that window IS the read's window, either strand).
+#ifndef SHK_BULK_SERVE_ATTR
+#define SHK_BULK_SERVE_ATTR __forceinline__
+#endif
+template <int MOD>
+__device__ SHK_BULK_SERVE_ATTR void serve_queue(const ReadKernelArgs &a, BulkWarp &sh, uint32_t slot, bool valid, uint32_t want,
+                                            uint32_t k, uint64_t kmask2, uint64_t pol_front, uint64_t pol_last)
+{
+    if (!valid) return;
+    const uint32_t bucket = sh.fq_bucket[slot], kb = sh.fq_key[slot], who = sh.fq_who[slot];
+    const uint32_t ow = who & 31u, p = who >> 8;
+    const bool wanted = (want >> ow) & 1u;
+    uint4 qq, anc = make_uint4(0u, 0u, 0u, 0u);
+    if (wanted) ld_front_pair(a.front + (uint64_t)bucket * 2u, pol_front, qq, anc);  // the anchors sit in the same sector
+    else qq = ld_front(a.front + (uint64_t)bucket * 2u, pol_front);
+    uint32_t A, B, cur = bucket;
+    for (;;) {  // the position's two smallest ids (slot - key; shk_device.cuh), along the bucket's chain
+        const uint32_t d0 = qq.x - kb, d1 = qq.y - kb, d2 = qq.z - kb, d3 = qq.w - kb;
+        const uint32_t lo01 = min(d0, d1), hi01 = max(d0, d1), lo23 = min(d2, d3), hi23 = max(d2, d3);
+        A = min(lo01, lo23);
+        B = min(max(lo01, lo23), min(hi01, hi23));
+        if (A < kFrontLim || (int32_t)qq.w >= -1) break;
+        cur = qq.w & 0x7FFFFFFFu;
+        qq = ld_front(a.front + (uint64_t)cur * 2u, pol_front);
+    }
+    if (A >= kFrontLim) return;
+    if (A < 0x10000u && (B < 0x10000u || B >= kFrontLim)) {  // a list of one or two ids
+        sh.res[ow][p] = A | ((B < 0x10000u ? B : A) << 16);
+        atomicOr(&sh.hit[ow], 1u << p);
+        if (wanted) {
+            if (cur != bucket) anc = ld_front(a.front + (uint64_t)cur * 2u + 1u, pol_front);
+            const uint32_t sa = A + kb;
+            const uint32_t e = qq.x == sa ? anc.x : (qq.y == sa ? anc.y : (qq.z == sa ? anc.z : anc.w));
+            const uint64_t rk = ref2_window(a.ref2, e, kmask2, pol_last);
+            uint64_t fwd, rcm;
+            window_kmers(sh.cprev[ow], sh.ccur[ow], p, k, kmask2, fwd, rcm);
+            if (rk == fwd) atomicMin(&sh.cand[ow], ((unsigned long long)p << 33) | e);
+            else if (rk == rcm) atomicMin(&sh.cand[ow], ((unsigned long long)p << 33) | (1ULL << 32) | e);
+        }
+    } else {
+        atomicOr(&sh.cplx[ow], 1u << p);  // 3 ids or more
+    }
 }
 
 template <int MOD>
@@ -142,6 +302,7 @@ __global__ void __launch_bounds__(kBulkThreads, SHK_BULK_MIN_BLOCKS)
 analyze_bulk_kernel(const ReadKernelArgs a)
 {
     __shared__ BulkWarp shared[kBulkWarps];
+    __shared__ BulkCold cold;
     const int lane = threadIdx.x & 31;
     BulkWarp &sh = shared[threadIdx.x >> 5];
     const uint32_t r = a.r0 + blockIdx.x * kBulkThreads + threadIdx.x;
@@ -152,7 +313,7 @@ analyze_bulk_kernel(const ReadKernelArgs a)
     const uint64_t kmask2 = (1ULL << (2 * k)) - 1ULL;
     const uint32_t fshift = a.fgeom.shift, fmask = a.fgeom.off_mask;
 
-    uint32_t count = 0, payload = 0, my_probes = 0, my_hits = 0, my_ext = 0, my_loads = 0;
+    uint32_t count = 0, payload = 0, my_loads = 0;
     bool slow = false;
     uint32_t n = 0, src0 = 0;
     if (r < a.r1) {
@@ -166,13 +327,23 @@ analyze_bulk_kernel(const ReadKernelArgs a)
     }
     const uint32_t my_words = (n + 31u) >> 5;
     const uint32_t rounds = __reduce_max_sync(kFull, my_words);
+    // the read's words are loaded one round ahead: round w funnels words gi0 + w and gi0 + w + 1 of the packed stream
+    const uint32_t gi0 = src0 >> 5, sb = src0 & 31u;
+    uint64_t c_lo = 0, c_hi = 0;
+    uint32_t v_lo = 0, v_hi = 0;
+    if (my_words) {
+        c_lo = ld_u64_hint(a.pcodes + gi0, pol_first), c_hi = ld_u64_hint(a.pcodes + gi0 + 1, pol_first);
+        v_lo = ld_text_word(a.pvalid + gi0, pol_first), v_hi = ld_text_word(a.pvalid + gi0 + 1, pol_first);
+    }
 
-    Mru4 tab;
-    tab.init();
+    BulkTab tab;
+    tab.init(cold);
     Diagonal dg{0, 0u, false};
-    uint64_t prevC = 0;
-    uint32_t prevV = 0, prevM = 0, prevDtop = 0, len = 0;
-    uint32_t prevA = kFrontEmpty, prevB = kFrontEmpty, last_ev = 0xFFFFFFF0u;  // ids and end of the last window with ids
+    RefRaw rw{0, 0, 0u, 0u};
+    sh.ccur[lane] = 0;  // (the previous word's codes stay in shared memory between rounds)
+    uint32_t prevV = 0, prevM = 0, prevDtop = 0;
+    sh.prev_a[lane] = kFrontEmpty, sh.prev_b[lane] = kFrontEmpty, sh.last_ev[lane] = 0xFFFFFFF0u;
+    sh.n_len[lane] = 0u, sh.n_probes[lane] = 0u, sh.n_hits[lane] = 0u, sh.n_ext[lane] = 0u;
 
     for (uint32_t w = 0; w < rounds; ++w) {
         // ---- the owner's word: validity runs, match runs under the diagonal, what has to be looked up ----
@@ -180,145 +351,148 @@ analyze_bulk_kernel(const ReadKernelArgs a)
         uint64_t C = 0;
         uint32_t V = 0;
         if (mine) {
-            const uint32_t bp = src0 + 32u * w, gi = bp >> 5, sb = bp & 31u;
-            const uint64_t c_lo = ld_u64_hint(a.pcodes + gi, pol_first), c_hi = ld_u64_hint(a.pcodes + gi + 1, pol_first);
-            const uint32_t v_lo = ld_text_word(a.pvalid + gi, pol_first), v_hi = ld_text_word(a.pvalid + gi + 1, pol_first);
             C = sb ? (c_lo >> (2u * sb)) | (c_hi << (64u - 2u * sb)) : c_lo;
             V = __funnelshift_r(v_lo, v_hi, sb);
             const uint32_t rem = n - 32u * w;  // positions past the read belong to the next one
             if (rem < 32u) V &= (1u << rem) - 1u;
+            c_lo = c_hi, v_lo = v_hi;
+            if (w + 1u < my_words) {
+                c_hi = ld_u64_hint(a.pcodes + gi0 + w + 2u, pol_first);
+                v_hi = ld_text_word(a.pvalid + gi0 + w + 2u, pol_first);
+            }
         }
         const uint32_t WV = runs_ge(prevV, V, k);
-        len += __popc(V);        // ReadAnalyzer.hpp:46-49
-        my_probes += __popc(WV);
+        sh.n_len[lane] += __popc(V);  // ReadAnalyzer.hpp:46-49
+        sh.n_probes[lane] += __popc(WV);
         uint32_t M, E;
-        match_word(a, dg, w, C, V, k, pol_last, M, E);
+        match_word(a, dg, w, C, V, k, rw, M, E);
         if (!mine) M = 0u;
-        const uint32_t D = runs_ge(prevM, M, k);
-        const uint32_t S = D & ((D << 1) | prevDtop) & E;
+        if (mine && w + 1u < my_words) ref_fetch(a, dg, w + 1u, k, pol_last, rw);  // for the next round, unless the diagonal changes
+        uint32_t D = runs_ge(prevM, M, k);
+        uint32_t S = D & ((D << 1) | prevDtop) & E;
         const uint32_t need = WV & ~S;
+        // A read whose diagonal explains nothing in this word takes the anchor of its first plain hit as the next one.
+        // It asks for its first window alone (pass 0) and, when that gives a diagonal, matches the word again before
+        // the rest is looked up (pass 1) - otherwise every window of the word in which a mate starts would be a lookup.
+        bool want_me = WV != 0u && S == 0u, rediag = false;
+        uint32_t now = want_me ? need & (0u - need) : need, later = need & ~now;
 
-        sh.cprev[lane] = prevC;
+        sh.cprev[lane] = sh.ccur[lane];
         sh.ccur[lane] = C;
-        sh.need[lane] = need;
         sh.hit[lane] = 0u;
         sh.cplx[lane] = 0u;
         sh.cand[lane] = ~0ULL;
-        const uint32_t incl = warp_incl_scan((uint32_t)__popc(need), lane);
-        sh.pre[lane + 1] = incl;
-        if (lane == 0) sh.pre[0] = 0u;
-        const uint32_t total = __shfl_sync(kFull, incl, 31);
-        // reads whose diagonal explains nothing in this round take the anchor of their first plain hit as the next one
-        const uint32_t want = __ballot_sync(kFull, WV != 0u && S == 0u);
-        __syncwarp();
+        for (int pass = 0;; ++pass) {
+            sh.need[lane] = now;
+            const uint32_t incl = warp_incl_scan((uint32_t)__popc(now), lane);
+            sh.pre[lane + 1] = incl;
+            if (lane == 0) sh.pre[0] = 0u;
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            const uint32_t want = __ballot_sync(kFull, want_me);
+            __syncwarp();
 
-        // ---- the warp's lookups, an equal slice per lane ----
-        if (total) {
-            const uint32_t per = (total + 31u) >> 5;
-            const uint32_t i0 = min(total, (uint32_t)lane * per), i1 = min(total, i0 + per);
-            uint32_t left = i1 - i0, o = 0, m = 0;
-            if (left) {
+            // ---- the warp's lookups, an equal slice per lane ----
+            if (total) {
+                const uint32_t per = (total + 31u) >> 5;
+                const uint32_t i0 = min(total, (uint32_t)lane * per), i1 = min(total, i0 + per);
+                uint32_t left = i1 - i0, o = 0, m = 0;
+                if (left) {
 #pragma unroll
-                for (uint32_t s = 16; s; s >>= 1)  // the largest o with pre[o] <= i0: the owner of item i0
-                    if (sh.pre[o + s] <= i0) o += s;
-                m = sh.need[o];
-                uint32_t j = i0 - sh.pre[o], at = 0, mm = m;  // drop the j lowest set bits of m
+                    for (uint32_t s = 16; s; s >>= 1)  // the largest o with pre[o] <= i0: the owner of item i0
+                        if (sh.pre[o + s] <= i0) o += s;
+                    m = sh.need[o];
+                    uint32_t j = i0 - sh.pre[o], at = 0, mm = m;  // drop the j lowest set bits of m
 #pragma unroll
-                for (uint32_t s = 16; s; s >>= 1) {
-                    const uint32_t c = __popc(mm & ((1u << s) - 1u));
-                    if (j >= c) {
-                        j -= c;
-                        mm >>= s;
-                        at += s;
-                    }
-                }
-                m &= ~0u << at;
-            }
-            while (left) {
-                uint32_t oo[SHK_BULK_ILP], pp[SHK_BULK_ILP], bucket[SHK_BULK_ILP], key[SHK_BULK_ILP], cidx[SHK_BULK_ILP],
-                    cwd[SHK_BULK_ILP];
-                uint64_t fwd[SHK_BULK_ILP], rcm[SHK_BULK_ILP];
-                bool ok[SHK_BULK_ILP];
-#pragma unroll
-                for (int u = 0; u < SHK_BULK_ILP; ++u) {
-                    ok[u] = left != 0u;
-                    oo[u] = 0u, pp[u] = 0u;
-                    if (ok[u]) {
-                        while (m == 0u) m = sh.need[++o];
-                        pp[u] = (uint32_t)__ffs(m) - 1u;
-                        m &= m - 1u;
-                        oo[u] = o;
-                        --left;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < SHK_BULK_ILP; ++u) {
-                    // the window ending at position 32 + p of (previous word : current word), LSB first
-                    const uint64_t lo = sh.cprev[oo[u]], hi = sh.ccur[oo[u]];
-                    const uint32_t s2 = 2u * (33u + pp[u] - k);  // >= 4
-                    uint64_t X = s2 < 64u ? (lo >> s2) | (hi << (64u - s2)) : hi >> (s2 - 64u);
-                    X &= kmask2;
-                    X ^= (X >> 1) & 0x5555555555555555ULL;           // A0 C1 T2 G3 -> A0 C1 G2 T3 (kmer_utils.hpp:29-41)
-                    rcm[u] = ~X & kmask2;                             // revcompl, kmer_utils.hpp:47-55: LSB-first complement
-                    fwd[u] = pair_reverse(X) >> (64u - 2u * k);       // first base in the most significant group
-                    const uint64_t pb = bit_index<MOD>(xxh64_u64(fwd[u] < rcm[u] ? fwd[u] : rcm[u]), a.geom);
-                    bucket[u] = (uint32_t)(pb >> fshift);
-                    key[u] = front_key((uint32_t)pb & fmask);
-                    cidx[u] = (bucket[u] << a.coarse_rel) | (key[u] >> a.coarse_key_shift);
-                    cwd[u] = 0u;
-                    if (ok[u]) cwd[u] = ld_u32_hint(a.coarse + (cidx[u] >> 5), pol_last);
-                }
-                uint4 q[SHK_BULK_ILP];
-#pragma unroll
-                for (int u = 0; u < SHK_BULK_ILP; ++u) {
-                    q[u] = make_uint4(kFrontEmpty, kFrontEmpty, kFrontEmpty, kFrontEmpty);
-                    if ((cwd[u] >> (cidx[u] & 31u)) & 1u) {
-                        q[u] = ld_front(a.front + (uint64_t)bucket[u] * 2u, pol_front);
-                        ++my_loads;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < SHK_BULK_ILP; ++u) {
-                    uint4 qq = q[u];
-                    const uint32_t kb = key[u];
-                    uint32_t A, B, cur = bucket[u];
-                    for (;;) {  // the position's two smallest ids (slot - key; shk_device.cuh), along the bucket's chain
-                        const uint32_t d0 = qq.x - kb, d1 = qq.y - kb, d2 = qq.z - kb, d3 = qq.w - kb;
-                        const uint32_t lo01 = min(d0, d1), hi01 = max(d0, d1), lo23 = min(d2, d3), hi23 = max(d2, d3);
-                        A = min(lo01, lo23);
-                        B = min(max(lo01, lo23), min(hi01, hi23));
-                        if (A < kFrontLim || (int32_t)qq.w >= -1) break;
-                        cur = qq.w & 0x7FFFFFFFu;
-                        qq = ld_front(a.front + (uint64_t)cur * 2u, pol_front);
-                    }
-                    if (A < kFrontLim) {
-                        const uint32_t ow = oo[u], p = pp[u];
-                        if (A < 0x10000u && (B < 0x10000u || B >= kFrontLim)) {  // a list of one or two ids
-                            sh.res[ow][p] = A | ((B < 0x10000u ? B : A) << 16);
-                            atomicOr(&sh.hit[ow], 1u << p);
-                            if ((want >> ow) & 1u) {
-                                // the slot's anchor names a reference window with the same filter bit; it gives a
-                                // diagonal only if that window IS the read's window (either strand)
-                                const uint4 an = ld_front(a.front + (uint64_t)cur * 2u + 1u, pol_front);
-                                const uint32_t sa = A + kb;
-                                const uint32_t e = qq.x == sa ? an.x : (qq.y == sa ? an.y : (qq.z == sa ? an.z : an.w));
-                                const uint64_t rk = ref2_window(a.ref2, e, kmask2, pol_last);
-                                if (rk == fwd[u]) atomicMin(&sh.cand[ow], ((unsigned long long)p << 33) | e);
-                                else if (rk == rcm[u]) atomicMin(&sh.cand[ow], ((unsigned long long)p << 33) | (1ULL << 32) | e);
-                            }
-                        } else {
-                            atomicOr(&sh.cplx[ow], 1u << p);  // 3 ids or more
+                    for (uint32_t s = 16; s; s >>= 1) {
+                        const uint32_t c = __popc(mm & ((1u << s) - 1u));
+                        if (j >= c) {
+                            j -= c;
+                            mm >>= s;
+                            at += s;
                         }
                     }
+                    m &= ~0u << at;
+                }
+                // Windows that pass the coarse filter queue up for the DRAM-sized table; the queue is served 32 entries at a
+                // time, one per lane, so that a warp waits for DRAM once per 32 table loads and probes with every lane.
+                uint32_t fq_head = 0, fq_n = 0;  // warp-uniform
+                // One item per iteration, its coarse word in flight while the next item is hashed (no unrolling: the
+                // kernel is bound by latency AND by the instruction cache, profiles/analyze_r2.md).
+                uint32_t q_bucket = 0, q_key = 0, q_who = 0, q_bit = 0, q_cwd = 0;
+                for (uint32_t it = 0; it <= per; ++it) {  // same trip count in every lane
+                    uint32_t n_bucket = 0, n_key = 0, n_who = 0, n_bit = 0, n_cwd = 0;
+                    if (it < per && left) {
+                        while (m == 0u) m = sh.need[++o];
+                        const uint32_t p = (uint32_t)__ffs(m) - 1u;
+                        m &= m - 1u;
+                        --left;
+                        uint64_t fwd, rcm;
+                        window_kmers(sh.cprev[o], sh.ccur[o], p, k, kmask2, fwd, rcm);
+                        const uint64_t pb = bit_index<MOD>(xxh64_u64(fwd < rcm ? fwd : rcm), a.geom);
+                        n_bucket = (uint32_t)(pb >> fshift);
+                        n_key = front_key((uint32_t)pb & fmask);
+                        const uint32_t cidx = (n_bucket << a.coarse_rel) | (n_key >> a.coarse_key_shift);
+                        n_bit = cidx & 31u;
+                        n_who = o | (p << 8);
+                        n_cwd = ld_u32_hint(a.coarse + (cidx >> 5), pol_last);
+                    }
+                    const bool push = (q_cwd >> q_bit) & 1u;
+                    const uint32_t pm = __ballot_sync(kFull, push);
+                    if (push) {
+                        const uint32_t slot = (fq_head + fq_n + (uint32_t)__popc(pm & ((1u << lane) - 1u))) & (kBulkQueue - 1u);
+                        sh.fq_bucket[slot] = q_bucket;
+                        sh.fq_key[slot] = q_key;
+                        sh.fq_who[slot] = (uint16_t)q_who;
+                        ++my_loads;
+                    }
+                    fq_n += (uint32_t)__popc(pm);
+                    if (fq_n >= 32u) {
+                        __syncwarp();
+                        serve_queue<MOD>(a, sh, (fq_head + (uint32_t)lane) & (kBulkQueue - 1u), true, want, k, kmask2, pol_front, pol_last);
+                        __syncwarp();
+                        fq_head = (fq_head + 32u) & (kBulkQueue - 1u);
+                        fq_n -= 32u;
+                    }
+                    q_bucket = n_bucket, q_key = n_key, q_who = n_who, q_bit = n_bit, q_cwd = n_cwd;
+                }
+                if (fq_n) {
+                    __syncwarp();
+                    serve_queue<MOD>(a, sh, (fq_head + (uint32_t)lane) & (kBulkQueue - 1u), (uint32_t)lane < fq_n, want, k, kmask2, pol_front, pol_last);
                 }
             }
+            __syncwarp();
+            if (pass == 1) break;
+            if (want_me) {
+                const unsigned long long cd = sh.cand[lane];
+                if (cd != ~0ULL) {  // a diagonal: the word (and the windows reaching back into the word before) matched again
+                    const uint32_t e = (uint32_t)cd, pos = 32u * w + (uint32_t)(cd >> 33);
+                    dg.on = true;
+                    dg.dir = (uint32_t)(cd >> 32) & 1u;
+                    dg.base = dg.dir ? (int64_t)e - (int64_t)k + 1 + (int64_t)pos : (int64_t)e - (int64_t)pos;
+                    uint32_t pm = 0u, E2;
+                    if (w) {
+                        ref_fetch(a, dg, w - 1u, k, pol_last, rw);
+                        match_word(a, dg, w - 1u, sh.cprev[lane], prevV, k, rw, pm, E2);
+                    }
+                    ref_fetch(a, dg, w, k, pol_last, rw);
+                    match_word(a, dg, w, sh.ccur[lane], V, k, rw, M, E2);
+                    if (w + 1u < my_words) ref_fetch(a, dg, w + 1u, k, pol_last, rw);
+                    D = runs_ge(pm, M, k);
+                    S = D & (D << 1) & E2;  // (nothing is known about the last window of the word before)
+                    later = WV & ~S & ~now;
+                    want_me = false;
+                    sh.cand[lane] = ~0ULL;
+                }
+            }
+            now = later;
+            later = 0u;
+            if (!__any_sync(kFull, now != 0u)) break;
         }
-        __syncwarp();
 
         // ---- the owner applies hits and runs in window order (ReadAnalyzer.hpp:56-62, 79-86) ----
-        bool rediag = false;
         if (mine) {
             const uint32_t cplx = sh.cplx[lane];
+            uint32_t prevA = sh.prev_a[lane], prevB = sh.prev_b[lane], last_ev = sh.last_ev[lane], my_hits = 0, my_ext = 0;
             uint32_t ev = sh.hit[lane] | cplx | S;
             while (ev && !tab.overflow) {
                 const uint32_t p = (uint32_t)__ffs(ev) - 1u, pos = 32u * w + p;
@@ -338,7 +512,8 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                     // a list of 3 or 4 ids (or a longer one: exact path): every slot of the bucket and of its chain, in
                     // list order, as analyze_reads_kernel's generic path does
                     const uint32_t s2 = 2u * (33u + p - k);
-                    uint64_t X = s2 < 64u ? (prevC >> s2) | (C << (64u - s2)) : C >> (s2 - 64u);
+                    const uint64_t pc = sh.cprev[lane], cc = sh.ccur[lane];
+                    uint64_t X = s2 < 64u ? (pc >> s2) | (cc << (64u - s2)) : cc >> (s2 - 64u);
                     X &= kmask2;
                     X ^= (X >> 1) & 0x5555555555555555ULL;
                     const uint64_t rcx = ~X & kmask2, fwx = pair_reverse(X) >> (64u - 2u * k);
@@ -352,7 +527,7 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                             const uint32_t d = sl ^ kb;
                             if (d < kFrontLim) {
                                 if (d & kFrontLongFlag) tab.overflow = true;
-                                else tab.hit(d & 0xFFFFu, pos, k);
+                                else tab.hit(cold, d & 0xFFFFu, pos, k);
                             }
                         }
                         if (!front_is_chain(qq.w)) break;
@@ -367,7 +542,10 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                     A = rr & 0xFFFFu;
                     B = rr >> 16;
                     if (B == A) B = kFrontEmpty;
-                    L = 1u;
+                    // ... and the run of windows with the same ids that follows it, in one step
+                    const uint32_t run = p < 31u ? (uint32_t)__ffs(~(S >> (p + 1u))) - 1u : 0u;
+                    L = 1u + run;
+                    my_ext += run;
                 }
                 ev &= ~(((L < 32u ? (1u << L) : 0u) - 1u) << p);
                 if (A != kFrontEmpty) {
@@ -386,10 +564,10 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                             tab.l1 = pos + L - 1u;
                         }
                     } else {
-                        tab.hit(A, pos, k);
+                        tab.hit(cold, A, pos, k);
                         if (!tab.overflow) tab.more(A, L - 1u);
                         if (hasB && !tab.overflow) {
-                            tab.hit(B, pos, k);
+                            tab.hit(cold, B, pos, k);
                             if (!tab.overflow) tab.more(B, L - 1u);
                         }
                     }
@@ -398,6 +576,8 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                     last_ev = pos + L - 1u;
                 }
             }
+            sh.prev_a[lane] = prevA, sh.prev_b[lane] = prevB, sh.last_ev[lane] = last_ev;
+            sh.n_hits[lane] += my_hits, sh.n_ext[lane] += my_ext;
             const unsigned long long cd = sh.cand[lane];
             if (cd != ~0ULL) {
                 const uint32_t e = (uint32_t)cd, pos = 32u * w + (uint32_t)(cd >> 33);
@@ -409,9 +589,10 @@ analyze_bulk_kernel(const ReadKernelArgs a)
         }
         if (rediag) {  // the next word's windows reach into this one: its matches under the new diagonal
             uint32_t E2;
-            match_word(a, dg, w, C, V, k, pol_last, M, E2);
+            ref_fetch(a, dg, w, k, pol_last, rw);
+            match_word(a, dg, w, sh.ccur[lane], V, k, rw, M, E2);
+            if (w + 1u < my_words) ref_fetch(a, dg, w + 1u, k, pol_last, rw);
         }
-        prevC = C;
         prevV = V;
         prevM = M;
         prevDtop = rediag ? 0u : D >> 31;
@@ -420,16 +601,17 @@ analyze_bulk_kernel(const ReadKernelArgs a)
     if (r < a.r1) {
         if (tab.overflow) slow = true;
         if (slow) {
-            count = 0, payload = 0, my_probes = 0, my_hits = 0;  // counted by the kernel that classifies the read
+            count = 0, payload = 0;
+            sh.n_probes[lane] = 0u, sh.n_hits[lane] = 0u;  // counted by the kernel that classifies the read
             a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
         } else {
-            finish_read(a, tab, len, count, payload);
+            finish_read(a, tab.full(cold), sh.n_len[lane], count, payload);
         }
         a.rec[r] = make_uint2(count, payload);
     }
-    const uint32_t wa = __reduce_add_sync(kFull, count), wp = __reduce_add_sync(kFull, my_probes),
-                   wh = __reduce_add_sync(kFull, my_hits), wm = __reduce_add_sync(kFull, multi_entries(count, payload)),
-                   wk = __popc(__ballot_sync(kFull, count != 0u)), we = __reduce_add_sync(kFull, my_ext),
+    const uint32_t wa = __reduce_add_sync(kFull, count), wp = __reduce_add_sync(kFull, sh.n_probes[lane]),
+                   wh = __reduce_add_sync(kFull, sh.n_hits[lane]), wm = __reduce_add_sync(kFull, multi_entries(count, payload)),
+                   wk = __popc(__ballot_sync(kFull, count != 0u)), we = __reduce_add_sync(kFull, sh.n_ext[lane]),
                    wl = __reduce_add_sync(kFull, my_loads);
     if (lane == 0) {
         if (wm) atomicAdd(&a.tile_sums[tile], wm);
@@ -442,11 +624,14 @@ analyze_bulk_kernel(const ReadKernelArgs a)
     }
 }
 
-// SHK_BULK=0 keeps packed reads on analyze_reads_kernel<EXT, PACKED> (A/B measurements, tests of both kernels).
+// SHK_BULK=1 sends packed reads to this kernel, SHK_BULK=0 keeps them on analyze_reads_kernel<EXT, PACKED> (A/B
+// measurements, tests of both kernels); unset = kBulkDefault.
+constexpr bool kBulkDefault = false;
 bool bulk_enabled()
 {
     const char *e = std::getenv("SHK_BULK");
-    return !(e && e[0] == '0');
+    if (!e || !e[0]) return kBulkDefault;
+    return e[0] != '0';
 }
 
 void launch_bulk_kernel(const ReadKernelArgs &a, cudaStream_t st, unsigned blocks)

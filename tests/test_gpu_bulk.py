@@ -129,7 +129,7 @@ def test_bulk_stress_parity(monkeypatch, k, c, single, bf_bits):
     # both kernels count the same valid windows and the same windows with ids
     assert out[True]["n_probes"] == out[False]["n_probes"]
     assert out[True]["n_hits"] == out[False]["n_hits"]
-    if k >= 17:
+    if k >= 17 and bf_bits >= 1 << 26:   # (a filter of 10^6 bits is dense: neighbouring windows rarely share a list)
         assert out[True]["n_extended"] > 0.3 * out[True]["n_hits"]
 
 
