@@ -104,7 +104,8 @@ struct BulkTab {
         }
     }
     // Mru4::other with slots 2 and 3 in shared memory
-    __device__ __noinline__ void other(BulkCold &cold, uint32_t g, uint32_t pos, uint32_t k)
+    __device__ __forceinline__ void other(BulkCold &cold,  // (never out of line: a call would put the table on the stack)
+                                           uint32_t g, uint32_t pos, uint32_t k)
     {
         const uint32_t t = threadIdx.x;
         uint32_t c = k, h = 1;
@@ -420,7 +421,9 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                 // kernel is bound by latency AND by the instruction cache, profiles/analyze_r2.md).
                 uint32_t q_bucket = 0, q_key = 0, q_who = 0, q_bit = 0, q_cwd = 0;
                 for (uint32_t it = 0; it <= per; ++it) {  // same trip count in every lane
-                    uint32_t n_bucket = 0, n_key = 0, n_who = 0, n_bit = 0, n_cwd = 0;
+                    // the next item is hashed while the coarse word of the one before is in flight
+                    uint32_t n_bucket = 0, n_key = 0, n_who = 0, n_bit = 0;
+                    const uint32_t *n_addr = nullptr;
                     if (it < per && left) {
                         while (m == 0u) m = sh.need[++o];
                         const uint32_t p = (uint32_t)__ffs(m) - 1u;
@@ -434,11 +437,13 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                         const uint32_t cidx = (n_bucket << a.coarse_rel) | (n_key >> a.coarse_key_shift);
                         n_bit = cidx & 31u;
                         n_who = o | (p << 8);
-                        n_cwd = ld_u32_hint(a.coarse + (cidx >> 5), pol_last);
+                        n_addr = a.coarse + (cidx >> 5);
                     }
                     const bool push = (q_cwd >> q_bit) & 1u;
                     const uint32_t pm = __ballot_sync(kFull, push);
                     if (push) {
+                        // on its way into L2 while it waits in the queue
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.front + (uint64_t)q_bucket * 2u));
                         const uint32_t slot = (fq_head + fq_n + (uint32_t)__popc(pm & ((1u << lane) - 1u))) & (kBulkQueue - 1u);
                         sh.fq_bucket[slot] = q_bucket;
                         sh.fq_key[slot] = q_key;
@@ -453,7 +458,8 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                         fq_head = (fq_head + 32u) & (kBulkQueue - 1u);
                         fq_n -= 32u;
                     }
-                    q_bucket = n_bucket, q_key = n_key, q_who = n_who, q_bit = n_bit, q_cwd = n_cwd;
+                    q_bucket = n_bucket, q_key = n_key, q_who = n_who, q_bit = n_bit;
+                    q_cwd = n_addr ? ld_u32_hint(n_addr, pol_last) : 0u;
                 }
                 if (fq_n) {
                     __syncwarp();
