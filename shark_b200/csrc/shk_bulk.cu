@@ -53,14 +53,15 @@ struct BulkWarp {
     uint32_t need[32];             // per lane: windows of the round that must be looked up
     uint32_t pre[33];              // exclusive prefix sum of popc(need)
     uint32_t hit[32];              // per lane: looked-up windows that are set in the filter (plain lists)
-    uint32_t res[32][33];          // [lane][pos in word]: ids of a hit, A | B << 16 (B == A: one id)
+    uint32_t res[32][32];          // [lane][(pos in word + lane) & 31]: ids of a hit, A | B << 16 (B == A: one id)
     uint32_t cplx[32];             // per lane: hits whose list has more than 2 ids (the owner walks the bucket itself)
     // queue of table loads (windows that passed the coarse filter): bucket, key, owner lane | position << 8
     uint32_t fq_bucket[kBulkQueue], fq_key[kBulkQueue];
     uint16_t fq_who[kBulkQueue];
+    uint32_t cw[32];               // per lane: the coarse-filter word of its item in flight (cp.async)
     // owner state that is idle while the warp does lookups (registers there are resident CTAs)
     uint32_t prev_a[32], prev_b[32], last_ev[32];  // ids and end of the last window with ids
-    uint32_t n_len[32], n_probes[32], n_hits[32], n_ext[32];
+    uint16_t n_len[32], n_probes[32], n_hits[32], n_ext[32];  // at most kMaxFastLen each
 };
 
 // The per-gene table of the owner (Mru4, shk_reads.cuh) with its two older genes in shared memory: they are touched only
@@ -281,7 +282,7 @@ __device__ SHK_BULK_SERVE_ATTR void serve_queue(const ReadKernelArgs &a, BulkWar
     }
     if (A >= kFrontLim) return;
     if (A < 0x10000u && (B < 0x10000u || B >= kFrontLim)) {  // a list of one or two ids
-        sh.res[ow][p] = A | ((B < 0x10000u ? B : A) << 16);
+        sh.res[ow][(p + ow) & 31u] = A | ((B < 0x10000u ? B : A) << 16);
         atomicOr(&sh.hit[ow], 1u << p);
         if (wanted) {
             if (cur != bucket) anc = ld_front(a.front + (uint64_t)cur * 2u + 1u, pol_front);
@@ -304,8 +305,11 @@ analyze_bulk_kernel(const ReadKernelArgs a)
 {
     __shared__ BulkWarp shared[kBulkWarps];
     __shared__ BulkCold cold;
-    const int lane = threadIdx.x & 31;
-    BulkWarp &sh = shared[threadIdx.x >> 5];
+    // (opaque to the compiler: under register pressure it would recompute both from %tid before every shared access)
+    int lane = threadIdx.x & 31;
+    uint32_t warp_in_cta = threadIdx.x >> 5;
+    asm volatile("" : "+r"(lane), "+r"(warp_in_cta));
+    BulkWarp &sh = shared[warp_in_cta];
     const uint32_t r = a.r0 + blockIdx.x * kBulkThreads + threadIdx.x;
     const uint32_t tile = a.r0 / kReadsPerTile + blockIdx.x;
     const uint64_t pol_first = a.pol_first, pol_last = a.pol_last;
@@ -344,7 +348,7 @@ analyze_bulk_kernel(const ReadKernelArgs a)
     sh.ccur[lane] = 0;  // (the previous word's codes stay in shared memory between rounds)
     uint32_t prevV = 0, prevM = 0, prevDtop = 0;
     sh.prev_a[lane] = kFrontEmpty, sh.prev_b[lane] = kFrontEmpty, sh.last_ev[lane] = 0xFFFFFFF0u;
-    sh.n_len[lane] = 0u, sh.n_probes[lane] = 0u, sh.n_hits[lane] = 0u, sh.n_ext[lane] = 0u;
+    sh.n_len[lane] = 0, sh.n_probes[lane] = 0, sh.n_hits[lane] = 0, sh.n_ext[lane] = 0;
 
     for (uint32_t w = 0; w < rounds; ++w) {
         // ---- the owner's word: validity runs, match runs under the diagonal, what has to be looked up ----
@@ -375,7 +379,7 @@ analyze_bulk_kernel(const ReadKernelArgs a)
         // A read whose diagonal explains nothing in this word takes the anchor of its first plain hit as the next one.
         // It asks for its first window alone (pass 0) and, when that gives a diagonal, matches the word again before
         // the rest is looked up (pass 1) - otherwise every window of the word in which a mate starts would be a lookup.
-        bool want_me = WV != 0u && S == 0u, rediag = false;
+        bool want_me = WV != 0u && S == 0u;
         uint32_t now = want_me ? need & (0u - need) : need, later = need & ~now;
 
         sh.cprev[lane] = sh.ccur[lane];
@@ -419,7 +423,11 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                 uint32_t fq_head = 0, fq_n = 0;  // warp-uniform
                 // One item per iteration, its coarse word in flight while the next item is hashed (no unrolling: the
                 // kernel is bound by latency AND by the instruction cache, profiles/analyze_r2.md).
-                uint32_t q_bucket = 0, q_key = 0, q_who = 0, q_bit = 0, q_cwd = 0;
+                // (The coarse word travels by cp.async into the lane's own shared-memory slot: ptxas does not keep a
+                // register load in flight across the loop's back edge, an asynchronous copy has no register to wait on.)
+                uint32_t q_bucket = 0, q_key = 0, q_who = 0, q_bit = 0;
+                bool q_has = false;
+                const uint32_t cw_slot = (uint32_t)__cvta_generic_to_shared(&sh.cw[lane]);
                 for (uint32_t it = 0; it <= per; ++it) {  // same trip count in every lane
                     // the next item is hashed while the coarse word of the one before is in flight
                     uint32_t n_bucket = 0, n_key = 0, n_who = 0, n_bit = 0;
@@ -439,7 +447,11 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                         n_who = o | (p << 8);
                         n_addr = a.coarse + (cidx >> 5);
                     }
-                    const bool push = (q_cwd >> q_bit) & 1u;
+                    bool push = false;
+                    if (q_has) {
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        push = (sh.cw[lane] >> q_bit) & 1u;
+                    }
                     const uint32_t pm = __ballot_sync(kFull, push);
                     if (push) {
                         // on its way into L2 while it waits in the queue
@@ -459,7 +471,8 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                         fq_n -= 32u;
                     }
                     q_bucket = n_bucket, q_key = n_key, q_who = n_who, q_bit = n_bit;
-                    q_cwd = n_addr ? ld_u32_hint(n_addr, pol_last) : 0u;
+                    q_has = n_addr != nullptr;
+                    if (q_has) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cw_slot), "l"(n_addr) : "memory");
                 }
                 if (fq_n) {
                     __syncwarp();
@@ -467,10 +480,12 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                 }
             }
             __syncwarp();
-            if (pass == 1) break;
             if (want_me) {
                 const unsigned long long cd = sh.cand[lane];
-                if (cd != ~0ULL) {  // a diagonal: the word (and the windows reaching back into the word before) matched again
+                if (cd != ~0ULL) {
+                    // A diagonal: the word (and the windows reaching back into the word before) is matched again.  After
+                    // pass 0 the runs it explains are no longer looked up; after pass 1 they already were, but the
+                    // owner still applies them as runs (a run clears the hits it covers) instead of window by window.
                     const uint32_t e = (uint32_t)cd, pos = 32u * w + (uint32_t)(cd >> 33);
                     dg.on = true;
                     dg.dir = (uint32_t)(cd >> 32) & 1u;
@@ -490,6 +505,7 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                     sh.cand[lane] = ~0ULL;
                 }
             }
+            if (pass == 1) break;
             now = later;
             later = 0u;
             if (!__any_sync(kFull, now != 0u)) break;
@@ -544,7 +560,7 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                     ev &= ev - 1u;
                     continue;
                 } else {
-                    const uint32_t rr = sh.res[lane][p];
+                    const uint32_t rr = sh.res[lane][(p + (uint32_t)lane) & 31u];
                     A = rr & 0xFFFFu;
                     B = rr >> 16;
                     if (B == A) B = kFrontEmpty;
@@ -584,31 +600,17 @@ analyze_bulk_kernel(const ReadKernelArgs a)
             }
             sh.prev_a[lane] = prevA, sh.prev_b[lane] = prevB, sh.last_ev[lane] = last_ev;
             sh.n_hits[lane] += my_hits, sh.n_ext[lane] += my_ext;
-            const unsigned long long cd = sh.cand[lane];
-            if (cd != ~0ULL) {
-                const uint32_t e = (uint32_t)cd, pos = 32u * w + (uint32_t)(cd >> 33);
-                dg.on = true;
-                dg.dir = (uint32_t)(cd >> 32) & 1u;
-                dg.base = dg.dir ? (int64_t)e - (int64_t)k + 1 + (int64_t)pos : (int64_t)e - (int64_t)pos;
-                rediag = true;
-            }
-        }
-        if (rediag) {  // the next word's windows reach into this one: its matches under the new diagonal
-            uint32_t E2;
-            ref_fetch(a, dg, w, k, pol_last, rw);
-            match_word(a, dg, w, sh.ccur[lane], V, k, rw, M, E2);
-            if (w + 1u < my_words) ref_fetch(a, dg, w + 1u, k, pol_last, rw);
         }
         prevV = V;
         prevM = M;
-        prevDtop = rediag ? 0u : D >> 31;
+        prevDtop = D >> 31;
     }
 
     if (r < a.r1) {
         if (tab.overflow) slow = true;
         if (slow) {
             count = 0, payload = 0;
-            sh.n_probes[lane] = 0u, sh.n_hits[lane] = 0u;  // counted by the kernel that classifies the read
+            sh.n_probes[lane] = 0, sh.n_hits[lane] = 0;  // counted by the kernel that classifies the read
             a.slow_list[atomicAdd(&a.counters->n_slow, 1u)] = r;
         } else {
             finish_read(a, tab.full(cold), sh.n_len[lane], count, payload);
@@ -632,7 +634,7 @@ analyze_bulk_kernel(const ReadKernelArgs a)
 
 // SHK_BULK=1 sends packed reads to this kernel, SHK_BULK=0 keeps them on analyze_reads_kernel<EXT, PACKED> (A/B
 // measurements, tests of both kernels); unset = kBulkDefault.
-constexpr bool kBulkDefault = false;
+constexpr bool kBulkDefault = true;
 bool bulk_enabled()
 {
     const char *e = std::getenv("SHK_BULK");
