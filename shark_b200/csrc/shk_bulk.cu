@@ -393,7 +393,7 @@ analyze_bulk_kernel(const ReadKernelArgs a)
             sh.pre[lane + 1] = incl;
             if (lane == 0) sh.pre[0] = 0u;
             const uint32_t total = __shfl_sync(kFull, incl, 31);
-            const uint32_t want = __ballot_sync(kFull, want_me);
+            const uint32_t want = __ballot_sync(kFull, want_me), nz = __ballot_sync(kFull, now != 0u);
             __syncwarp();
 
             // ---- the warp's lookups, an equal slice per lane ----
@@ -433,7 +433,10 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                     uint32_t n_bucket = 0, n_key = 0, n_who = 0, n_bit = 0;
                     const uint32_t *n_addr = nullptr;
                     if (it < per && left) {
-                        while (m == 0u) m = sh.need[++o];
+                        while (m == 0u) {  // the next owner that asks for anything
+                            o = (uint32_t)__ffs(nz & (0xFFFFFFFEu << o)) - 1u;
+                            m = sh.need[o];
+                        }
                         const uint32_t p = (uint32_t)__ffs(m) - 1u;
                         m &= m - 1u;
                         --left;
