@@ -647,17 +647,20 @@ def run_workload(name, args, rank, world, local_rank, cores, dist, torch):
         ms = probe_ms_max / max(launches, 1)
         achieved = 32.0 * ppl / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         traffic, traffic_src = traffic_for(name + "_" + form)
-        # packed reads over the extension structures are classified by the bulk kernel (shk_bulk.cu) unless SHK_BULK=0
+        # packed reads over the extension structures are classified by the bulk kernel (shk_bulk.cu) unless SHK_BULK=0;
+        # the thread-per-read kernel extends only over a DRAM-sized table (info.plain_front: slots-only copy in L2)
         bulk = form == "packed" and info.extend and os.environ.get("SHK_BULK", "1")[:1] != "0"
+        ext_k6 = bool(info.extend) and not info.plain_front
+        uses_ext = bulk or ext_k6
         kname = "analyze_bulk_kernel (packed reads, diagonals + shared lookups)" if bulk else \
-            "analyze_reads_kernel<%s%s>" % ("PACKED" if form == "packed" else "TEXT", ", EXT" if info.extend else "")
+            "analyze_reads_kernel<%s%s>" % ("PACKED" if form == "packed" else "TEXT", ", EXT" if ext_k6 else "")
         return {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": 32.0 * ppl,
                 "probes_per_launch": ppl, "kernel_ms_per_launch": ms, "launches_per_step": n_chunks,
-                "hit_fraction": res["n_hits"] / max(res["n_probes"], 1), "extend": bool(info.extend),
+                "hit_fraction": res["n_hits"] / max(res["n_probes"], 1), "extend": bool(uses_ext),
                 "extended_fraction": res["n_extended"] / max(res["n_probes"], 1),
-                "table_loads_per_probe": (res["n_table_loads"] / max(res["n_probes"], 1)) if info.extend else 1.0,
+                "table_loads_per_probe": (res["n_table_loads"] / max(res["n_probes"], 1)) if uses_ext else 1.0,
                 "random_sector_ceiling_gbs": rs_gbs, "frac_of_random_sector_ceiling": achieved / rs_gbs if rs_gbs else None,
                 "limiter": ("instruction issue (hash + coarse filter of the windows that are not copied from the window before) "
                             "and L2/DRAM latency at 24 warps per SM; DRAM traffic is below the algorithmic bytes because "

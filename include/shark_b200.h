@@ -109,7 +109,10 @@ typedef struct shk_index_info {
     uint32_t n_shards;     /* 1 = built by shk_index_build; n = sharded build over n contexts;
                               0 = staged protocol / adopted                                         */
     uint32_t id_bits;      /* width of a gene id in the CSR: 16, or 32 with SHK_F_WIDE_IDS            */
-    uint32_t reserved;
+    uint32_t plain_front;  /* 1 = the table is L2-sized and no flag forces a path: text reads are classified
+                              over a derived slots-only copy of the front table (16-byte entries, stays in
+                              L2), packed reads by the bulk kernel over the extension structures.  Set by
+                              every context for itself when its index becomes ready (was `reserved`)    */
 } shk_index_info;
 
 /* One association = one line of the reference's stdout (ReadOutput.hpp:43): read `read_idx`

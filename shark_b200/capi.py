@@ -51,7 +51,7 @@ class IndexInfo(C.Structure):
                 ("n_windows", C.c_uint64), ("bf_bits", C.c_uint64), ("device_bytes", C.c_uint64), ("build_ms", C.c_float),
                 ("front_shift", C.c_uint32), ("front_entries", C.c_uint64), ("ref_bases", C.c_uint64),
                 ("extend", C.c_uint32), ("coarse_shift", C.c_uint32), ("build_wall_ms", C.c_float),
-                ("n_shards", C.c_uint32), ("id_bits", C.c_uint32), ("reserved", C.c_uint32)]
+                ("n_shards", C.c_uint32), ("id_bits", C.c_uint32), ("plain_front", C.c_uint32)]
 
 
 class ShardMem(C.Structure):

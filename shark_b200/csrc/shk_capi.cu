@@ -234,6 +234,7 @@ static ReadKernelArgs make_args(shk_ctx *ctx, Slot &s)
     a.ref2 = ctx->index.ref2;
     a.coarse = ctx->index.coarse;
     a.refr = ctx->index.refr;
+    a.front_plain = ctx->index.front_plain;
     a.ebits = ctx->index.ebits;
     a.ref_total = ctx->index.egeom.total;
     a.coarse_rel = ctx->index.egeom.enabled ? ctx->index.fgeom.shift - ctx->index.egeom.coarse_shift : 0;
@@ -580,6 +581,7 @@ void shk_destroy(shk_ctx *ctx)
     cudaFree(ctx->index.coarse);
     cudaFree(ctx->index.refr);
     cudaFree(ctx->index.ebits);
+    cudaFree(ctx->index.front_plain);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);

@@ -719,8 +719,11 @@ static void free_index_arrays(DeviceIndex &ix)
     if (ix.coarse) cudaFree(ix.coarse);
     if (ix.refr) cudaFree(ix.refr);
     if (ix.ebits) cudaFree(ix.ebits);
+    if (ix.front_plain) cudaFree(ix.front_plain);
     ix.refr = nullptr;
     ix.ebits = nullptr;
+    ix.front_plain = nullptr;
+    ix.derived_bytes = 0;
     ix.front = nullptr;
     ix.entries = nullptr;
     ix.csr_off = nullptr;
@@ -751,15 +754,26 @@ static int ext_alloc(shk_ctx *ctx)
     return SHK_OK;
 }
 
-// Extension on/off: forced by shk_params.flags (or SHK_EXTEND=0/1, tuning), else on when the
-// plain front table (16 bytes per entry) would not stay in L2 next to the streamed reads.
+// Is a path forced (shk_params.flags, or SHK_EXTEND=0/1 for tuning)?  -1 = no, else 0 / 1.
+static int forced_extend(const shk_ctx *ctx)
+{
+    if (ctx->params.flags & SHK_F_EXTEND_ON) return 1;
+    if (ctx->params.flags & SHK_F_EXTEND_OFF) return 0;
+    if (const char *ev = getenv("SHK_EXTEND")) return atoi(ev) != 0;
+    return -1;
+}
+// A plain front table (16 bytes per entry) of this many entries stays in L2 next to the streamed reads.
+static bool front_fits_l2(uint64_t front_entries) { return front_entries * 16 <= (96ull << 20); }
+
+// Extension structures: built unless forced off.  They serve the bulk kernel (packed reads) for any table size; the
+// thread-per-read kernels use them only when the table is DRAM-sized or the flag forces it - for an L2-sized table
+// they probe a slots-only copy of it (index_derive_bulk, info.plain_front) exactly as without the structures.
 static bool decide_extend(const shk_ctx *ctx, uint64_t front_entries, uint64_t total)
 {
+    (void)front_entries;
     if (total == 0 || total >= 0xFFFFFF00ull) return false;
-    if (ctx->params.flags & SHK_F_EXTEND_ON) return true;
-    if (ctx->params.flags & SHK_F_EXTEND_OFF) return false;
-    if (const char *ev = getenv("SHK_EXTEND")) return atoi(ev) != 0;
-    return front_entries * 16 > (96ull << 20);
+    const int f = forced_extend(ctx);
+    return f != 0;
 }
 
 // Front table geometry: at most ~0.7 keys per 4-slot bucket (C2: 64 MB for 2.8 M keys; measured
@@ -792,7 +806,9 @@ int index_alloc_front(shk_ctx *ctx)
     if (ix.coarse) cudaFree(ix.coarse);
     if (ix.refr) cudaFree(ix.refr);
     if (ix.ebits) cudaFree(ix.ebits);
-    ix.refr = nullptr, ix.ebits = nullptr;
+    if (ix.front_plain) cudaFree(ix.front_plain);
+    ix.refr = nullptr, ix.ebits = nullptr, ix.front_plain = nullptr;
+    ix.derived_bytes = 0;
     ix.front = nullptr;
     ix.estream = nullptr, ix.ref2 = nullptr, ix.coarse = nullptr;
     ix.egeom = ExtGeom{};
@@ -843,24 +859,45 @@ derive_bulk_kernel(const uint64_t *__restrict__ estream, uint64_t total, uint64_
     ebits[w + kDerivedPad] = e;
 }
 
+__global__ void __launch_bounds__(256)
+derive_plain_kernel(const uint4 *__restrict__ front, uint64_t n_entries, uint4 *plain)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_entries) plain[i] = front[2 * i];  // the slots; chain pointers are entry indices, valid for any stride
+}
+
 int index_derive_bulk(shk_ctx *ctx)
 {
     DeviceIndex &ix = ctx->index;
     if (ix.refr) cudaFree(ix.refr);
     if (ix.ebits) cudaFree(ix.ebits);
-    ix.refr = nullptr, ix.ebits = nullptr;
+    if (ix.front_plain) cudaFree(ix.front_plain);
+    ix.refr = nullptr, ix.ebits = nullptr, ix.front_plain = nullptr;
+    ix.info.device_bytes -= std::min(ix.info.device_bytes, ix.derived_bytes);
+    ix.derived_bytes = 0;
+    ix.info.plain_front = 0;
     if (!ix.egeom.enabled || !ix.estream) return SHK_OK;
     const uint64_t words = ix.egeom.total / 32 + 1 + kDerivedPad + kDerivedTail;
     SHK_CUDA(ctx, cudaMalloc((void **)&ix.refr, words * 8));
     SHK_CUDA(ctx, cudaMalloc((void **)&ix.ebits, words * 4));
+    ix.derived_bytes = words * 12;
     cudaStream_t st = ctx->build_stream;
     SHK_CUDA(ctx, cudaMemsetAsync(ix.refr, 0, words * 8, st));
     SHK_CUDA(ctx, cudaMemsetAsync(ix.ebits, 0, words * 4, st));
     const uint64_t n = (ix.egeom.total + 31) / 32;
     if (n) derive_bulk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ix.estream, ix.egeom.total, ix.refr, ix.ebits);
     SHK_CUDA(ctx, cudaGetLastError());
-    SHK_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->launches += 1;
+    if (forced_extend(ctx) < 0 && ix.front && ix.fgeom.stride == 2 && ix.fgeom.n_entries && front_fits_l2(ix.fgeom.n_entries)) {
+        SHK_CUDA(ctx, cudaMalloc((void **)&ix.front_plain, ix.fgeom.n_entries * 16));
+        derive_plain_kernel<<<(unsigned)((ix.fgeom.n_entries + 255) / 256), 256, 0, st>>>(ix.front, ix.fgeom.n_entries, ix.front_plain);
+        SHK_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        ix.derived_bytes += ix.fgeom.n_entries * 16;
+        ix.info.plain_front = 1;
+    }
+    SHK_CUDA(ctx, cudaStreamSynchronize(st));
+    ix.info.device_bytes += ix.derived_bytes;
     return SHK_OK;
 }
 

@@ -32,6 +32,9 @@ struct DeviceIndex {
     uint64_t *refr = nullptr;     // reference in the layout of the packed reads (base t at bits 2*(t&31) of word
                                   // (t>>5)+kDerivedPad, codes A0 C1 T2 G3), zero words on both sides
     uint32_t *ebits = nullptr;    // E[t] (shk_device.cuh) at bit t&31 of word (t>>5)+kDerivedPad
+    uint4 *front_plain = nullptr; // slots of every front-table entry without the anchors (16-byte stride): what the
+                                  // text kernel probes when the table is L2-sized (info.plain_front)
+    uint64_t derived_bytes = 0;   // bytes of refr + ebits + front_plain (part of info.device_bytes)
     ExtGeom egeom{};
     shk_index_info info{};
     bool built = false;
@@ -79,6 +82,7 @@ struct ReadKernelArgs {
     const uint64_t *ref2;
     const uint32_t *coarse;
     const uint64_t *refr;       // bulk kernel: see DeviceIndex
+    const uint4 *front_plain;   // non-null: thread-per-read kernels probe this table (16-byte entries), no extension
     const uint32_t *ebits;
     uint64_t ref_total;         // reference bases
     uint32_t coarse_rel;        // fgeom.shift - coarse_shift: coarse index = bucket << rel | offset >> coarse_shift

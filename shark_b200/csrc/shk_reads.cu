@@ -850,20 +850,30 @@ static void launch_typed(const ReadKernelArgs &a0, cudaStream_t st, unsigned til
         return;
     }
     const uint32_t split = std::min(a.pack_first, a.n_reads);
+    // The thread-per-read kernels extend only over a DRAM-sized table; an L2-sized one they probe window by window in
+    // its slots-only copy (info.plain_front), which is faster there.
+    const bool ext = a.estream && !a.front_plain;
     if (split > 0) {  // text part
         a.r0 = 0;
         a.r1 = split;
+        if (a.front_plain) a.front = a.front_plain;
         const unsigned blocks = (split + kReadsPerTile - 1) / kReadsPerTile;
-        if (a.estream) analyze_reads_kernel<HAS_QUAL, MOD, true, false><<<blocks, kFastThreads, 0, st>>>(a);
+        if (ext) analyze_reads_kernel<HAS_QUAL, MOD, true, false><<<blocks, kFastThreads, 0, st>>>(a);
         else analyze_reads_kernel<HAS_QUAL, MOD, false, false><<<blocks, kFastThreads, 0, st>>>(a);
+        a.front = a0.front;
     }
     if (split < a.n_reads) {  // packed part
         a.r0 = split;
         a.r1 = a.n_reads;
         const unsigned blocks = (a.n_reads - split + kReadsPerTile - 1) / kReadsPerTile;
-        if (a.estream && a.refr && bulk_enabled()) launch_bulk_kernel(a, st, blocks);
-        else if (a.estream) analyze_reads_kernel<false, MOD, true, true><<<blocks, kFastThreads, 0, st>>>(a);
-        else analyze_reads_kernel<false, MOD, false, true><<<blocks, kFastThreads, 0, st>>>(a);
+        if (a.estream && a.refr && bulk_enabled()) {
+            launch_bulk_kernel(a, st, blocks);
+        } else {
+            if (a.front_plain) a.front = a.front_plain;
+            if (ext) analyze_reads_kernel<false, MOD, true, true><<<blocks, kFastThreads, 0, st>>>(a);
+            else analyze_reads_kernel<false, MOD, false, true><<<blocks, kFastThreads, 0, st>>>(a);
+            a.front = a0.front;
+        }
     }
     if (ev_ka) cudaEventRecord(ev_ka, st);
     analyze_mid_kernel<HAS_QUAL, MOD, false><<<mid_blocks, kMidWarps * 32, 0, st>>>(a);

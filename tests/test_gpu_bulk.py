@@ -153,3 +153,30 @@ def test_bulk_single_diagonal_reads(monkeypatch):
         assert np.array_equal(ar, ar0) and np.array_equal(ag, ag0)
         assert np.array_equal(keep, (cnt0 > 0).astype(np.uint8))
         assert stats["n_extended"] > 0.8 * stats["n_hits"]
+
+
+def test_auto_mode_small_table(monkeypatch):
+    """Without a forcing flag an index whose front table fits L2 still carries the extension structures: packed reads go
+    to the bulk kernel, text reads to the thread-per-read kernel over the slots-only copy of the table
+    (info.plain_front); both equal the oracle.  A forcing flag keeps the single table of its path."""
+    from shark_b200.engine import Shark
+    monkeypatch.delenv("SHK_BULK", raising=False)
+    rng = np.random.default_rng(99)
+    genes = rnd_genes(rng, 30, 800, 2500)
+    genes[11] = genes[10][:600] + genes[11][600:]
+    bases, rec_off = po.concat_records(genes)
+    texts = stress_reads(rng, [g.upper() for g in genes], 4000, 21)
+    seq, off = to_soa(texts)
+    ref = po.Index(bases, rec_off, 21, 1 << 28)
+    cnt0, ar0, ag0 = ref.analyze(seq, off, 0.5)
+    for extend, want_ext, want_plain in ((None, 1, 1), (True, 1, 0), (False, 0, 0)):
+        with Shark(max_reads_per_chunk=1500, extend=extend, compact=True, k=21, c=0.5, bf_bits=1 << 28) as sh:
+            info = sh.build_index(bases, rec_off)
+            assert (info.extend, info.plain_front) == (want_ext, want_plain), extend
+            for packed in (False, True):
+                keep, ar, ag, stats = sh.analyze(seq, off, None, packed=packed)
+                assert np.array_equal(ar, ar0) and np.array_equal(ag, ag0), (extend, packed)
+                assert np.array_equal(keep, (cnt0 > 0).astype(np.uint8)), (extend, packed)
+                # who extends: the bulk kernel whenever the structures exist, the thread-per-read kernel only when forced
+                extends = (packed and want_ext) or (want_ext and not want_plain)
+                assert (stats["n_extended"] > 0) == bool(extends), (extend, packed, stats["n_extended"])
