@@ -8,8 +8,8 @@ for w in c4 c3 c2; do
   for form in text packed; do
     skip=1; [ $form = packed ] && skip=7
     kern=analyze_reads_kernel
-    # packed reads over the extension structures (c3, c4) run the bulk kernel: its first launches are the packed legs'
-    if [ $form = packed ] && [ $w != c2 ]; then kern=analyze_bulk_kernel; skip=1; fi
+    # packed reads run the bulk kernel: its first launches are the packed legs'
+    if [ $form = packed ]; then kern=analyze_bulk_kernel; skip=1; fi
     ncu --set full --clock-control none --import-source on -k regex:$kern -s $skip -c 1 -f \
         -o gpurun_out/prof_r2_${w}_${form} python bench.py --workloads $w --reads 2097152 --steps 1 --warmup 1 \
         --no-cpu-baseline --no-cli > gpurun_out/ncu_r2_${w}_${form}.log 2>&1
