@@ -288,8 +288,10 @@ __device__ SHK_BULK_SERVE_ATTR void serve_queue(const ReadKernelArgs &a, BulkWar
             if (cur != bucket) anc = ld_front(a.front + (uint64_t)cur * 2u + 1u, pol_front);
             const uint32_t sa = A + kb;
             const uint32_t e = qq.x == sa ? anc.x : (qq.y == sa ? anc.y : (qq.z == sa ? anc.z : anc.w));
-            const uint64_t rk = ref2_window(a.ref2, e, kmask2, pol_last);
-            uint64_t fwd, rcm;
+            // the reference window ending at e, from the same array the match words come from (one array less in L2)
+            const uint64_t rwi = (uint64_t)(e >> 5) + kDerivedPad;
+            uint64_t rk, rk_rc, fwd, rcm;
+            window_kmers(ld_u64_hint(a.refr + rwi - 1, pol_last), ld_u64_hint(a.refr + rwi, pol_last), e & 31u, k, kmask2, rk, rk_rc);
             window_kmers(sh.cprev[ow], sh.ccur[ow], p, k, kmask2, fwd, rcm);
             if (rk == fwd) atomicMin(&sh.cand[ow], ((unsigned long long)p << 33) | e);
             else if (rk == rcm) atomicMin(&sh.cand[ow], ((unsigned long long)p << 33) | (1ULL << 32) | e);
