@@ -459,8 +459,6 @@ analyze_bulk_kernel(const ReadKernelArgs a)
                     }
                     const uint32_t pm = __ballot_sync(kFull, push);
                     if (push) {
-                        // on its way into L2 while it waits in the queue
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.front + (uint64_t)q_bucket * 2u));
                         const uint32_t slot = (fq_head + fq_n + (uint32_t)__popc(pm & ((1u << lane) - 1u))) & (kBulkQueue - 1u);
                         sh.fq_bucket[slot] = q_bucket;
                         sh.fq_key[slot] = q_key;
