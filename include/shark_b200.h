@@ -57,10 +57,12 @@ typedef struct shk_params {
     uint32_t reserved[6];         /* must be zero                                                  */
 } shk_params;
 
-/* shk_params.flags.  Anchor-and-extend: results are identical either way; by default
- * it is switched on when the front table is too large to stay in L2. */
-#define SHK_F_EXTEND_ON 1u  /* always build and use the extension structures                       */
-#define SHK_F_EXTEND_OFF 2u /* never                                                               */
+/* shk_params.flags.  Anchor-and-extend: results are identical on every path.  Default (neither flag):
+ * the extension structures are built; packed reads (shk_reads_submit_packed, the packed part of a split upload) are
+ * classified by the bulk kernel over them, text reads by the thread-per-read kernel - extending when the front table is
+ * too large to stay in L2, window by window over a slots-only copy of it otherwise (shk_index_info.plain_front). */
+#define SHK_F_EXTEND_ON 1u  /* build the structures; the thread-per-read kernel extends whatever the table size */
+#define SHK_F_EXTEND_OFF 2u /* never build them: every read is classified window by window               */
 /* Split upload: the plain path is PCIe-bound at 3-5 x below the kernels' rate, with the host cores idle.
  * With this flag shk_reads_submit sends the first part of a chunk as it is and, WHILE that copy runs,
  * reduces the rest to what the kernels use of a text byte - one validity bit (after the -q masking rule,

@@ -1,9 +1,10 @@
 // Bulk classification of packed reads over the extension structures (K6b).  Replaces the same reference code as
 // analyze_reads_kernel - ReadAnalyzer::operator() (ReadAnalyzer.hpp:39-110) behind FastqSplitter's masking
-// (FastqSplitter.hpp:104-109, already folded into the validity bits of the packed form) - for indexes whose front
-// table is DRAM-sized.  Citations are reference file:line.
+// (FastqSplitter.hpp:104-109, already folded into the validity bits of the packed form).  Every packed read takes this
+// kernel whenever the index carries the extension structures (any table size; SHK_BULK=0 or SHK_F_EXTEND_OFF keep
+// analyze_reads_kernel).  Citations are reference file:line.
 //
-// Why another kernel.  analyze_reads_kernel<EXT> walks every read base by base and hashes every window, although most
+// Why another kernel.  analyze_reads_kernel walks every read base by base and hashes every window, although most
 // windows of a read that follows the reference are known without a hash; in its thread-per-read layout a warp pays for
 // the union of its lanes' paths, so skipping hashes per lane buys nothing (profiles/analyze_r2.md).  Here the two halves
 // of the work are separated and each runs in the layout that suits it:
@@ -18,17 +19,27 @@
 //     (cov += min(k, pos - last) + L - 1, hits += L; the reference's per-window update summed over the run).
 //   * all windows that are valid but not S (WV & ~S: the windows covering a mismatch, the first window of a run,
 //     every window of a read that follows no reference) are LOOKUPS, and the warp shares them evenly: the lookups of a
-//     round form one queue (prefix sum over the lanes' counts), every lane takes an equal slice whoever owns the
+//     pass form one list (prefix sum over the lanes' counts), every lane takes an equal slice whoever owns the
 //     windows, builds the k-mers from the owners' code words in shared memory (no rolling: a window is a funnel shift),
-//     and does hash -> coarse filter -> front table exactly like analyze_reads_kernel.  Hits go back to the owner
-//     through shared memory; a plain hit of a read without a working diagonal is verified against the reference
-//     (ref2) and becomes the read's new diagonal.
-//   * the owner applies hits and runs in window order to the same 4-gene register table and ends the read with the
-//     same code as analyze_reads_kernel (shk_reads.cuh).  Reads it cannot hold (more than 4 genes, a list of more than
-//     2 ids, more than kMaxFastLen bases) go to the warp-per-read kernels as before.
+//     hashes, and tests the coarse filter (the word travels by cp.async while the next item is hashed).  Windows that
+//     pass are queued in shared memory; the queue is served 32 entries at a time, one front-table load per lane.  Hits
+//     go back to the owner through shared memory.
+//   * a read without a working diagonal (the start of a mate, a chimera, an indel) asks for its first window alone
+//     (pass 0).  A plain hit whose anchor names a reference window that IS the read's window (checked against refr,
+//     either strand) gives the diagonal; the word and the one before are matched again, and only what is still
+//     unexplained is looked up (pass 1).  A diagonal found in pass 1 re-matches the word as well, so that the owner
+//     applies the hits it explains as one run.
+//   * the owner applies hits and runs in window order to the 4-gene table (two hot genes in registers, two cold ones
+//     in shared memory) and ends the read with the same code as analyze_reads_kernel (shk_reads.cuh).  Lists of 3 or 4
+//     ids are walked by the owner itself; reads it cannot hold (more than 4 genes, a list of more than 4 ids, a run of
+//     windows over lists of more than 2 ids, more than kMaxFastLen bases) go to the warp-per-read kernels as before.
 //
 // Results are those of the reference by construction: the ids of every valid window are either looked up in the exact
 // front table or copied from the previous window under a condition that implies equality.
+//
+// Shape: 4 warps per CTA (one scan tile), 6 CTAs per SM (79 registers, 32 KB of shared memory per CTA).  The kernel is
+// bound by instruction issue, by L2 / DRAM latency at 24 warps per SM, and by the instruction cache (38 KB of code:
+// nothing in it is unrolled) - the trail of measurements behind each choice is profiles/analyze_r2.md, part 2.
 #include "shk_internal.h"
 #include "shk_reads.cuh"
 #include "shk_scan.cuh"
