@@ -47,6 +47,25 @@ def test_struct_sizes():
     assert ctypes.sizeof(capi.ShardMem) == 24 + 192 + 8 + 16
 
 
+def test_index_info_layout_matches_header(tmp_path):
+    """Field by field: the ctypes view of shk_index_info against the header as gcc lays it out (the last field was
+    `reserved` until round 2 and is `plain_front` now - same offset, same ABI version)."""
+    import subprocess
+    from shark_b200 import capi
+    fields = [f[0] for f in capi.IndexInfo._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "shark_b200.h"\nint main(void) {\n'
+                   '  printf("%zu", sizeof(shk_index_info));\n' +
+                   "".join('  printf(" %%zu", offsetof(shk_index_info, %s));\n' % f for f in fields) +
+                   '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(capi.IndexInfo)
+    assert out[1:] == [getattr(capi.IndexInfo, f).offset for f in fields]
+    assert fields[-1] == "plain_front"
+
+
 def test_no_cpu_fallback(lib_path):
     """Without a device shk_create must fail loudly (SHK_E_CUDA), never compute on the host."""
     import torch
